@@ -1,0 +1,114 @@
+"""Workload definitions (SURVEY.md §8d / BASELINE.md §4): BUGS text + synthetic inputs for configs C1..C5.
+Shared by the tests and bench.py.  Data seed 20261019 as proposed by the survey."""
+import numpy as np
+
+DATA_SEED = 20261019
+
+
+def c1_vignette(nObs=100, K=8):
+    """nimbleAPT/vignettes/nimbleAPT-vignette.Rmd:56-72,129-135 verbatim model; Temps=1:K, ULT=1000."""
+    rng = np.random.default_rng(DATA_SEED)
+    y = rng.standard_normal((nObs, 2)) + 3.0  # simulated from centroids=(-3,-3): abs() -> mean (3,3), cov I
+    code = """{
+    for (ii in 1:nObs) {
+        y[ii,1:2] ~ dmnorm(mean=absCentroids[1:2], cholesky=cholCov[1:2,1:2], prec_param=0)
+    }
+    absCentroids[1:2] <- abs(centroids[1:2])
+    for (ii in 1:2) {
+        centroids[ii] ~ dnorm(0, sd=1E3)
+    }
+    }"""
+    return dict(code=code, constants=dict(nObs=nObs, cholCov=np.eye(2)), data=dict(y=y),
+                inits=dict(centroids=np.array([-3.0, -3.0])),
+                samplers=[dict(target="centroids[1]", type="sampler_RW_tempered", control=dict(temperPriors=True)),
+                          dict(target="centroids[2]", type="sampler_RW_tempered", control=dict(temperPriors=True))],
+                monitors=["centroids"], Temps=np.arange(1, K + 1, dtype=float), ULT=1000.0)
+
+
+def c2_mixture(n=20, K=32, tmax=1000.0):
+    """2-D bimodal posterior through an abs() link; exact posterior is a 2-component Gaussian mixture."""
+    rng = np.random.default_rng(DATA_SEED + 2)
+    y = np.stack([rng.standard_normal(n) + 3.0, rng.standard_normal(n)], axis=1)
+    code = """{
+    for (i in 1:n) {
+        y[i,1] ~ dnorm(abs(theta[1]), sd=1)
+        y[i,2] ~ dnorm(theta[2], sd=1)
+    }
+    for (j in 1:2) {
+        theta[j] ~ dnorm(0, sd=100)
+    }
+    }"""
+    temps = np.exp(np.linspace(0.0, np.log(tmax), K))
+    return dict(code=code, constants=dict(n=n), data=dict(y=y), inits=dict(theta=np.array([3.0, 0.0])),
+                samplers=[dict(target="theta[1]", type="sampler_RW_tempered", control=dict(temperPriors=True)),
+                          dict(target="theta[2]", type="sampler_RW_tempered", control=dict(temperPriors=True))],
+                monitors=["theta"], Temps=temps, ULT=1e6)
+
+
+def logistic(N, p, K, tmax=50.0, seed_off=3, propcov=True):
+    """C3 (N=1e6,p=50,K=16) / C5 (N=1024,p=8,K=64): Bayesian logistic regression, one block sampler."""
+    rng = np.random.default_rng(DATA_SEED + seed_off)
+    X = rng.standard_normal((N, p)); X[:, 0] = 1.0
+    beta_true = rng.standard_normal(p) * 0.25
+    eta = X @ beta_true
+    y = (rng.random(N) < 1.0 / (1.0 + np.exp(-eta))).astype(float)
+    code = """{
+    for (i in 1:N) {
+        y[i] ~ dbinom(prob=p[i], size=1)
+        logit(p[i]) <- inprod(beta[1:P], X[i,1:P])
+    }
+    for (j in 1:P) {
+        beta[j] ~ dnorm(0, sd=10)
+    }
+    }"""
+    ctl = dict(temperPriors=True)
+    if propcov:
+        pr = 1.0 / (1.0 + np.exp(-eta))
+        W = pr * (1 - pr)
+        H = (X * W[:, None]).T @ X + np.eye(p) / 100.0
+        cov = np.linalg.inv(H) * (2.38 ** 2 / p)
+        ctl["propCov"] = (cov + cov.T) / 2
+    temps = np.exp(np.linspace(0.0, np.log(tmax), K))
+    return dict(code=code, constants=dict(N=N, P=p, X=X), data=dict(y=y), inits=dict(beta=np.zeros(p)),
+                samplers=[dict(target="beta[1:%d]" % p, type="sampler_RW_block_tempered", control=ctl)],
+                monitors=["beta"], Temps=temps, ULT=1e6)
+
+
+def c3_logistic(N=1000000, p=50, K=16):
+    return logistic(N, p, K, seed_off=3)
+
+
+def c5_small_logistic(N=1024, p=8, K=64):
+    return logistic(N, p, K, seed_off=5)
+
+
+def c4_glmm(G=1000, per=100, K=24, tmax=30.0):
+    """Hierarchical Poisson GLMM, mixed scalar / block / log-scale samplers."""
+    rng = np.random.default_rng(DATA_SEED + 4)
+    N = G * per
+    g = np.repeat(np.arange(1, G + 1), per).astype(float)
+    x = rng.standard_normal(N)
+    u_true = rng.standard_normal(G) * 0.5
+    lam = np.exp(0.5 + 0.3 * x + u_true[g.astype(int) - 1])
+    y = rng.poisson(lam).astype(float)
+    code = """{
+    for (i in 1:N) {
+        y[i] ~ dpois(lam[i])
+        log(lam[i]) <- b[1] + b[2]*x[i] + u[g[i]]
+    }
+    for (k in 1:G) {
+        u[k] ~ dnorm(0, sd=sigma)
+    }
+    sigma ~ dunif(0, 5)
+    for (j in 1:2) {
+        b[j] ~ dnorm(0, sd=10)
+    }
+    }"""
+    samplers = [dict(target="u[%d]" % (k + 1), type="sampler_RW_tempered", control=dict(temperPriors=True))
+                for k in range(G)]
+    samplers.append(dict(target="b[1:2]", type="sampler_RW_block_tempered", control=dict(temperPriors=True)))
+    samplers.append(dict(target="sigma", type="sampler_RW_tempered", control=dict(temperPriors=True, log=True)))
+    temps = np.exp(np.linspace(0.0, np.log(tmax), K))
+    return dict(code=code, constants=dict(N=N, G=G, x=x, g=g), data=dict(y=y),
+                inits=dict(u=np.zeros(G), sigma=np.array(1.0), b=np.zeros(2)), samplers=samplers,
+                monitors=["b", "sigma"], Temps=temps, ULT=1e6)
