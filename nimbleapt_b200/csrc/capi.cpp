@@ -1,0 +1,509 @@
+// capi.cpp — the public C ABI (include/aptb200.h) on top of the front end and the lowered-model modules.
+#include <dlfcn.h>
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include "engine/apt_module_abi.h"
+#include "front.h"
+
+using namespace aptf;
+
+static thread_local std::string g_err;
+
+struct apt_model {
+    ModelSpec spec;
+};
+
+struct ModFns {
+    int (*abi_version)(void);
+    int (*create)(const aptmod_init*, void**, char*, int);
+    void (*destroy)(void*);
+    int (*run)(void*, const aptmod_run_args*, char*, int);
+    int (*get)(void*, int, int, double*, int64_t, int64_t*, char*, int);
+    long long (*info)(void*, int);
+    int (*logprob)(void*, const double*, int, double*, char*, int);
+    int (*set_model_theta)(void*, const double*, int, char*, int);
+    int (*set_array)(void*, int, const double*, int64_t, char*, int);
+    void (*timing_get)(void*, aptmod_timing*);
+    int (*device_ptr)(void*, int, void**, int64_t*, void**);
+};
+
+struct apt_engine {
+    void* dl = nullptr;
+    void* mod = nullptr;
+    ModFns fn{};
+    Lowered low;
+    int n_ladders = 1, device = 0;
+    // NCCL (lazy)
+    void* nccl_dl = nullptr;
+    void* comm = nullptr;
+    int world = 1, rank = 0;
+};
+
+#define API_BEGIN try {
+#define API_END                          \
+    return 0;                            \
+    }                                    \
+    catch (const std::exception& e) {    \
+        g_err = e.what();                \
+        return 1;                        \
+    }                                    \
+    catch (...) {                        \
+        g_err = "unknown error";         \
+        return 1;                        \
+    }
+
+extern "C" {
+
+const char* apt_last_error(void) { return g_err.c_str(); }
+const char* apt_version(void) { return "aptb200 0.1 (sm_100a)"; }
+
+void apt_sampler_control_default(apt_sampler_control* c) {
+    c->log = 0; c->reflective = 0; c->adaptive = 1; c->adaptScaleOnly = 0; c->adaptInterval = 200;
+    c->adaptFactorExponent = 0.8; c->scale = 1.0; c->temperPriors = -1; c->propCov = nullptr; c->propCov_dim = 0;
+}
+void apt_build_opts_default(apt_build_opts* o) {
+    memset(o, 0, sizeof *o);
+    o->monitorTmax = 1; o->ULT = 1e6; o->n_ladders = 1; o->ladder0 = 0; o->seed = 11; o->device = 0;
+    o->record_decisions = 0; o->fuse_links = 1;
+}
+void apt_run_args_default(apt_run_args* a) {
+    memset(a, 0, sizeof *a);
+    a->reset = 1; a->adaptTemps = 1; a->tuneTemper1 = 10; a->tuneTemper2 = 1; a->progressBar = 1; a->thin = -1; a->thin2 = -1;
+}
+
+int apt_model_create(const char* bugs_code, apt_model** out) {
+    API_BEGIN
+    if (!bugs_code || !out) throw Error("null argument");
+    auto* m = new apt_model();
+    try {
+        m->spec.code = bugs_code;
+        m->spec.decls = parse_bugs(bugs_code);
+        if (m->spec.decls.empty()) throw Error("the model has no declarations");
+    } catch (...) {
+        delete m;
+        throw;
+    }
+    *out = m;
+    API_END
+}
+void apt_model_free(apt_model* m) { delete m; }
+
+int apt_model_set_array(apt_model* m, const char* name, int role, const double* values, const int64_t* dims, int ndim) {
+    API_BEGIN
+    if (!m || !name || (!values && ndim >= 0)) throw Error("null argument");
+    Array a;
+    a.name = name; a.role = role;
+    int64_t n = 1;
+    for (int i = 0; i < ndim; i++) {
+        if (dims[i] < 1) throw Error("non-positive dimension");
+        a.dims.push_back(dims[i]);
+        n *= dims[i];
+    }
+    if (ndim == 1 && n == 1) a.dims.clear();  // length-1 vector == scalar
+    a.v.assign(values, values + n);
+    auto& dst = role == APT_ROLE_CONSTANT ? m->spec.constants : role == APT_ROLE_DATA ? m->spec.data : m->spec.inits;
+    if (role < 0 || role > 2) throw Error("unknown role");
+    dst[name] = std::move(a);
+    API_END
+}
+
+int apt_model_add_sampler(apt_model* m, const char* target, const char* type, const apt_sampler_control* control) {
+    API_BEGIN
+    if (!m || !target || !type) throw Error("null argument");
+    SamplerConf sc;
+    sc.target = target; sc.type = type;
+    if (control) sc.ctl = *control; else apt_sampler_control_default(&sc.ctl);
+    if (sc.ctl.propCov) {
+        if (sc.ctl.propCov_dim < 1) throw Error("propCov must be a matrix\n");  // APT:814
+        sc.propCov.assign(sc.ctl.propCov, sc.ctl.propCov + (size_t)sc.ctl.propCov_dim * sc.ctl.propCov_dim);
+        for (double v : sc.propCov)
+            if (!std::isfinite(v)) throw Error("propCov matrix must be numeric\n");  // APT:815
+    }
+    sc.ctl.propCov = nullptr;
+    m->spec.samplers.push_back(std::move(sc));
+    API_END
+}
+int apt_model_remove_samplers(apt_model* m) {
+    API_BEGIN
+    m->spec.samplers.clear();
+    API_END
+}
+int apt_model_set_monitors(apt_model* m, int which, const char* const* names, int n) {
+    API_BEGIN
+    auto& dst = which == 2 ? m->spec.monitors2 : m->spec.monitors;
+    dst.clear();
+    for (int i = 0; i < n; i++) dst.push_back(names[i]);
+    API_END
+}
+int apt_model_set_thin(apt_model* m, int thin, int thin2) {
+    API_BEGIN
+    if (thin < 1 || thin2 < 1) throw Error("thin must be >= 1");
+    m->spec.thin = thin; m->spec.thin2 = thin2;
+    API_END
+}
+
+static ModelSpec with_default_monitors(const ModelSpec& s) {
+    ModelSpec spec = s;
+    if (spec.monitors.empty()) {  // configureMCMC default: monitor the top-level stochastic nodes; here: all sampled nodes
+        std::vector<std::string> seen;
+        for (auto& d : spec.decls)
+            if (d.stoch && !spec.data.count(d.lhs->name)) {
+                bool dup = false;
+                for (auto& x : seen) dup |= (x == d.lhs->name);
+                if (!dup) seen.push_back(d.lhs->name);
+            }
+        spec.monitors = seen;
+    }
+    return spec;
+}
+
+static void copy_out(const std::string& s, char* buf, int64_t buflen, int64_t* needed) {
+    if (needed) *needed = (int64_t)s.size() + 1;
+    if (buf && buflen > 0) {
+        size_t n = std::min<size_t>(s.size(), (size_t)buflen - 1);
+        memcpy(buf, s.data(), n);
+        buf[n] = 0;
+    }
+}
+
+int apt_model_names(apt_model* m, int which, char* buf, int64_t buflen) {
+    API_BEGIN
+    apt_build_opts o;
+    apt_build_opts_default(&o);
+    Lowered L = lower_model(with_default_monitors(m->spec), 2, o);
+    const auto& v = which == 0 ? L.param_names : which == 2 ? L.mon2_names : L.mon_names;
+    std::string s;
+    for (size_t i = 0; i < v.size(); i++) s += (i ? "\n" : "") + v[i];
+    if ((int64_t)s.size() + 1 > buflen) throw Error("buffer too small");
+    copy_out(s, buf, buflen, nullptr);
+    API_END
+}
+
+int apt_model_lower(apt_model* m, int n_temps, const apt_build_opts* opts, char* buf, int64_t buflen, int64_t* needed) {
+    API_BEGIN
+    apt_build_opts o;
+    if (opts) o = *opts; else apt_build_opts_default(&o);
+    Lowered L = lower_model(with_default_monitors(m->spec), n_temps, o);
+    copy_out(L.source, buf, buflen, needed);
+    API_END
+}
+
+int apt_build(apt_model* m, const double* temps, int n_temps, const apt_build_opts* opts, apt_engine** out) {
+    API_BEGIN
+    if (!m || !temps || !out) throw Error("null argument");
+    apt_build_opts o;
+    if (opts) o = *opts; else apt_build_opts_default(&o);
+    for (int i = 0; i < n_temps; i++)
+        if (!(temps[i] > 0) || !std::isfinite(temps[i])) throw Error("temperatures must be positive and finite");
+    auto* e = new apt_engine();
+    // the lowered description borrows the arrays of this copy until they have been uploaded
+    const ModelSpec spec = with_default_monitors(m->spec);
+    try {
+        e->low = lower_model(spec, n_temps, o);
+        if (o.verbose) {  // message(paste("Initial temperatures:", ...))  APT:279
+            std::vector<double> t(temps, temps + n_temps);
+            std::sort(t.begin(), t.end());
+            fprintf(stderr, "Initial temperatures:");
+            for (double x : t) fprintf(stderr, " %g", x);
+            fprintf(stderr, "\n");
+        }
+        std::string so = jit_compile(e->low.source, o.verbose != 0);
+        // Modules stay loaded for the life of the process: unloading a library that embeds the CUDA runtime and
+        // registered kernels is not safe, and a second engine for the same model reuses the loaded code.
+        static std::map<std::string, void*> loaded;
+        auto it = loaded.find(so);
+        if (it != loaded.end()) e->dl = it->second;
+        else {
+            e->dl = dlopen(so.c_str(), RTLD_NOW | RTLD_LOCAL);
+            if (!e->dl) throw Error(std::string("cannot load the compiled module: ") + dlerror());
+            loaded[so] = e->dl;
+        }
+        auto sym = [&](const char* n) {
+            void* p = dlsym(e->dl, n);
+            if (!p) throw Error(std::string("compiled module lacks symbol ") + n);
+            return p;
+        };
+        e->fn.abi_version = (int (*)(void))sym("aptmod_abi_version");
+        if (e->fn.abi_version() != APTMOD_ABI_VERSION) throw Error("stale module in the JIT cache (ABI version mismatch)");
+        e->fn.create = (decltype(e->fn.create))sym("aptmod_create");
+        e->fn.destroy = (decltype(e->fn.destroy))sym("aptmod_destroy");
+        e->fn.run = (decltype(e->fn.run))sym("aptmod_run");
+        e->fn.get = (decltype(e->fn.get))sym("aptmod_get");
+        e->fn.info = (decltype(e->fn.info))sym("aptmod_info");
+        e->fn.logprob = (decltype(e->fn.logprob))sym("aptmod_logprob");
+        e->fn.set_model_theta = (decltype(e->fn.set_model_theta))sym("aptmod_set_model_theta");
+        e->fn.set_array = (decltype(e->fn.set_array))sym("aptmod_set_array");
+        e->fn.timing_get = (decltype(e->fn.timing_get))sym("aptmod_timing_get");
+        e->fn.device_ptr = (decltype(e->fn.device_ptr))dlsym(e->dl, "aptmod_device_ptr");
+        aptmod_init in{};
+        in.n_ladders = o.n_ladders; in.ladder0 = o.ladder0; in.seed = o.seed; in.device = o.device;
+        in.temps = temps; in.n_temps = n_temps; in.ULT = o.ULT; in.monitor_tmax = o.monitorTmax;
+        std::vector<const double*> ap;
+        std::vector<int64_t> al;
+        for (auto* a : e->low.arrays) { ap.push_back(a->v.data()); al.push_back(a->size()); }
+        std::vector<const int*> ip;
+        std::vector<int64_t> il;
+        for (auto& v : e->low.iarrays) { ip.push_back(v.data()); il.push_back((int64_t)v.size()); }
+        in.n_arrays = (int)ap.size(); in.arrays = ap.data(); in.array_len = al.data();
+        in.n_iarrays = (int)ip.size(); in.iarrays = ip.data(); in.iarray_len = il.data();
+        in.theta0 = e->low.theta0.data();
+        in.record = o.record_decisions;
+        in.thin_conf = m->spec.thin; in.thin2_conf = m->spec.thin2;
+        char err[2048] = {0};
+        if (e->fn.create(&in, &e->mod, err, sizeof err)) throw Error(err);
+        e->n_ladders = o.n_ladders; e->device = o.device;
+        // arrays were copied to the device: drop the borrowed pointers
+        e->low.arrays.clear();
+    } catch (...) {
+        if (e->mod && e->fn.destroy) e->fn.destroy(e->mod);
+        delete e;
+        throw;
+    }
+    *out = e;
+    API_END
+}
+
+int apt_comm_finalize(apt_engine* e);
+
+void apt_free(apt_engine* e) {
+    if (!e) return;
+    apt_comm_finalize(e);
+    if (e->mod) e->fn.destroy(e->mod);
+    delete e;
+}
+
+int apt_run(apt_engine* e, const apt_run_args* args) {
+    API_BEGIN
+    if (!e || !args) throw Error("null argument");
+    if (args->simulateAll) throw Error("simulateAll = TRUE is not supported by the device engine (set initial values with apt_set_inits)");
+    aptmod_run_args ra{};
+    ra.niter = args->niter; ra.reset = args->reset; ra.resetMV = args->resetMV; ra.resetTempering = args->resetTempering;
+    ra.adaptTemps = args->adaptTemps; ra.tuneTemper1 = args->tuneTemper1; ra.tuneTemper2 = args->tuneTemper2;
+    ra.thin = args->thin; ra.thin2 = args->thin2;
+    ra.tabZ = args->inject_normals; ra.tabU = args->inject_accept_u; ra.tabS = args->inject_swap_u;
+    ra.should_abort = args->should_abort; ra.abort_arg = args->abort_arg; ra.iters_per_launch = args->iters_per_launch;
+    char err[2048] = {0};
+    if (e->fn.run(e->mod, &ra, err, sizeof err)) throw Error(err);
+    if (args->printTemps) {  // nimPrint(iter, " ", totalIters-1, " ", size_mvSamples, " ", size_mvSamples2, asRow(Temps))  APT:524
+        std::vector<double> t((size_t)e->low.K);
+        int64_t n = 0;
+        if (!e->fn.get(e->mod, APTMOD_TEMPS, 0, t.data(), (int64_t)t.size(), &n, err, sizeof err)) {
+            printf("%lld %lld %lld %lld", (long long)args->niter, e->fn.info(e->mod, APTMOD_INFO_TOTALITERS) - 1,
+                   e->fn.info(e->mod, APTMOD_INFO_ROWS), e->fn.info(e->mod, APTMOD_INFO_ROWS2));
+            for (double x : t) printf(" %g", x);
+            printf("\n");
+        }
+    }
+    API_END
+}
+
+int64_t apt_info(apt_engine* e, int what) {
+    if (!e) return -1;
+    return e->fn.info(e->mod, what);
+}
+
+int apt_get(apt_engine* e, int what, int ladder, double* out, int64_t capacity, int64_t* n_written) {
+    API_BEGIN
+    if (!e || !out) throw Error("null argument");
+    char err[2048] = {0};
+    int64_t n = 0;
+    if (e->fn.get(e->mod, what, ladder, out, capacity, &n, err, sizeof err)) throw Error(err);
+    if (n_written) *n_written = n;
+    API_END
+}
+
+int apt_get_timing(apt_engine* e, apt_timing* t) {
+    API_BEGIN
+    aptmod_timing mt{};
+    e->fn.timing_get(e->mod, &mt);
+    t->kernel_ms = mt.kernel_ms; t->main_kernel_ms = mt.main_kernel_ms; t->launches = mt.launches; t->main_launches = mt.main_launches;
+    API_END
+}
+
+int apt_logprob(apt_engine* e, const double* theta, int n, double* out_total, double* out_groups) {
+    API_BEGIN
+    if (!e || !theta || !out_total) throw Error("null argument");
+    const int ND = e->low.ND;
+    std::vector<double> g((size_t)n * ND);
+    char err[2048] = {0};
+    if (e->fn.logprob(e->mod, theta, n, g.data(), err, sizeof err)) throw Error(err);
+    for (int i = 0; i < n; i++) {
+        double s = 0;
+        for (int d = 0; d < ND; d++) s += g[(size_t)i * ND + d];
+        out_total[i] = s;
+    }
+    if (out_groups) memcpy(out_groups, g.data(), g.size() * sizeof(double));
+    API_END
+}
+
+int apt_set_inits(apt_engine* e, const double* theta, int ladder) {
+    API_BEGIN
+    char err[2048] = {0};
+    if (e->fn.set_model_theta(e->mod, theta, ladder, err, sizeof err)) throw Error(err);
+    API_END
+}
+
+int apt_set_array(apt_engine* e, const char* name, const double* values, int64_t n) {
+    API_BEGIN
+    int idx = -1;
+    for (size_t i = 0; i < e->low.array_names.size(); i++)
+        if (e->low.array_names[i] == name) idx = (int)i;
+    if (idx < 0) throw Error(std::string("array '") + name + "' is not resident on the device (unknown, unused, or folded into the code as a small constant)");
+    char err[2048] = {0};
+    if (e->fn.set_array(e->mod, idx, values, n, err, sizeof err)) throw Error(err);
+    API_END
+}
+
+// ------------------------------------------------------------------------------------------------ NCCL
+// Loaded lazily so that the library itself has no link-time dependency on NCCL or CUDA (it must load on a
+// host without a GPU).  Only gathers of traces and sums of pooled statistics cross NVLink.
+typedef struct { char internal[128]; } nccl_uid;
+struct NcclFns {
+    int (*GetUniqueId)(nccl_uid*);
+    int (*CommInitRank)(void**, int, nccl_uid, int);
+    int (*CommDestroy)(void*);
+    int (*AllGather)(const void*, void*, size_t, int, void*, void*);
+    int (*AllReduce)(const void*, void*, size_t, int, int, void*, void*);
+    const char* (*GetErrorString)(int);
+};
+static NcclFns g_nccl{};
+static void* g_nccl_dl = nullptr;
+static void* g_cudart_dl = nullptr;
+struct RtFns {
+    int (*SetDevice)(int);
+    int (*Malloc)(void**, size_t);
+    int (*Free)(void*);
+    int (*Memcpy)(void*, const void*, size_t, int);
+    int (*DeviceSynchronize)(void);
+    int (*StreamSynchronize)(void*);
+};
+static RtFns g_rt{};
+
+static void load_nccl() {
+    if (g_nccl_dl) return;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (auto n : names) {
+        g_nccl_dl = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (g_nccl_dl) break;
+    }
+    if (!g_nccl_dl) throw Error(std::string("cannot load NCCL: ") + dlerror());
+    auto s = [&](const char* n) {
+        void* p = dlsym(g_nccl_dl, n);
+        if (!p) throw Error(std::string("NCCL lacks ") + n);
+        return p;
+    };
+    g_nccl.GetUniqueId = (decltype(g_nccl.GetUniqueId))s("ncclGetUniqueId");
+    g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))s("ncclCommInitRank");
+    g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))s("ncclCommDestroy");
+    g_nccl.AllGather = (decltype(g_nccl.AllGather))s("ncclAllGather");
+    g_nccl.AllReduce = (decltype(g_nccl.AllReduce))s("ncclAllReduce");
+    g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))s("ncclGetErrorString");
+    const char* rts[] = {"libcudart.so.12", "libcudart.so"};
+    for (auto n : rts) {
+        g_cudart_dl = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (g_cudart_dl) break;
+    }
+    if (!g_cudart_dl) throw Error(std::string("cannot load libcudart: ") + dlerror());
+    auto r = [&](const char* n) {
+        void* p = dlsym(g_cudart_dl, n);
+        if (!p) throw Error(std::string("libcudart lacks ") + n);
+        return p;
+    };
+    g_rt.SetDevice = (decltype(g_rt.SetDevice))r("cudaSetDevice");
+    g_rt.Malloc = (decltype(g_rt.Malloc))r("cudaMalloc");
+    g_rt.Free = (decltype(g_rt.Free))r("cudaFree");
+    g_rt.Memcpy = (decltype(g_rt.Memcpy))r("cudaMemcpy");
+    g_rt.DeviceSynchronize = (decltype(g_rt.DeviceSynchronize))r("cudaDeviceSynchronize");
+    g_rt.StreamSynchronize = (decltype(g_rt.StreamSynchronize))r("cudaStreamSynchronize");
+}
+#define NCCL_OK(x)                                                                             \
+    do {                                                                                       \
+        int r_ = (x);                                                                          \
+        if (r_ != 0) throw Error(std::string("NCCL: ") + g_nccl.GetErrorString(r_) + " in " #x); \
+    } while (0)
+#define RT_OK(x)                                                          \
+    do {                                                                  \
+        int r_ = (x);                                                     \
+        if (r_ != 0) throw Error("CUDA runtime error " + std::to_string(r_) + " in " #x); \
+    } while (0)
+
+int apt_comm_unique_id(unsigned char id_out[128]) {
+    API_BEGIN
+    load_nccl();
+    nccl_uid id;
+    NCCL_OK(g_nccl.GetUniqueId(&id));
+    memcpy(id_out, &id, 128);
+    API_END
+}
+
+int apt_comm_init(apt_engine* e, int world_size, int rank, const unsigned char unique_id[128]) {
+    API_BEGIN
+    load_nccl();
+    if (e->comm) throw Error("communicator already initialised");
+    nccl_uid id;
+    memcpy(&id, unique_id, 128);
+    RT_OK(g_rt.SetDevice(e->device));
+    NCCL_OK(g_nccl.CommInitRank(&e->comm, world_size, id, rank));
+    e->world = world_size; e->rank = rank;
+    API_END
+}
+
+// NCCL type/op codes: ncclFloat64 = 8, ncclSum = 0
+int apt_comm_allgather_samples(apt_engine* e, int what, double* out, int64_t capacity, int64_t* n_written) {
+    API_BEGIN
+    if (!e->comm) throw Error("apt_comm_init has not been called");
+    RT_OK(g_rt.SetDevice(e->device));
+    // stage through the getter (device -> host) is avoided: gather straight from the device-resident trace
+    if (!e->fn.device_ptr) throw Error("module lacks aptmod_device_ptr");
+    void* dptr = nullptr; int64_t n_local = 0; void* stream = nullptr;
+    if (e->fn.device_ptr(e->mod, what, &dptr, &n_local, &stream)) throw Error("trace not available on the device");
+    const int64_t total = n_local * e->world;
+    if (total > capacity) throw Error("output buffer too small");
+    void* dall = nullptr;
+    RT_OK(g_rt.Malloc(&dall, (size_t)total * 8));
+    try {
+        NCCL_OK(g_nccl.AllGather(dptr, dall, (size_t)n_local, 8 /* ncclFloat64 */, e->comm, stream));
+        RT_OK(g_rt.StreamSynchronize(stream));
+        RT_OK(g_rt.Memcpy(out, dall, (size_t)total * 8, 2 /* D2H */));
+    } catch (...) {
+        g_rt.Free(dall);
+        throw;
+    }
+    g_rt.Free(dall);
+    if (n_written) *n_written = total;
+    API_END
+}
+
+int apt_comm_allreduce_sum(apt_engine* e, double* inout, int64_t n) {
+    API_BEGIN
+    if (!e->comm) throw Error("apt_comm_init has not been called");
+    RT_OK(g_rt.SetDevice(e->device));
+    void* d = nullptr;
+    RT_OK(g_rt.Malloc(&d, (size_t)n * 8));
+    try {
+        RT_OK(g_rt.Memcpy(d, inout, (size_t)n * 8, 1 /* H2D */));
+        NCCL_OK(g_nccl.AllReduce(d, d, (size_t)n, 8 /* ncclFloat64 */, 0 /* ncclSum */, e->comm, nullptr));
+        RT_OK(g_rt.DeviceSynchronize());
+        RT_OK(g_rt.Memcpy(inout, d, (size_t)n * 8, 2));
+    } catch (...) {
+        g_rt.Free(d);
+        throw;
+    }
+    g_rt.Free(d);
+    API_END
+}
+
+int apt_comm_finalize(apt_engine* e) {
+    API_BEGIN
+    if (e && e->comm) {
+        g_nccl.CommDestroy(e->comm);
+        e->comm = nullptr;
+    }
+    API_END
+}
+
+}  // extern "C"

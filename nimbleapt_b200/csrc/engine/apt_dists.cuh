@@ -1,0 +1,261 @@
+// apt_dists.cuh — device log-densities for the lowered BUGS subset (sm_100a, fp64).
+//
+// These stand in for what the reference reaches through nimble's calculateDiff()/calculate()
+// (call sites /root/reference/nimbleAPT/R/APT_functions.R:711,715,825-829): nimble evaluates each
+// stochastic node with R's Rmath d*(…, log=TRUE).  The algorithms below follow the published Rmath
+// algorithms (Loader's saddle-point stirlerr/bd0 for dbinom/dpois, dgamma/dbeta built on them, dnorm4,
+// dunif) so that logProb agrees with the reference path to ~1e-14 relative; they are written for the GPU
+// (branch-light, no error signalling: invalid parameters yield NaN exactly as Rmath's ML_ERR_return_NAN does,
+// which the samplers then reject, nimble `decide`: NaN -> FALSE).
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include "apt_sferr_table.cuh"
+
+namespace apt {
+
+#define APT_LN_SQRT_2PI 0.918938533204672741780329736406
+#define APT_LN_2PI 1.837877066409345483560659472811
+#define APT_TWO_PI 6.283185307179586476925286766559
+#define APT_DBL_MIN 2.2250738585072014e-308
+#define APT_NEG_INF (-CUDART_INF)
+#ifndef CUDART_INF
+#define CUDART_INF __longlong_as_double(0x7ff0000000000000LL)
+#endif
+#ifndef CUDART_NAN
+#define CUDART_NAN __longlong_as_double(0xfff8000000000000LL)
+#endif
+
+__device__ __forceinline__ double stirlerr(double n) {
+    const double S0 = 1.0 / 12.0, S1 = 1.0 / 360.0, S2 = 1.0 / 1260.0, S3 = 1.0 / 1680.0, S4 = 1.0 / 1188.0;
+    if (n <= 15.0) {
+        double nn = n + n;
+        if (nn == (double)(int)nn) return APT_SFERR_HALVES_DEV[(int)nn];
+        return lgamma(n + 1.0) - (n + 0.5) * log(n) + n - APT_LN_SQRT_2PI;
+    }
+    double nn = n * n;
+    if (n > 500) return (S0 - S1 / nn) / n;
+    if (n > 80) return (S0 - (S1 - S2 / nn) / nn) / n;
+    if (n > 35) return (S0 - (S1 - (S2 - S3 / nn) / nn) / nn) / n;
+    return (S0 - (S1 - (S2 - (S3 - S4 / nn) / nn) / nn) / nn) / n;
+}
+
+__device__ __forceinline__ double bd0(double x, double np) {
+    if (!isfinite(x) || !isfinite(np) || np == 0.0) return CUDART_NAN;
+    if (fabs(x - np) < 0.1 * (x + np)) {
+        double v = (x - np) / (x + np);
+        double s = (x - np) * v;
+        if (fabs(s) < APT_DBL_MIN) return s;
+        double ej = 2 * x * v;
+        v = v * v;
+        for (int j = 1; j < 1000; j++) {
+            ej *= v;
+            double s1 = s + ej / ((j << 1) + 1);
+            if (s1 == s) return s1;
+            s = s1;
+        }
+    }
+    return x * log(x / np) + np - x;
+}
+
+__device__ __forceinline__ double dpois_raw_log(double x, double lambda) {
+    if (lambda == 0) return (x == 0) ? 0.0 : APT_NEG_INF;
+    if (!isfinite(lambda)) return APT_NEG_INF;
+    if (x < 0) return APT_NEG_INF;
+    if (x <= lambda * APT_DBL_MIN) return -lambda;
+    if (lambda < x * APT_DBL_MIN) {
+        if (!isfinite(x)) return APT_NEG_INF;
+        return -lambda + x * log(lambda) - lgamma(x + 1);
+    }
+    return -0.5 * log(APT_TWO_PI * x) + (-stirlerr(x) - bd0(x, lambda));
+}
+
+__device__ __forceinline__ double dbinom_raw_log(double x, double n, double p, double q) {
+    if (p == 0) return (x == 0) ? 0.0 : APT_NEG_INF;
+    if (q == 0) return (x == n) ? 0.0 : APT_NEG_INF;
+    if (x == 0) {
+        if (n == 0) return 0.0;
+        return (p < 0.1) ? -bd0(n, n * q) - n * p : n * log(q);
+    }
+    if (x == n) return (q < 0.1) ? -bd0(n, n * p) - n * q : n * log(p);
+    if (x < 0 || x > n) return APT_NEG_INF;
+    double lc = stirlerr(n) - stirlerr(x) - stirlerr(n - x) - bd0(x, n * p) - bd0(n - x, n * q);
+    double lf = APT_LN_2PI + log(x) + log1p(-x / n);
+    return lc - 0.5 * lf;
+}
+
+__device__ __forceinline__ bool nonint(double x) { return fabs(x - nearbyint(x)) > 1e-7 * fmax(1.0, fabs(x)); }
+
+__device__ __forceinline__ double dnorm_log(double x, double mu, double sigma) {
+    if (isnan(x) || isnan(mu) || isnan(sigma)) return x + mu + sigma;
+    if (!isfinite(sigma)) return APT_NEG_INF;
+    if (!isfinite(x) && mu == x) return CUDART_NAN;
+    if (sigma <= 0) {
+        if (sigma < 0) return CUDART_NAN;
+        return (x == mu) ? CUDART_INF : APT_NEG_INF;
+    }
+    x = (x - mu) / sigma;
+    if (!isfinite(x)) return APT_NEG_INF;
+    x = fabs(x);
+    if (x >= 2.6815615859885194e154) return APT_NEG_INF;  // 2*sqrt(DBL_MAX)
+    return -(APT_LN_SQRT_2PI + 0.5 * x * x + log(sigma));
+}
+
+__device__ __forceinline__ double dunif_log(double x, double a, double b) {
+    if (isnan(x) || isnan(a) || isnan(b)) return x + a + b;
+    if (b <= a) return CUDART_NAN;
+    if (a <= x && x <= b) return -log(b - a);
+    return APT_NEG_INF;
+}
+
+__device__ __forceinline__ double dgamma_log(double x, double shape, double scale) {
+    if (isnan(x) || isnan(shape) || isnan(scale)) return x + shape + scale;
+    if (shape < 0 || scale <= 0) return CUDART_NAN;
+    if (x < 0) return APT_NEG_INF;
+    if (shape == 0) return (x == 0) ? CUDART_INF : APT_NEG_INF;
+    if (x == 0) {
+        if (shape < 1) return CUDART_INF;
+        if (shape > 1) return APT_NEG_INF;
+        return -log(scale);
+    }
+    if (shape < 1) {
+        double pr = dpois_raw_log(shape, x / scale);
+        return pr + (isfinite(shape / x) ? log(shape / x) : log(shape) - log(x));
+    }
+    return dpois_raw_log(shape - 1, x / scale) - log(scale);
+}
+
+__device__ __forceinline__ double lgammacor_series(double x) {
+    double x2 = x * x;
+    return (1.0 / 12.0 - (1.0 / 360.0 - (1.0 / 1260.0 - (1.0 / 1680.0 - (1.0 / 1188.0) / x2) / x2) / x2) / x2) / x;
+}
+
+__device__ __forceinline__ double lbeta_fn(double a, double b) {
+    double p = fmin(a, b), q = fmax(a, b);
+    if (p < 0) return CUDART_NAN;
+    if (p == 0) return CUDART_INF;
+    if (!isfinite(q)) return APT_NEG_INF;
+    if (p >= 10) {
+        double corr = lgammacor_series(p) + lgammacor_series(q) - lgammacor_series(p + q);
+        return log(q) * -0.5 + APT_LN_SQRT_2PI + corr + (p - 0.5) * log(p / (p + q)) + q * log1p(-p / (p + q));
+    } else if (q >= 10) {
+        double corr = lgammacor_series(q) - lgammacor_series(p + q);
+        return lgamma(p) + corr + p - p * log(p + q) + (q - 0.5) * log1p(-p / (p + q));
+    }
+    return lgamma(p) + lgamma(q) - lgamma(p + q);
+}
+
+__device__ __forceinline__ double dbeta_log(double x, double a, double b) {
+    if (isnan(x) || isnan(a) || isnan(b)) return x + a + b;
+    if (a < 0 || b < 0) return CUDART_NAN;
+    if (x < 0 || x > 1) return APT_NEG_INF;
+    if (a == 0 || b == 0 || !isfinite(a) || !isfinite(b)) {
+        if (a == 0 && b == 0) return (x == 0 || x == 1) ? CUDART_INF : APT_NEG_INF;
+        if (a == 0 || a / b == 0) return (x == 0) ? CUDART_INF : APT_NEG_INF;
+        if (b == 0 || b / a == 0) return (x == 1) ? CUDART_INF : APT_NEG_INF;
+        return (x == 0.5) ? CUDART_INF : APT_NEG_INF;
+    }
+    if (x == 0) {
+        if (a > 1) return APT_NEG_INF;
+        if (a < 1) return CUDART_INF;
+        return log(b);
+    }
+    if (x == 1) {
+        if (b > 1) return APT_NEG_INF;
+        if (b < 1) return CUDART_INF;
+        return log(a);
+    }
+    if (a <= 2 || b <= 2) return (a - 1) * log(x) + (b - 1) * log1p(-x) - lbeta_fn(a, b);
+    return log(a + b - 1) + dbinom_raw_log(a - 1, a + b - 2, x, 1 - x);
+}
+
+// canonical BUGS order (prob, size)
+__device__ __forceinline__ double dbinom_log(double x, double p, double n) {
+    if (isnan(x) || isnan(n) || isnan(p)) return x + n + p;
+    if (p < 0 || p > 1 || n < 0 || nonint(n)) return CUDART_NAN;
+    if (nonint(x) || x < 0 || !isfinite(x)) return APT_NEG_INF;
+    n = nearbyint(n);
+    x = nearbyint(x);
+    return dbinom_raw_log(x, n, p, 1 - p);
+}
+
+__device__ __forceinline__ double dpois_log(double x, double lambda) {
+    if (isnan(x) || isnan(lambda)) return x + lambda;
+    if (lambda < 0) return CUDART_NAN;
+    if (nonint(x)) return APT_NEG_INF;
+    if (x < 0 || !isfinite(x)) return APT_NEG_INF;
+    x = nearbyint(x);
+    return dpois_raw_log(x, lambda);
+}
+
+__device__ __forceinline__ double dexp_log(double x, double scale) {
+    if (isnan(x) || isnan(scale)) return x + scale;
+    if (scale <= 0.0) return CUDART_NAN;
+    if (x < 0.) return APT_NEG_INF;
+    return (-x / scale) - log(scale);
+}
+
+// Fused form of  y ~ dbinom(prob = ilogit(eta), size = 1)  (lowering peephole, build option fuse_links):
+//   log p(y | eta) = y*eta - log(1 + exp(eta)),  evaluated as  -(softplus(-s*eta)) with s = 2y-1.
+// One exp + one log1p instead of exp + divide + (log | bd0 series); more accurate than the literal
+// ilogit -> 1-p -> dbinom_raw chain, and equal to it to ~1e-16 absolute per term.
+//
+// The reference's own chain p = 1/(1+exp(-eta)); q = 1-p; dbinom_raw(y, 1, p, q) loses accuracy as |eta| grows
+// (q carries an absolute error of ~1.1e-16, i.e. a relative error 1.1e-16 * e^|eta|) and saturates to -Inf for
+// |eta| > 36.74 (p rounds to 1).  To give the SAME accept/reject decisions as the reference even for hot chains
+// that wander there, the fused form is used only for |eta| <= 8, where both agree to < 3.3e-13 absolute per
+// term; beyond that the literal chain is evaluated (a rare, divergent branch: < 4e-6 of rows at the posterior).
+__device__ __forceinline__ double bern_logit_log(double y, double eta) {
+    if (!(y == 0.0 || y == 1.0)) return isnan(y) ? y : APT_NEG_INF;
+    if (fabs(eta) <= 8.0) {
+        double t = (y == 1.0) ? -eta : eta;  // log p = -log(1 + exp(t))
+        double l = log1p(exp(-fabs(t)));
+        return -(fmax(t, 0.0) + l);
+    }
+    if (isnan(eta)) return eta;
+    const double p = 1.0 / (1.0 + exp(-eta));
+    return dbinom_raw_log(y, 1.0, p, 1.0 - p);
+}
+
+__device__ __forceinline__ double ilogit(double x) { return 1.0 / (1.0 + exp(-x)); }
+__device__ __forceinline__ double logit(double p) { return log(p / (1.0 - p)); }
+__device__ __forceinline__ double iprobit(double x) { return 0.5 * erfc(-x * 0.70710678118654752440); }
+__device__ __forceinline__ double icloglog(double x) { return 1.0 - exp(-exp(x)); }
+__device__ __forceinline__ double cloglog(double p) { return log(-log(1.0 - p)); }
+__device__ __forceinline__ double stepfn(double x) { return x >= 0 ? 1.0 : 0.0; }
+
+// nimble dmnorm_chol(x, mean, chol = upper U column-major, n, prec_param): small fixed n, register arrays.
+template <int N>
+__device__ __forceinline__ double dmnorm_chol_log(const double (&x)[N], const double (&mu)[N], const double (&U)[N * N],
+                                                  bool prec_param) {
+    double dens = -N * APT_LN_SQRT_2PI;
+    double w[N];
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        dens += prec_param ? log(U[i * N + i]) : -log(U[i * N + i]);
+        w[i] = x[i] - mu[i];
+    }
+    if (prec_param) {
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+            double s = 0;
+#pragma unroll
+            for (int j = i; j < N; j++) s += U[i + j * N] * w[j];
+            w[i] = s;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+            double s = w[i];
+#pragma unroll
+            for (int j = 0; j < i; j++) s -= U[j + i * N] * w[j];
+            w[i] = s / U[i + i * N];
+        }
+    }
+    double ss = 0;
+#pragma unroll
+    for (int i = 0; i < N; i++) ss += w[i] * w[i];
+    return dens - 0.5 * ss;
+}
+
+}  // namespace apt

@@ -1,0 +1,498 @@
+// apt_host.cuh — host side of a lowered-model module: device state, the run prologue of buildAPT$run
+// (/root/reference/nimbleAPT/R/APT_functions.R:350-393), kernel launches on a private stream, CUDA-event
+// timing, getters.  Instantiated once per generated model G and exported through the plain-C module ABI
+// (apt_module_abi.h) by APT_DEFINE_MODULE(G).  No torch, no CPU fallback: every failure is an error string.
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "apt_engine.cuh"
+#include "apt_module_abi.h"
+
+namespace apt {
+
+struct HostSamplerInfo {
+    int kind, d, unit0, count, blkoff, empoff, adapt_interval;
+    double scale0;
+    const double* propcov0;  // d*d column-major or nullptr (identity)
+};
+
+struct ApiError {
+    std::string msg;
+};
+#define APT_CUDA(x)                                                                                   \
+    do {                                                                                              \
+        cudaError_t e_ = (x);                                                                         \
+        if (e_ != cudaSuccess) throw ApiError{std::string(#x) + ": " + cudaGetErrorString(e_)};      \
+    } while (0)
+
+inline int host_chol_upper(const double* A, double* U, int n) {
+    for (int i = 0; i < n * n; i++) U[i] = 0.0;
+    for (int j = 0; j < n; j++) {
+        double s = A[j + j * n];
+        for (int k = 0; k < j; k++) s -= U[k + j * n] * U[k + j * n];
+        if (!(s > 0)) return -1;
+        double d = std::sqrt(s);
+        U[j + j * n] = d;
+        for (int i = j + 1; i < n; i++) {
+            double t = A[j + i * n];
+            for (int k = 0; k < j; k++) t -= U[k + j * n] * U[k + i * n];
+            U[j + i * n] = t / d;
+        }
+    }
+    return 0;
+}
+
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    void alloc(size_t count) {
+        release();
+        n = count;
+        if (count) APT_CUDA(cudaMalloc((void**)&p, count * sizeof(T)));
+    }
+    void zero(cudaStream_t s) {
+        if (n) APT_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s));
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    ~DevBuf() { release(); }
+};
+
+template <class G>
+struct Engine {
+    using SH = Shape<G>;
+    static constexpr int K = G::K, P = G::P;
+    int L = 0, device = 0;
+    uint32_t ladder0 = 0, seed = 0;
+    double ULT = 1e6;
+    int monitor_tmax = 1, record = 0, thin_conf = 1, thin2_conf = 1;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::vector<DevBuf<double>> arrays;
+    std::vector<DevBuf<int>> iarrays;
+    Data D{};
+    DevBuf<double> theta, lpd, temps, lp, scale, blk, empir, famdelta, model_theta, scale0, blk0;
+    DevBuf<int> slot, cnt, accswap;
+    DevBuf<double> samples, samples2, samplesT, samples2T, logprobs, temptraj;
+    DevBuf<double> tabZ, tabU, tabS;
+    DevBuf<unsigned char> rec;
+    DevBuf<int> recswap;
+    long long cap = 0, cap2 = 0, ttcap = 0, rows = 0, rows2 = 0, ttrows = 0, rec_iters = 0;
+    long long totalIters = 1;
+    uint64_t rngIter = 0;
+    bool resetAnyway = true;
+    aptmod_timing timing{};
+    long long launches_total = 0;
+
+    void create(const aptmod_init* in) {
+        L = in->n_ladders;
+        if (L < 1) throw ApiError{"n_ladders must be >= 1"};
+        if (in->n_temps != K) throw ApiError{"module was lowered for a different number of temperatures"};
+        device = in->device;
+        int ndev = 0;
+        cudaError_t e = cudaGetDeviceCount(&ndev);
+        if (e != cudaSuccess || ndev == 0)
+            throw ApiError{std::string("no CUDA device available (aptb200 has no CPU fallback): ") + cudaGetErrorString(e)};
+        APT_CUDA(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        APT_CUDA(cudaGetDeviceProperties(&prop, device));
+        if (prop.major != 10)
+            throw ApiError{"aptb200 modules are compiled for sm_100a (B200) only; found compute capability " +
+                           std::to_string(prop.major) + "." + std::to_string(prop.minor)};
+        APT_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        APT_CUDA(cudaEventCreate(&ev0));
+        APT_CUDA(cudaEventCreate(&ev1));
+        ladder0 = in->ladder0; seed = in->seed; ULT = in->ULT; monitor_tmax = in->monitor_tmax; record = in->record;
+        thin_conf = in->thin_conf > 0 ? in->thin_conf : 1;
+        thin2_conf = in->thin2_conf > 0 ? in->thin2_conf : 1;
+        if (in->n_arrays != G::NARR || in->n_iarrays != G::NIARR) throw ApiError{"array count mismatch between lowering and module"};
+        arrays.resize(G::NARR);
+        for (int i = 0; i < G::NARR; i++) {
+            arrays[i].alloc((size_t)std::max<int64_t>(in->array_len[i], 1));
+            if (in->array_len[i])
+                APT_CUDA(cudaMemcpyAsync(arrays[i].p, in->arrays[i], in->array_len[i] * sizeof(double), cudaMemcpyHostToDevice, stream));
+            D.a[i] = arrays[i].p;
+        }
+        iarrays.resize(G::NIARR);
+        for (int i = 0; i < G::NIARR; i++) {
+            iarrays[i].alloc((size_t)std::max<int64_t>(in->iarray_len[i], 1));
+            if (in->iarray_len[i])
+                APT_CUDA(cudaMemcpyAsync(iarrays[i].p, in->iarrays[i], in->iarray_len[i] * sizeof(int), cudaMemcpyHostToDevice, stream));
+            D.ia[i] = iarrays[i].p;
+        }
+        const size_t nch = (size_t)L * K;
+        theta.alloc(nch * P); lpd.alloc(nch * G::ND); temps.alloc(nch); lp.alloc(nch); slot.alloc(nch);
+        scale.alloc(nch * G::NU); cnt.alloc(nch * G::NU * 3);
+        blk.alloc(std::max<size_t>(nch * G::BLKSZ, 1)); empir.alloc(std::max<size_t>(nch * G::EMPSZ, 1));
+        accswap.alloc(nch * K); model_theta.alloc((size_t)L * P);
+        famdelta.alloc(G::HAS_FAMILY ? nch * G::NU * APT_FAM_MAXG : 1); famdelta.zero(stream);
+        empir.zero(stream); lp.zero(stream);
+        // Temps <- sort(Temps)  (APT:266)
+        std::vector<double> t(in->temps, in->temps + K);
+        std::sort(t.begin(), t.end());
+        std::vector<double> tl(nch);
+        for (size_t i = 0; i < nch; i++) tl[i] = t[i % K];
+        APT_CUDA(cudaMemcpyAsync(temps.p, tl.data(), nch * sizeof(double), cudaMemcpyHostToDevice, stream));
+        std::vector<double> mt((size_t)L * P);
+        for (size_t i = 0; i < mt.size(); i++) mt[i] = in->theta0[i % P];
+        APT_CUDA(cudaMemcpyAsync(model_theta.p, mt.data(), mt.size() * sizeof(double), cudaMemcpyHostToDevice, stream));
+        // sampler reset images (scaleOriginal, propCovOriginal, chol(propCov), scale*chol: APT:675,796-806)
+        std::vector<double> s0(G::NU, 1.0), b0(std::max(G::BLKSZ, 1), 0.0);
+        for (int s = 0; s < G::NSAMP; s++) {
+            const HostSamplerInfo& hi = G::sampler_info(s);
+            for (int m = 0; m < hi.count; m++) s0[hi.unit0 + m] = hi.scale0;
+            if (hi.kind == 1) {
+                const int d = hi.d;
+                double* pc = &b0[hi.blkoff];
+                for (int i = 0; i < d * d; i++) pc[i] = hi.propcov0 ? hi.propcov0[i] : ((i % (d + 1)) == 0 ? 1.0 : 0.0);
+                if (host_chol_upper(pc, pc + d * d, d)) throw ApiError{"propCov is not positive definite"};
+                for (int i = 0; i < d * d; i++) pc[2 * d * d + i] = pc[d * d + i] * hi.scale0;
+            }
+        }
+        scale0.alloc(G::NU); blk0.alloc(b0.size());
+        APT_CUDA(cudaMemcpyAsync(scale0.p, s0.data(), s0.size() * sizeof(double), cudaMemcpyHostToDevice, stream));
+        APT_CUDA(cudaMemcpyAsync(blk0.p, b0.data(), b0.size() * sizeof(double), cudaMemcpyHostToDevice, stream));
+        if (SH::SM_BYTES > 48 * 1024)
+            APT_CUDA(cudaFuncSetAttribute(ladder_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SH::SM_BYTES));
+        APT_CUDA(cudaStreamSynchronize(stream));
+    }
+
+    ~Engine() {
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+        if (stream) cudaStreamDestroy(stream);
+    }
+
+    void set_model_theta(const double* th, int ladder) {
+        APT_CUDA(cudaSetDevice(device));
+        for (int l = 0; l < L; l++)
+            if (ladder < 0 || ladder == l)
+                APT_CUDA(cudaMemcpyAsync(model_theta.p + (size_t)l * P, th, P * sizeof(double), cudaMemcpyHostToDevice, stream));
+        APT_CUDA(cudaStreamSynchronize(stream));
+    }
+    void set_array(int idx, const double* v, int64_t n) {
+        APT_CUDA(cudaSetDevice(device));
+        if (idx < 0 || idx >= G::NARR || (size_t)n != arrays[idx].n) throw ApiError{"set_array: bad index or length"};
+        APT_CUDA(cudaMemcpyAsync(arrays[idx].p, v, n * sizeof(double), cudaMemcpyHostToDevice, stream));
+    }
+
+    static void grow_trace(DevBuf<double>& b, int L, long long oldcap, long long newcap, long long keep_rows, int cols,
+                           cudaStream_t s) {
+        if (cols == 0) return;
+        DevBuf<double> nb;
+        nb.alloc((size_t)L * newcap * cols);
+        if (b.p && keep_rows > 0)
+            APT_CUDA(cudaMemcpy2DAsync(nb.p, (size_t)newcap * cols * 8, b.p, (size_t)oldcap * cols * 8, (size_t)keep_rows * cols * 8,
+                                       L, cudaMemcpyDeviceToDevice, s));
+        APT_CUDA(cudaStreamSynchronize(s));
+        std::swap(b.p, nb.p);
+        std::swap(b.n, nb.n);
+    }
+
+    void refresh_lpd() {  // initializeModel / calculate(): recompute every chain's per-declaration logProbs
+        const int nst = L * K;
+        const int threads = 128;
+        const int blocks = (int)(((size_t)nst * G::W + threads - 1) / threads);
+        logprob_kernel<G><<<blocks, threads, 0, stream>>>(D, theta.p, nst, lpd.p);
+        APT_CUDA(cudaGetLastError());
+        timing.launches++;
+    }
+
+    void run(const aptmod_run_args* ra) {
+        APT_CUDA(cudaSetDevice(device));
+        if (ra->niter < 0) throw ApiError{"cannot specify niter < 0"};  // APT:350
+        int thin = ra->thin != -1 ? ra->thin : thin_conf;               // APT:351-353
+        int thin2 = ra->thin2 != -1 ? ra->thin2 : thin2_conf;
+        if (thin < 1 || thin2 < 1) throw ApiError{"thin and thin2 must be >= 1"};
+        bool reset = ra->reset != 0, resetTempering = ra->resetTempering != 0;
+        if (resetAnyway) {  // APT:358-363
+            reset = true; resetTempering = true; resetAnyway = false; totalIters = 1;
+        }
+        if (resetTempering) totalIters = 1;  // APT:365-367
+        timing = aptmod_timing{};
+        accswap.zero(stream);                // APT:368
+        long long off, off2;
+        if (reset) {                         // APT:369-377
+            reset_kernel<G><<<std::min<size_t>((size_t)L * K, 65535), 64, 0, stream>>>(L, model_theta.p, theta.p, slot.p, scale.p,
+                                                                                     cnt.p, blk.p, scale0.p, blk0.p);
+            APT_CUDA(cudaGetLastError());
+            timing.launches++;
+            off = 0; off2 = 0;
+        } else {                             // APT:378-385
+            off = rows; off2 = rows2;
+            if (ra->resetMV) { off = 0; off2 = 0; }
+        }
+        const long long nr = ra->niter / thin, nr2 = ra->niter / thin2;
+        if (off + nr > cap) {
+            long long nc = off + nr;
+            grow_trace(samples, L, cap, nc, off, G::NMON, stream);
+            grow_trace(samplesT, L, cap, nc, off, G::NMON, stream);
+            grow_trace(logprobs, L, cap, nc, off, 1, stream);
+            cap = nc;
+        }
+        if (off2 + nr2 > cap2) {
+            long long nc = off2 + nr2;
+            grow_trace(samples2, L, cap2, nc, off2, G::NMON2, stream);
+            grow_trace(samples2T, L, cap2, nc, off2, G::NMON2, stream);
+            cap2 = nc;
+        }
+        if (nr > ttcap) { temptraj.alloc((size_t)L * nr * K); ttcap = nr; }
+        rows = off + nr; rows2 = off2 + nr2; ttrows = nr;
+        refresh_lpd();
+        // test hooks
+        const size_t nz = (size_t)ra->niter * L * K * G::NU;
+        if (ra->tabZ) { tabZ.alloc(nz * G::DMAX); APT_CUDA(cudaMemcpyAsync(tabZ.p, ra->tabZ, nz * G::DMAX * 8, cudaMemcpyHostToDevice, stream)); }
+        if (ra->tabU) { tabU.alloc(nz); APT_CUDA(cudaMemcpyAsync(tabU.p, ra->tabU, nz * 8, cudaMemcpyHostToDevice, stream)); }
+        if (ra->tabS) { tabS.alloc((size_t)ra->niter * L * K * 2); APT_CUDA(cudaMemcpyAsync(tabS.p, ra->tabS, (size_t)ra->niter * L * K * 16, cudaMemcpyHostToDevice, stream)); }
+        if (record) {
+            rec.alloc(std::max<size_t>(nz, 1)); rec.zero(stream);
+            recswap.alloc(std::max<size_t>((size_t)ra->niter * L * K, 1)); recswap.zero(stream);
+            rec_iters = ra->niter;
+        }
+        KArgs a{};
+        a.D = D; a.L = L; a.ladder0 = ladder0; a.seed = seed;
+        a.adapt_temps = ra->adaptTemps; a.tune1 = ra->tuneTemper1; a.tune2 = ra->tuneTemper2; a.ULT = ULT;
+        a.thin = thin; a.thin2 = thin2; a.monitor_tmax = monitor_tmax;
+        a.off = off; a.off2 = off2; a.cap = cap; a.cap2 = cap2; a.ttcap = ttcap;
+        a.theta = theta.p; a.lpd = lpd.p; a.temps = temps.p; a.lp = lp.p; a.scale = scale.p; a.blk = blk.p; a.empir = empir.p; a.famdelta = famdelta.p;
+        a.slot = slot.p; a.cnt = cnt.p; a.accswap = accswap.p;
+        a.samples = samples.p; a.samples2 = samples2.p; a.samplesT = samplesT.p; a.samples2T = samples2T.p;
+        a.logprobs = logprobs.p; a.temptraj = temptraj.p;
+        a.tabZ = ra->tabZ ? tabZ.p : nullptr; a.tabU = ra->tabU ? tabU.p : nullptr; a.tabS = ra->tabS ? tabS.p : nullptr;
+        a.rec = record ? rec.p : nullptr; a.recswap = record ? recswap.p : nullptr;
+        long long chunk = ra->iters_per_launch > 0 ? ra->iters_per_launch : 4096;
+        const int grid = (L + SH::TEAMS - 1) / SH::TEAMS;
+        bool aborted = false;
+        for (long long it0 = 0; it0 < ra->niter; it0 += chunk) {
+            if (ra->should_abort && ra->should_abort(ra->abort_arg)) { aborted = true; break; }
+            a.it0 = it0; a.it1 = std::min<long long>(ra->niter, it0 + chunk);
+            a.rng_iter0 = rngIter; a.total_iters0 = totalIters;
+            APT_CUDA(cudaEventRecord(ev0, stream));
+            ladder_kernel<G><<<grid, SH::CTA, SH::SM_BYTES, stream>>>(a);
+            APT_CUDA(cudaGetLastError());
+            APT_CUDA(cudaEventRecord(ev1, stream));
+            APT_CUDA(cudaEventSynchronize(ev1));
+            float ms = 0;
+            APT_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
+            timing.kernel_ms += ms; timing.main_kernel_ms += ms; timing.launches++; timing.main_launches++;
+            rngIter += (uint64_t)(a.it1 - a.it0);
+            totalIters += (a.it1 - a.it0);
+        }
+        // APT:548: the model is left parameterised with the T=1 state
+        model_from_rung1_kernel<G><<<std::min(L, 65535), 64, 0, stream>>>(L, theta.p, slot.p, model_theta.p);
+        APT_CUDA(cudaGetLastError());
+        timing.launches++;
+        APT_CUDA(cudaStreamSynchronize(stream));
+        launches_total += timing.launches;
+        if (aborted) throw ApiError{"run interrupted by the caller"};
+    }
+
+    // whole-model logProb of caller-provided states (host pointers): out_lpd [n][ND]
+    void logprob(const double* th, int n, double* out_lpd) {
+        APT_CUDA(cudaSetDevice(device));
+        DevBuf<double> dth, dout;
+        dth.alloc((size_t)n * P); dout.alloc((size_t)n * G::ND);
+        APT_CUDA(cudaMemcpyAsync(dth.p, th, (size_t)n * P * 8, cudaMemcpyHostToDevice, stream));
+        const int threads = 128;
+        logprob_kernel<G><<<(int)(((size_t)n * G::W + threads - 1) / threads), threads, 0, stream>>>(D, dth.p, n, dout.p);
+        APT_CUDA(cudaGetLastError());
+        APT_CUDA(cudaMemcpyAsync(out_lpd, dout.p, (size_t)n * G::ND * 8, cudaMemcpyDeviceToHost, stream));
+        APT_CUDA(cudaStreamSynchronize(stream));
+    }
+
+    long long info(int what) const {
+        switch (what) {
+            case APTMOD_INFO_P: return P;
+            case APTMOD_INFO_K: return K;
+            case APTMOD_INFO_NU: return G::NU;
+            case APTMOD_INFO_ND: return G::ND;
+            case APTMOD_INFO_NMON: return G::NMON;
+            case APTMOD_INFO_NMON2: return G::NMON2;
+            case APTMOD_INFO_DMAX: return G::DMAX;
+            case APTMOD_INFO_ROWS: return rows;
+            case APTMOD_INFO_ROWS2: return rows2;
+            case APTMOD_INFO_TTROWS: return ttrows;
+            case APTMOD_INFO_L: return L;
+            case APTMOD_INFO_LAUNCHES: return launches_total;
+            case APTMOD_INFO_TOTALITERS: return totalIters;
+            case APTMOD_INFO_W: return G::W;
+            case APTMOD_INFO_CTA: return SH::CTA;
+            case APTMOD_INFO_ENGINE: return 0;
+            case APTMOD_INFO_BLKSZ: return G::BLKSZ;
+        }
+        return -1;
+    }
+
+    template <class T>
+    std::vector<T> d2h(const T* p, size_t n) {
+        std::vector<T> v(n);
+        if (n) APT_CUDA(cudaMemcpyAsync(v.data(), p, n * sizeof(T), cudaMemcpyDeviceToHost, stream));
+        APT_CUDA(cudaStreamSynchronize(stream));
+        return v;
+    }
+    void trace_out(const DevBuf<double>& b, long long capr, long long nrows, int cols, int ladder, double* out, int64_t capn,
+                   int64_t& n) {
+        if (ladder >= L) throw ApiError{"ladder index out of range"};
+        const int nl = ladder < 0 ? L : 1;
+        n = (int64_t)nl * nrows * cols;
+        if (n > capn) throw ApiError{"output buffer too small"};
+        if (n == 0) return;
+        const double* src = b.p + (size_t)(ladder < 0 ? 0 : ladder) * capr * cols;
+        APT_CUDA(cudaMemcpy2DAsync(out, (size_t)nrows * cols * 8, src, (size_t)capr * cols * 8, (size_t)nrows * cols * 8, nl,
+                                   cudaMemcpyDeviceToHost, stream));
+        APT_CUDA(cudaStreamSynchronize(stream));
+    }
+
+    // copies into caller-allocated host memory; returns the number of doubles written
+    int64_t get(int what, int ladder, double* out, int64_t capn) {
+        APT_CUDA(cudaSetDevice(device));
+        int64_t n = 0;
+        const int l = ladder < 0 ? 0 : ladder;
+        if (ladder >= L) throw ApiError{"ladder index out of range"};
+        switch (what) {
+            case APTMOD_SAMPLES: trace_out(samples, cap, rows, G::NMON, ladder, out, capn, n); return n;
+            case APTMOD_SAMPLES_TMAX: trace_out(samplesT, cap, rows, G::NMON, ladder, out, capn, n); return n;
+            case APTMOD_SAMPLES2: trace_out(samples2, cap2, rows2, G::NMON2, ladder, out, capn, n); return n;
+            case APTMOD_SAMPLES2_TMAX: trace_out(samples2T, cap2, rows2, G::NMON2, ladder, out, capn, n); return n;
+            case APTMOD_LOGPROBS: trace_out(logprobs, cap, rows, 1, ladder, out, capn, n); return n;
+            case APTMOD_TEMPTRAJ: trace_out(temptraj, ttcap, ttrows, K, ladder, out, capn, n); return n;
+            case APTMOD_TEMPS:
+            case APTMOD_LOGPROBTEMPS: {
+                const int nl = ladder < 0 ? L : 1;
+                n = (int64_t)nl * K;
+                if (n > capn) throw ApiError{"output buffer too small"};
+                auto v = d2h((what == APTMOD_TEMPS ? temps.p : lp.p) + (size_t)l * K, (size_t)n);
+                std::memcpy(out, v.data(), n * 8);
+                return n;
+            }
+            case APTMOD_ACCSWAP: {
+                n = (int64_t)K * K;
+                if (n > capn) throw ApiError{"output buffer too small"};
+                auto v = d2h(accswap.p + (size_t)l * K * K, (size_t)n);
+                for (int64_t i = 0; i < n; i++) out[i] = v[i];
+                return n;
+            }
+            case APTMOD_THETA: {  // [K][P] in rung order
+                n = (int64_t)K * P;
+                if (n > capn) throw ApiError{"output buffer too small"};
+                auto v = d2h(theta.p + (size_t)l * K * P, (size_t)n);
+                auto s = d2h(slot.p + (size_t)l * K, (size_t)K);
+                for (int k = 0; k < K; k++) std::memcpy(out + (size_t)k * P, v.data() + (size_t)s[k] * P, P * 8);
+                return n;
+            }
+            case APTMOD_MODEL_THETA: {
+                n = P;
+                if (n > capn) throw ApiError{"output buffer too small"};
+                auto v = d2h(model_theta.p + (size_t)l * P, (size_t)P);
+                std::memcpy(out, v.data(), P * 8);
+                return n;
+            }
+            case APTMOD_SCALE: {
+                n = (int64_t)K * G::NU;
+                if (n > capn) throw ApiError{"output buffer too small"};
+                auto v = d2h(scale.p + (size_t)l * K * G::NU, (size_t)n);
+                std::memcpy(out, v.data(), n * 8);
+                return n;
+            }
+            case APTMOD_PROPCOV: {
+                n = (int64_t)K * G::BLKSZ;
+                if (n > capn) throw ApiError{"output buffer too small"};
+                auto v = d2h(blk.p + (size_t)l * K * G::BLKSZ, (size_t)n);
+                std::memcpy(out, v.data(), n * 8);
+                return n;
+            }
+            case APTMOD_DECISIONS: {  // [iters][K][NU]
+                if (!record) throw ApiError{"decision recording was not enabled at build"};
+                n = rec_iters * K * G::NU;
+                if (n > capn) throw ApiError{"output buffer too small"};
+                auto v = d2h(rec.p, (size_t)rec_iters * L * K * G::NU);
+                for (long long it = 0; it < rec_iters; it++)
+                    for (int i = 0; i < K * G::NU; i++) out[it * K * G::NU + i] = v[((size_t)it * L + l) * K * G::NU + i];
+                return n;
+            }
+            case APTMOD_SWAPREC: {  // [iters][K]  value = iTo | accepted << 16
+                if (!record) throw ApiError{"decision recording was not enabled at build"};
+                n = rec_iters * K;
+                if (n > capn) throw ApiError{"output buffer too small"};
+                auto v = d2h(recswap.p, (size_t)rec_iters * L * K);
+                for (long long it = 0; it < rec_iters; it++)
+                    for (int i = 0; i < K; i++) out[it * K + i] = v[((size_t)it * L + l) * K + i];
+                return n;
+            }
+        }
+        throw ApiError{"unknown getter"};
+    }
+};
+
+inline void set_err(char* err, int errlen, const std::string& m) {
+    if (err && errlen > 0) {
+        std::snprintf(err, (size_t)errlen, "%s", m.c_str());
+    }
+}
+
+}  // namespace apt
+
+#define APT_GUARD(body)                                                    \
+    try {                                                                  \
+        body;                                                              \
+        return 0;                                                          \
+    } catch (const apt::ApiError& e) {                                     \
+        apt::set_err(err, errlen, e.msg);                                  \
+        return 1;                                                          \
+    } catch (const std::exception& e) {                                    \
+        apt::set_err(err, errlen, e.what());                               \
+        return 1;                                                          \
+    } catch (...) {                                                        \
+        apt::set_err(err, errlen, "unknown error");                        \
+        return 1;                                                          \
+    }
+
+#define APT_EXPORT __attribute__((visibility("default")))
+#define APT_DEFINE_MODULE(G)                                                                                        \
+    extern "C" {                                                                                                    \
+    APT_EXPORT int aptmod_abi_version(void) { return APTMOD_ABI_VERSION; }                                                     \
+    APT_EXPORT int aptmod_create(const aptmod_init* in, void** out, char* err, int errlen) {                                   \
+        *out = nullptr;                                                                                             \
+        apt::Engine<G>* e = nullptr;                                                                                \
+        try {                                                                                                       \
+            e = new apt::Engine<G>();                                                                               \
+            e->create(in);                                                                                          \
+            *out = e;                                                                                               \
+            return 0;                                                                                               \
+        } catch (const apt::ApiError& x) {                                                                          \
+            apt::set_err(err, errlen, x.msg);                                                                       \
+        } catch (const std::exception& x) {                                                                         \
+            apt::set_err(err, errlen, x.what());                                                                    \
+        } catch (...) {                                                                                             \
+            apt::set_err(err, errlen, "unknown error");                                                             \
+        }                                                                                                           \
+        delete e;                                                                                                   \
+        return 1;                                                                                                   \
+    }                                                                                                               \
+    APT_EXPORT void aptmod_destroy(void* h) { delete static_cast<apt::Engine<G>*>(h); }                                        \
+    APT_EXPORT int aptmod_run(void* h, const aptmod_run_args* ra, char* err, int errlen) {                                     \
+        APT_GUARD(static_cast<apt::Engine<G>*>(h)->run(ra))                                                         \
+    }                                                                                                               \
+    APT_EXPORT int aptmod_get(void* h, int what, int ladder, double* out, int64_t cap, int64_t* n, char* err, int errlen) {    \
+        APT_GUARD(*n = static_cast<apt::Engine<G>*>(h)->get(what, ladder, out, cap))                                \
+    }                                                                                                               \
+    APT_EXPORT long long aptmod_info(void* h, int what) { return static_cast<apt::Engine<G>*>(h)->info(what); }                \
+    APT_EXPORT int aptmod_logprob(void* h, const double* th, int n, double* out, char* err, int errlen) {                      \
+        APT_GUARD(static_cast<apt::Engine<G>*>(h)->logprob(th, n, out))                                             \
+    }                                                                                                               \
+    APT_EXPORT int aptmod_set_model_theta(void* h, const double* th, int ladder, char* err, int errlen) {                      \
+        APT_GUARD(static_cast<apt::Engine<G>*>(h)->set_model_theta(th, ladder))                                     \
+    }                                                                                                               \
+    APT_EXPORT int aptmod_set_array(void* h, int idx, const double* v, int64_t n, char* err, int errlen) {                     \
+        APT_GUARD(static_cast<apt::Engine<G>*>(h)->set_array(idx, v, n))                                            \
+    }                                                                                                               \
+    APT_EXPORT void aptmod_timing_get(void* h, aptmod_timing* t) { *t = static_cast<apt::Engine<G>*>(h)->timing; }             \
+    }

@@ -1,0 +1,1344 @@
+// lower.cpp — the lowering step: BUGS subset -> CUDA device log-probability code for sm_100a.
+//
+// Stands in for nimble's model compilation and for the sampler `setup` functions of the reference
+// (/root/reference/nimbleAPT/R/APT_functions.R:652-689, 773-820): canonical parameterisations, deterministic
+// nodes inlined into their consumers, `model$getDependencies(target)` computed concretely per sampler, and the
+// result emitted as C++/CUDA that is instantiated into the engine kernels (engine/apt_engine.cuh).
+//
+// Per sampler the dependent stochastic nodes are grouped by declaration:
+//   FULL    – every instance of the declaration depends on the target: the engine keeps the declaration's
+//             log-probability SUM per chain and compares new sum vs stored sum (1 pass over the data);
+//   PARTIAL – a subset of instances (a prior term, the observations of one random-effect group, ...):
+//             old and new terms are both evaluated over the explicit instance list.
+// Runs of scalar samplers on consecutive elements of one variable whose dependent sets are disjoint (e.g. the
+// 1000 random effects of a GLMM) are recognised as a FAMILY and executed in parallel; this is exactly equivalent
+// to the reference's serial order (APT:440-444) because no member's update reads another member's target.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <functional>
+#include <set>
+#include <sstream>
+#include "front.h"
+
+namespace aptf {
+namespace {
+
+struct Var {
+    std::string name;
+    enum Role { PARAM, DATA, CONST, DET } role = CONST;
+    std::vector<int64_t> dims;
+    int64_t size = 1;
+    int64_t theta_off = -1;
+    const Array* arr = nullptr;
+    int arr_idx = -1;
+    int64_t nrow() const { return dims.empty() ? 1 : dims[0]; }
+};
+struct LoopC {
+    std::string var;
+    long lo, hi;
+};
+struct CDecl {
+    std::vector<LoopC> loops;
+    EP lhs;
+    bool stoch = false;
+    std::string dist;
+    std::vector<EP> args;          // canonical (not inlined)
+    std::vector<EP> iargs;         // deterministic nodes inlined (scalar args)
+    std::vector<EP> mean_elems;    // dmnorm
+    std::vector<EP> chol_elems;    // dmnorm, column-major n*n
+    int mvn_n = 0;
+    int lpidx = -1;
+    bool lhs_param = false;
+    long ninst = 1;
+    int line = 0;
+};
+struct Pattern {  // one read of (or the write to) a PARAM variable by a stochastic declaration
+    const Var* v;
+    EP ref;
+    bool own;
+    bool loop_dep;
+    std::vector<std::vector<int>> by_elem;  // element -> instances (loop-dependent, non-range)
+    bool built = false;
+};
+struct Group {
+    int decl;
+    bool full, prior;
+    std::vector<int> inst;  // linear instance indices when !full
+};
+struct Unit {  // one generated sampler struct: a single sampler or a family
+    int kind = 0, d = 1, unit0 = 0, count = 1;
+    std::vector<int> tgt;  // theta indices of member 0
+    const SamplerConf* conf = nullptr;
+    std::vector<Group> groups;
+    // family CSR arrays (Data::ia indices) per group: ptr, idx
+    std::vector<int> ia_ptr, ia_idx;
+    // explicit lists for non-family partial groups
+    std::vector<int> ia_list;
+    int blkoff = 0, empoff = 0;
+    EP lower, upper;
+    std::map<std::string, double> bound_env;
+};
+
+std::string fmt_d(double v) {
+    if (std::isinf(v)) return v > 0 ? "CUDART_INF" : "(-CUDART_INF)";
+    if (std::isnan(v)) return "CUDART_NAN";
+    char buf[64];
+    snprintf(buf, sizeof buf, "%.17g", v);
+    std::string s = buf;
+    if (s.find_first_of(".eEn") == std::string::npos) s += ".0";
+    return s;
+}
+
+struct Lowerer {
+    const ModelSpec& spec;
+    int K;
+    apt_build_opts opts;
+    std::map<std::string, Var> vars;
+    std::vector<std::string> param_order;
+    std::vector<CDecl> decls;
+    std::vector<int> stoch_decls;
+    std::vector<std::vector<Pattern>> patterns;  // per stochastic decl (index = position in decls)
+    int P = 0, ND = 0;
+    std::vector<const Array*> used_arrays;
+    std::vector<std::vector<int>> iarrays;
+    std::vector<Unit> units;
+    std::ostringstream out;
+
+    Lowerer(const ModelSpec& s, int k, const apt_build_opts& o) : spec(s), K(k), opts(o) {}
+
+    // ------------------------------------------------------------------ constants
+    const Array* find_const(const std::string& n) const {
+        auto it = spec.constants.find(n);
+        if (it != spec.constants.end()) return &it->second;
+        return nullptr;
+    }
+    double ceval(const EP& e, const std::map<std::string, double>& env) const {
+        switch (e->k) {
+            case Expr::NUM: return e->num;
+            case Expr::NEG: return -ceval(e->a[0], env);
+            case Expr::BIN: {
+                double a = ceval(e->a[0], env), b = ceval(e->a[1], env);
+                switch (e->op) {
+                    case '+': return a + b;
+                    case '-': return a - b;
+                    case '*': return a * b;
+                    case '/': return a / b;
+                    case '^': return std::pow(a, b);
+                }
+                break;
+            }
+            case Expr::VAR: {
+                if (e->a.empty()) {
+                    auto it = env.find(e->name);
+                    if (it != env.end()) return it->second;
+                }
+                const Array* c = find_const(e->name);
+                if (!c) {
+                    auto it = spec.data.find(e->name);
+                    if (it != spec.data.end() && !vars.count(e->name)) c = &it->second;
+                    else if (it != spec.data.end() && vars.at(e->name).role == Var::CONST) c = &it->second;
+                }
+                if (c) {
+                    if (e->a.empty()) {
+                        if (c->size() != 1) throw Error("array constant '" + e->name + "' used as a scalar");
+                        return c->v[0];
+                    }
+                    int64_t off = 0, stride = 1;
+                    if (e->a.size() != c->dims.size()) throw Error("wrong number of indices for '" + e->name + "'");
+                    for (size_t k = 0; k < e->a.size(); k++) {
+                        if (e->a[k]->k == Expr::RANGE) throw Error("range where a scalar index is required: " + to_string(e));
+                        long idx = (long)std::llround(ceval(e->a[k], env));
+                        if (idx < 1 || idx > c->dims[k]) throw Error("index out of range: " + to_string(e));
+                        off += (idx - 1) * stride;
+                        stride *= c->dims[k];
+                    }
+                    return c->v[off];
+                }
+                throw Error("not a constant: " + e->name);
+            }
+            case Expr::CALL: {
+                if (e->name == "length" && e->a.size() == 1 && e->a[0]->k == Expr::VAR) {
+                    const Array* c = find_const(e->a[0]->name);
+                    if (c) return (double)c->size();
+                }
+                if (e->a.size() == 1) {
+                    double x = ceval(e->a[0], env);
+                    if (e->name == "exp") return std::exp(x);
+                    if (e->name == "log") return std::log(x);
+                    if (e->name == "sqrt") return std::sqrt(x);
+                    if (e->name == "abs") return std::fabs(x);
+                }
+                break;
+            }
+            default: break;
+        }
+        throw Error("expression is not a compile-time constant: " + to_string(e));
+    }
+    bool try_ceval(const EP& e, const std::map<std::string, double>& env, double& v) const {
+        try {
+            v = ceval(e, env);
+            return true;
+        } catch (const Error&) {
+            return false;
+        }
+    }
+
+    // ------------------------------------------------------------------ canonical declarations
+    static EP kwarg(const EP& call, const char* name, size_t pos) {
+        for (auto& kv : call->kw)
+            if (kv.first == name) return kv.second;
+        // positional arguments fill the formals that were not named, in order
+        return pos < call->a.size() ? call->a[pos] : nullptr;
+    }
+    static bool has_kw(const EP& call, const char* name) {
+        for (auto& kv : call->kw)
+            if (kv.first == name) return true;
+        return false;
+    }
+
+    EP substitute(const EP& e, const std::map<std::string, EP>& m) const {
+        if (e->k == Expr::VAR && e->a.empty()) {
+            auto it = m.find(e->name);
+            if (it != m.end()) return it->second;
+            return e;
+        }
+        auto r = std::make_shared<Expr>(*e);
+        for (auto& x : r->a) x = substitute(x, m);
+        for (auto& x : r->kw) x.second = substitute(x.second, m);
+        return r;
+    }
+
+    void canonicalise() {
+        int idx = 0;
+        for (const RawDecl& rd : spec.decls) {
+            CDecl d;
+            d.line = rd.line;
+            for (auto& l : rd.loops) {
+                LoopC lc;
+                lc.var = l.var;
+                lc.lo = (long)std::llround(ceval(l.lo, {}));
+                lc.hi = (long)std::llround(ceval(l.hi, {}));
+                if (lc.hi < lc.lo) throw Error("empty loop range for '" + l.var + "'");
+                d.loops.push_back(lc);
+            }
+            d.lhs = rd.lhs;
+            d.stoch = rd.stoch;
+            if (rd.stoch) {
+                EP c = rd.rhs;
+                std::string dist = c->name;
+                EP one = mk_num(1.0);
+                auto need = [&](EP e, const char* what) {
+                    if (!e) throw Error("line " + std::to_string(rd.line) + ": " + dist + " is missing argument '" + what + "'");
+                    return e;
+                };
+                if (dist == "dbern") {
+                    d.dist = "dbinom";
+                    d.args = {need(kwarg(c, "prob", 0), "prob"), one};
+                } else if (dist == "dnorm") {
+                    d.dist = dist;
+                    EP mean = need(kwarg(c, "mean", 0), "mean"), sd;
+                    if (has_kw(c, "sd")) sd = kwarg(c, "sd", 99);
+                    else if (has_kw(c, "var")) sd = mk_call("sqrt", {kwarg(c, "var", 99)});
+                    else sd = mk_bin('/', one, mk_call("sqrt", {need(kwarg(c, "tau", 1), "tau")}));
+                    d.args = {mean, sd};
+                } else if (dist == "dunif") {
+                    d.dist = dist;
+                    d.args = {need(kwarg(c, "min", 0), "min"), need(kwarg(c, "max", 1), "max")};
+                } else if (dist == "dgamma") {
+                    d.dist = dist;
+                    EP shape = need(kwarg(c, "shape", 0), "shape");
+                    EP scale = has_kw(c, "scale") ? kwarg(c, "scale", 99) : mk_bin('/', one, need(kwarg(c, "rate", 1), "rate"));
+                    d.args = {shape, scale};
+                } else if (dist == "dbeta") {
+                    d.dist = dist;
+                    d.args = {need(kwarg(c, "shape1", 0), "shape1"), need(kwarg(c, "shape2", 1), "shape2")};
+                } else if (dist == "dbinom") {
+                    d.dist = dist;
+                    EP prob, size;
+                    const bool kp = has_kw(c, "prob"), ks = has_kw(c, "size");
+                    if (kp && ks) { prob = kwarg(c, "prob", 99); size = kwarg(c, "size", 99); }
+                    else if (kp) { prob = kwarg(c, "prob", 99); size = c->a.empty() ? nullptr : c->a[0]; }
+                    else if (ks) { size = kwarg(c, "size", 99); prob = c->a.empty() ? nullptr : c->a[0]; }
+                    else { prob = c->a.size() > 0 ? c->a[0] : nullptr; size = c->a.size() > 1 ? c->a[1] : nullptr; }
+                    d.args = {need(prob, "prob"), need(size, "size")};
+                } else if (dist == "dpois") {
+                    d.dist = dist;
+                    d.args = {need(kwarg(c, "lambda", 0), "lambda")};
+                } else if (dist == "dexp") {
+                    d.dist = dist;
+                    d.args = {has_kw(c, "scale") ? kwarg(c, "scale", 99) : mk_bin('/', one, need(kwarg(c, "rate", 0), "rate"))};
+                } else if (dist == "dmnorm") {
+                    d.dist = dist;
+                    if (!has_kw(c, "cholesky"))
+                        throw Error("line " + std::to_string(rd.line) + ": dmnorm is supported as dmnorm(mean, cholesky = , prec_param = )");
+                    d.args = {need(kwarg(c, "mean", 0), "mean"), kwarg(c, "cholesky", 99),
+                              has_kw(c, "prec_param") ? kwarg(c, "prec_param", 99) : one};
+                } else {
+                    throw Error("line " + std::to_string(rd.line) + ": unsupported distribution '" + dist +
+                                "' (supported: dnorm dunif dgamma dbeta dbinom dbern dpois dexp dmnorm)");
+                }
+            } else {
+                EP rhs = rd.rhs;
+                if (!rd.link.empty()) {
+                    static const std::map<std::string, std::string> inv = {{"log", "exp"}, {"logit", "ilogit"}, {"probit", "iprobit"}, {"cloglog", "icloglog"}};
+                    auto it = inv.find(rd.link);
+                    if (it == inv.end()) throw Error("unsupported link function '" + rd.link + "'");
+                    rhs = mk_call(it->second, {rhs});
+                }
+                // scalarise element-wise vector declarations  v[a:b] <- f(w[c:d])
+                int rdim = -1;
+                for (size_t k = 0; k < d.lhs->a.size(); k++)
+                    if (d.lhs->a[k]->k == Expr::RANGE) {
+                        if (rdim >= 0) throw Error("matrix-valued deterministic declarations are not supported");
+                        rdim = (int)k;
+                    }
+                if (rdim >= 0) {
+                    long lo = (long)std::llround(ceval(d.lhs->a[rdim]->a[0], {}));
+                    long hi = (long)std::llround(ceval(d.lhs->a[rdim]->a[1], {}));
+                    std::string ev = "_e" + std::to_string(idx);
+                    d.loops.push_back({ev, lo, hi});
+                    auto lhs = std::make_shared<Expr>(*d.lhs);
+                    lhs->a[rdim] = mk_var(ev);
+                    d.lhs = lhs;
+                    std::function<EP(const EP&)> scal = [&](const EP& e) -> EP {
+                        auto r = std::make_shared<Expr>(*e);
+                        if (e->k == Expr::CALL && (e->name == "inprod" || e->name == "sum"))
+                            throw Error("vector reductions inside vector declarations are not supported");
+                        for (auto& x : r->a) {
+                            if (e->k == Expr::VAR && x->k == Expr::RANGE) {
+                                long l2 = (long)std::llround(ceval(x->a[0], {}));
+                                x = mk_bin('+', mk_var(ev), mk_num((double)(l2 - lo)));
+                            } else {
+                                x = scal(x);
+                            }
+                        }
+                        return r;
+                    };
+                    rhs = scal(rhs);
+                }
+                d.args = {rhs};
+            }
+            d.ninst = 1;
+            for (auto& l : d.loops) d.ninst *= (l.hi - l.lo + 1);
+            if (d.loops.size() > 3) throw Error("more than 3 nested loops are not supported");
+            decls.push_back(d);
+            idx++;
+        }
+    }
+
+    // ------------------------------------------------------------------ variables
+    void build_vars() {
+        for (auto& d : decls) {
+            const std::string& name = d.lhs->name;
+            Var::Role role = d.stoch ? (spec.data.count(name) ? Var::DATA : Var::PARAM) : Var::DET;
+            const Array* src = nullptr;
+            if (role == Var::DATA) src = &spec.data.at(name);
+            if (role == Var::PARAM && spec.inits.count(name)) src = &spec.inits.at(name);
+            std::vector<int64_t> dims;
+            if (src && !(src->dims.empty())) dims = src->dims;
+            else {
+                // extent of the LHS indices over the loop ranges
+                for (auto& ix : d.lhs->a) {
+                    if (ix->k == Expr::RANGE) { dims.push_back((int64_t)std::llround(ceval(ix->a[1], {}))); continue; }
+                    double best = 0;
+                    // evaluate at loop corners
+                    size_t nl = d.loops.size();
+                    for (size_t mask = 0; mask < (1u << nl); mask++) {
+                        std::map<std::string, double> env;
+                        for (size_t l = 0; l < nl; l++) env[d.loops[l].var] = (mask >> l & 1) ? d.loops[l].hi : d.loops[l].lo;
+                        best = std::max(best, ceval(ix, env));
+                    }
+                    dims.push_back((int64_t)std::llround(best));
+                }
+            }
+            auto it = vars.find(name);
+            if (it == vars.end()) {
+                Var v;
+                v.name = name; v.role = role; v.dims = dims; v.arr = src;
+                vars[name] = v;
+                if (role == Var::PARAM) param_order.push_back(name);
+            } else {
+                if (it->second.role != role) throw Error("variable '" + name + "' is declared with mixed roles");
+                if (!src)
+                    for (size_t k = 0; k < dims.size() && k < it->second.dims.size(); k++)
+                        it->second.dims[k] = std::max(it->second.dims[k], dims[k]);
+            }
+        }
+        auto add_const = [&](const std::map<std::string, Array>& m) {
+            for (auto& kv : m)
+                if (!vars.count(kv.first) && kv.second.size() > 1) {
+                    Var v;
+                    v.name = kv.first; v.role = Var::CONST; v.dims = kv.second.dims; v.arr = &kv.second;
+                    vars[kv.first] = v;
+                }
+        };
+        add_const(spec.constants);
+        add_const(spec.data);  // right-hand-side-only "data" (covariates) behave as constants
+        P = 0;
+        for (auto& kv : vars) {
+            Var& v = kv.second;
+            v.size = 1;
+            for (auto dd : v.dims) v.size *= dd;
+            if (v.arr && v.arr->size() != v.size)
+                throw Error("array '" + v.name + "' has " + std::to_string(v.arr->size()) + " values but the model needs " + std::to_string(v.size));
+        }
+        for (auto& n : param_order) {
+            Var& v = vars[n];
+            if (!v.arr) throw Error("no initial values for parameter '" + n + "' (pass them as inits)");
+            v.theta_off = P;
+            P += (int)v.size;
+        }
+        ND = 0;
+        for (size_t i = 0; i < decls.size(); i++)
+            if (decls[i].stoch) {
+                decls[i].lpidx = ND++;
+                decls[i].lhs_param = vars[decls[i].lhs->name].role == Var::PARAM;
+                stoch_decls.push_back((int)i);
+            }
+    }
+
+    // ------------------------------------------------------------------ deterministic-node inlining
+    EP inline_det(const EP& e, int depth = 0) const {
+        if (depth > 32) throw Error("deterministic nodes nest too deeply (cycle?)");
+        if (e->k == Expr::VAR) {
+            auto it = vars.find(e->name);
+            if (it != vars.end() && it->second.role == Var::DET) {
+                for (auto& ix : e->a)
+                    if (ix->k == Expr::RANGE) return e;  // vector context: expanded element-wise by the caller
+                // find the declaration that defines this element
+                const CDecl* best = nullptr;
+                std::map<std::string, EP> bind;
+                int nmatch = 0;
+                for (auto& d : decls) {
+                    if (d.stoch || d.lhs->name != e->name) continue;
+                    if (d.lhs->a.size() != e->a.size()) continue;
+                    std::map<std::string, EP> b;
+                    bool ok = true;
+                    for (size_t k = 0; k < e->a.size() && ok; k++) {
+                        const EP& li = d.lhs->a[k];
+                        if (li->k == Expr::VAR && li->a.empty()) {
+                            bool isloop = false;
+                            for (auto& l : d.loops)
+                                if (l.var == li->name) isloop = true;
+                            if (isloop) { b[li->name] = inline_det(e->a[k], depth + 1); continue; }
+                        }
+                        double lv, rv;
+                        if (try_ceval(li, {}, lv)) {
+                            if (try_ceval(e->a[k], {}, rv)) ok = (lv == rv);
+                            else ok = false;  // cannot decide statically
+                        } else {
+                            throw Error("unsupported index pattern on the left-hand side of deterministic node '" + e->name + "'");
+                        }
+                    }
+                    if (ok) { best = &d; bind = b; nmatch++; }
+                }
+                if (!best) throw Error("no deterministic declaration matches " + to_string(e));
+                if (nmatch > 1) {
+                    // several loop-declared pieces: choose by constant index range if possible
+                    nmatch = 0;
+                    for (auto& d : decls) {
+                        if (d.stoch || d.lhs->name != e->name) continue;
+                        bool ok = true;
+                        std::map<std::string, EP> b;
+                        for (size_t k = 0; k < e->a.size() && ok; k++) {
+                            const EP& li = d.lhs->a[k];
+                            double rv;
+                            if (li->k == Expr::VAR && li->a.empty()) {
+                                const LoopC* lc = nullptr;
+                                for (auto& l : d.loops) if (l.var == li->name) lc = &l;
+                                if (lc) {
+                                    if (try_ceval(e->a[k], {}, rv)) ok = rv >= lc->lo && rv <= lc->hi;
+                                    b[li->name] = inline_det(e->a[k], depth + 1);
+                                    continue;
+                                }
+                            }
+                            double lv;
+                            if (try_ceval(li, {}, lv) && try_ceval(e->a[k], {}, rv)) ok = lv == rv; else ok = false;
+                        }
+                        if (ok) { best = &d; bind = b; nmatch++; }
+                    }
+                    if (nmatch != 1) throw Error("ambiguous deterministic declaration for " + to_string(e));
+                }
+                EP body = substitute(best->args[0], bind);
+                return inline_det(body, depth + 1);
+            }
+        }
+        auto r = std::make_shared<Expr>(*e);
+        for (auto& x : r->a) x = inline_det(x, depth);
+        for (auto& x : r->kw) x.second = inline_det(x.second, depth);
+        return r;
+    }
+
+    // element e (0-based) of a vector-valued argument (a slice  v[.., lo:hi, ..]  or a whole vector)
+    std::vector<EP> vector_elements(const EP& e) const {
+        if (e->k != Expr::VAR) throw Error("vector argument must be a variable slice: " + to_string(e));
+        auto it = vars.find(e->name);
+        std::vector<EP> out;
+        int rdim = -1;
+        for (size_t k = 0; k < e->a.size(); k++)
+            if (e->a[k]->k == Expr::RANGE) rdim = (int)k;
+        if (e->a.empty()) {
+            int64_t n = it != vars.end() ? it->second.size : 0;
+            const Array* c = find_const(e->name);
+            if (it == vars.end() && c) n = c->size();
+            for (int64_t i = 0; i < n; i++) out.push_back(mk_var(e->name, {mk_num((double)(i + 1))}));
+            return out;
+        }
+        if (rdim < 0) throw Error("expected a vector slice: " + to_string(e));
+        long lo = (long)std::llround(ceval(e->a[rdim]->a[0], {})), hi = (long)std::llround(ceval(e->a[rdim]->a[1], {}));
+        for (long i = lo; i <= hi; i++) {
+            auto r = std::make_shared<Expr>(*e);
+            r->a[rdim] = mk_num((double)i);
+            out.push_back(r);
+        }
+        return out;
+    }
+
+    void inline_all() {
+        for (auto& d : decls) {
+            if (!d.stoch) continue;
+            if (d.dist == "dmnorm") {
+                for (auto& el : vector_elements(d.args[0])) d.mean_elems.push_back(inline_det(el));
+                d.mvn_n = (int)d.mean_elems.size();
+                if (d.mvn_n < 1 || d.mvn_n > 8) throw Error("dmnorm dimension must be between 1 and 8");
+                const EP& ch = d.args[1];
+                if (ch->k != Expr::VAR) throw Error("cholesky= must be a matrix variable");
+                long r0 = 1, c0 = 1;
+                if (!ch->a.empty()) {
+                    if (ch->a.size() != 2 || ch->a[0]->k != Expr::RANGE || ch->a[1]->k != Expr::RANGE)
+                        throw Error("cholesky= must be given as M[a:b, c:d]");
+                    r0 = (long)std::llround(ceval(ch->a[0]->a[0], {}));
+                    c0 = (long)std::llround(ceval(ch->a[1]->a[0], {}));
+                }
+                for (int j = 0; j < d.mvn_n; j++)
+                    for (int i = 0; i < d.mvn_n; i++)
+                        d.chol_elems.push_back(inline_det(mk_var(ch->name, {mk_num((double)(r0 + i)), mk_num((double)(c0 + j))})));
+                // reorder: chol_elems is filled column by column -> index i + j*n
+                d.iargs = {inline_det(d.args[2])};
+                int ln = 0;
+                for (auto& ix : d.lhs->a)
+                    if (ix->k == Expr::RANGE) ln = (int)(std::llround(ceval(ix->a[1], {})) - std::llround(ceval(ix->a[0], {})) + 1);
+                if (ln != d.mvn_n) throw Error("dmnorm: node and mean have different lengths");
+            } else {
+                for (auto& a : d.args) d.iargs.push_back(inline_det(a));
+            }
+        }
+    }
+
+    // ------------------------------------------------------------------ dependency analysis
+    void collect_param_reads(const EP& e, std::vector<EP>& acc) const {
+        if (e->k == Expr::VAR) {
+            auto it = vars.find(e->name);
+            if (it != vars.end() && it->second.role == Var::PARAM) acc.push_back(e);
+        }
+        for (auto& x : e->a) collect_param_reads(x, acc);
+        for (auto& x : e->kw) collect_param_reads(x.second, acc);
+    }
+    bool depends_on_loops(const EP& e, const CDecl& d) const {
+        if (e->k == Expr::VAR && e->a.empty())
+            for (auto& l : d.loops)
+                if (l.var == e->name) return true;
+        for (auto& x : e->a)
+            if (depends_on_loops(x, d)) return true;
+        return false;
+    }
+    void inst_env(const CDecl& d, long inst, std::map<std::string, double>& env) const {
+        for (auto& l : d.loops) {
+            long n = l.hi - l.lo + 1;
+            env[l.var] = (double)(l.lo + inst % n);
+            inst /= n;
+        }
+    }
+    // theta elements (relative to the variable) touched by a reference at a given instance
+    void ref_elements(const Var& v, const EP& ref, const std::map<std::string, double>& env, std::vector<int64_t>& out) const {
+        out.clear();
+        if (ref->a.empty()) {
+            for (int64_t i = 0; i < v.size; i++) out.push_back(i);
+            return;
+        }
+        if (ref->a.size() != v.dims.size()) throw Error("wrong number of indices: " + to_string(ref));
+        std::vector<int64_t> cur = {0};
+        int64_t stride = 1;
+        for (size_t k = 0; k < ref->a.size(); k++) {
+            long lo, hi;
+            if (ref->a[k]->k == Expr::RANGE) {
+                lo = (long)std::llround(ceval(ref->a[k]->a[0], env));
+                hi = (long)std::llround(ceval(ref->a[k]->a[1], env));
+            } else {
+                lo = hi = (long)std::llround(ceval(ref->a[k], env));
+            }
+            if (lo < 1 || hi > v.dims[k]) throw Error("index out of range: " + to_string(ref));
+            std::vector<int64_t> nxt;
+            for (auto base : cur)
+                for (long i = lo; i <= hi; i++) nxt.push_back(base + (i - 1) * stride);
+            cur.swap(nxt);
+            stride *= v.dims[k];
+        }
+        out = cur;
+    }
+
+    void build_patterns() {
+        patterns.resize(decls.size());
+        for (int di : stoch_decls) {
+            CDecl& d = decls[di];
+            std::vector<EP> reads;
+            for (auto& a : d.iargs) collect_param_reads(a, reads);
+            for (auto& a : d.mean_elems) collect_param_reads(a, reads);
+            for (auto& a : d.chol_elems) collect_param_reads(a, reads);
+            std::set<std::string> seen;
+            for (auto& r : reads) {
+                std::string key = to_string(r);
+                if (!seen.insert(key).second) continue;
+                Pattern p;
+                p.v = &vars.at(r->name);
+                p.ref = r;
+                p.own = false;
+                p.loop_dep = depends_on_loops(r, d);
+                patterns[di].push_back(p);
+            }
+            if (d.lhs_param) {
+                Pattern p;
+                p.v = &vars.at(d.lhs->name);
+                p.ref = d.lhs;
+                p.own = true;
+                p.loop_dep = depends_on_loops(d.lhs, d);
+                patterns[di].push_back(p);
+            }
+        }
+    }
+    void build_inverse(int di, Pattern& p) {
+        if (p.built) return;
+        const CDecl& d = decls[di];
+        p.by_elem.assign((size_t)p.v->size, {});
+        std::map<std::string, double> env;
+        std::vector<int64_t> els;
+        for (long inst = 0; inst < d.ninst; inst++) {
+            inst_env(d, inst, env);
+            ref_elements(*p.v, p.ref, env, els);
+            for (auto e : els) p.by_elem[(size_t)e].push_back((int)inst);
+        }
+        p.built = true;
+    }
+
+    std::vector<Group> dependencies(const std::vector<int>& tgt) {
+        std::vector<char> inT((size_t)P, 0);
+        for (int t : tgt) inT[(size_t)t] = 1;
+        std::vector<Group> groups;
+        for (int di : stoch_decls) {
+            const CDecl& d = decls[di];
+            std::vector<char> own((size_t)d.ninst, 0), dep((size_t)d.ninst, 0);
+            bool all_dep = false;
+            for (auto& p : patterns[di]) {
+                const int64_t base = p.v->theta_off;
+                bool touches = false;
+                for (int t : tgt)
+                    if (t >= base && t < base + p.v->size) touches = true;
+                if (!touches) continue;
+                if (!p.loop_dep) {
+                    std::vector<int64_t> els;
+                    ref_elements(*p.v, p.ref, {}, els);
+                    bool hit = false;
+                    for (auto e : els) hit |= inT[(size_t)(base + e)] != 0;
+                    if (hit) {
+                        if (p.own) std::fill(own.begin(), own.end(), 1);
+                        else all_dep = true;
+                    }
+                } else {
+                    build_inverse(di, p);
+                    for (int t : tgt) {
+                        if (t < base || t >= base + p.v->size) continue;
+                        for (int inst : p.by_elem[(size_t)(t - base)]) (p.own ? own : dep)[(size_t)inst] = 1;
+                    }
+                }
+            }
+            Group gp{di, false, true, {}}, gd{di, false, false, {}};
+            for (long i = 0; i < d.ninst; i++) {
+                if (own[(size_t)i]) gp.inst.push_back((int)i);
+                else if (all_dep || dep[(size_t)i]) gd.inst.push_back((int)i);
+            }
+            if (!gp.inst.empty()) {
+                gp.full = (long)gp.inst.size() == d.ninst;
+                groups.push_back(gp);
+            }
+            if (!gd.inst.empty()) {
+                gd.full = (long)gd.inst.size() == d.ninst;
+                groups.push_back(gd);
+            }
+        }
+        return groups;
+    }
+
+    // ------------------------------------------------------------------ targets
+    std::vector<int> expand_target(const std::string& text) const {
+        // "a[1:3]", "a", "c('a','b[2]')" and comma-separated lists
+        std::string s = text;
+        std::vector<std::string> parts;
+        {
+            std::string t = s;
+            size_t c = t.find("c(");
+            if (c == 0 && t.back() == ')') t = t.substr(2, t.size() - 3);
+            int depth = 0;
+            std::string cur;
+            for (char ch : t) {
+                if (ch == '[' || ch == '(') depth++;
+                if (ch == ']' || ch == ')') depth--;
+                if (ch == ',' && depth == 0) { parts.push_back(cur); cur.clear(); continue; }
+                if (ch == '\'' || ch == '"' || ch == ' ') continue;
+                cur += ch;
+            }
+            if (!cur.empty()) parts.push_back(cur);
+        }
+        std::vector<int> out;
+        for (auto& part : parts) {
+            EP e = parse_expr_text(part);
+            if (e->k != Expr::VAR) throw Error("cannot parse node name '" + part + "'");
+            auto it = vars.find(e->name);
+            if (it == vars.end()) throw Error("unknown node '" + e->name + "'");
+            if (it->second.role != Var::PARAM) throw Error("'" + e->name + "' is not a sampled (non-data stochastic) node");
+            std::vector<int64_t> els;
+            ref_elements(it->second, e, {}, els);
+            for (auto el : els) out.push_back((int)(it->second.theta_off + el));
+        }
+        return out;
+    }
+    std::vector<std::string> theta_names() const {
+        std::vector<std::string> out;
+        for (auto& n : param_order) {
+            const Var& v = vars.at(n);
+            for (int64_t e = 0; e < v.size; e++) {
+                if (v.size == 1 && v.dims.empty()) out.push_back(v.name);
+                else if (v.dims.size() <= 1) out.push_back(v.name + "[" + std::to_string(e + 1) + "]");
+                else out.push_back(v.name + "[" + std::to_string(e % v.dims[0] + 1) + ", " + std::to_string(e / v.dims[0] + 1) + "]");
+            }
+        }
+        return out;
+    }
+
+    // ------------------------------------------------------------------ samplers -> units
+    static bool same_ctl(const apt_sampler_control& a, const apt_sampler_control& b) {
+        return a.log == b.log && a.reflective == b.reflective && a.adaptive == b.adaptive && a.adaptScaleOnly == b.adaptScaleOnly &&
+               a.adaptInterval == b.adaptInterval && a.adaptFactorExponent == b.adaptFactorExponent && a.scale == b.scale &&
+               a.temperPriors == b.temperPriors;
+    }
+    int add_iarray(const std::vector<int>& v) {
+        iarrays.push_back(v);
+        return (int)iarrays.size() - 1;
+    }
+
+    void set_bounds(Unit& u, int tgt) {
+        // model$getBound(target, 'lower' | 'upper')  (APT:702-703) from the target's own distribution
+        for (int di : stoch_decls) {
+            const CDecl& d = decls[di];
+            if (!d.lhs_param) continue;
+            const Var& v = vars.at(d.lhs->name);
+            if (tgt < v.theta_off || tgt >= v.theta_off + v.size) continue;
+            std::map<std::string, double> env;
+            std::vector<int64_t> els;
+            for (long inst = 0; inst < d.ninst; inst++) {
+                inst_env(d, inst, env);
+                ref_elements(v, d.lhs, env, els);
+                for (auto e : els)
+                    if (v.theta_off + e == tgt) {
+                        u.bound_env = env;
+                        if (d.dist == "dunif") { u.lower = d.iargs[0]; u.upper = d.iargs[1]; }
+                        else if (d.dist == "dgamma" || d.dist == "dexp") { u.lower = mk_num(0); u.upper = mk_num(INFINITY); }
+                        else if (d.dist == "dbeta") { u.lower = mk_num(0); u.upper = mk_num(1); }
+                        else { u.lower = mk_num(-INFINITY); u.upper = mk_num(INFINITY); }
+                        return;
+                    }
+            }
+        }
+        throw Error("target has no stochastic declaration");
+    }
+
+    void build_units() {
+        const auto& S = spec.samplers;
+        if (S.empty()) throw Error("no samplers configured: add sampler_RW_tempered / sampler_RW_block_tempered samplers");
+        int unit = 0, blkoff = 0, empoff = 0;
+        size_t s = 0;
+        while (s < S.size()) {
+            const SamplerConf& sc = S[s];
+            int kind;
+            if (sc.type == "sampler_RW_tempered" || sc.type == "RW_tempered") kind = 0;
+            else if (sc.type == "sampler_RW_block_tempered" || sc.type == "RW_block_tempered") kind = 1;
+            else throw Error("unsupported sampler type '" + sc.type + "' (supported: sampler_RW_tempered, sampler_RW_block_tempered)");
+            if (sc.ctl.temperPriors < 0)  // APT:660, APT:781
+                throw Error("control$temperPriors unspecified in " + std::string(kind == 0 ? "sampler_RW_tempered" : "sampler_RW_block_tempered"));
+            std::vector<int> tgt = expand_target(sc.target);
+            if (kind == 0 && tgt.size() > 1) throw Error("cannot use RW sampler on more than one target; try RW_block sampler");  // APT:682
+            if (kind == 0 && sc.ctl.log && sc.ctl.reflective)
+                throw Error("cannot use reflective RW sampler on a log scale (i.e. with options log=TRUE and reflective=TRUE");  // APT:684
+            if (sc.ctl.adaptFactorExponent < 0) throw Error("cannot use RW sampler with adaptFactorExponent control parameter less than 0");  // APT:685
+            if (sc.ctl.scale < 0) throw Error("cannot use RW sampler with scale control parameter less than 0");  // APT:686
+            if (sc.ctl.adaptInterval < 1) throw Error("adaptInterval must be >= 1");
+            Unit u;
+            u.kind = kind; u.d = (int)tgt.size(); u.unit0 = unit; u.count = 1; u.tgt = tgt; u.conf = &sc;
+            if (kind == 1) {
+                if (!sc.propCov.empty()) {
+                    if (sc.ctl.propCov_dim != u.d || (int)sc.propCov.size() != u.d * u.d)
+                        throw Error("propCov matrix must have dimension " + std::to_string(u.d) + "x" + std::to_string(u.d));  // APT:816
+                    for (int i = 0; i < u.d; i++)
+                        for (int j = 0; j < i; j++)
+                            if (std::fabs(sc.propCov[i + j * u.d] - sc.propCov[j + i * u.d]) > 1e-10 * (std::fabs(sc.propCov[i + j * u.d]) + 1e-300))
+                                throw Error("propCov matrix must be symmetric");  // APT:817
+                }
+                u.blkoff = blkoff; blkoff += 3 * u.d * u.d;
+                u.empoff = empoff;
+                if (sc.ctl.adaptive && !sc.ctl.adaptScaleOnly) empoff += sc.ctl.adaptInterval * u.d;
+            }
+            // family detection: a run of scalar samplers on consecutive theta elements with identical control
+            size_t e = s + 1;
+            std::vector<std::vector<Group>> member_groups;
+            if (kind == 0 && !sc.ctl.reflective) {
+                while (e < S.size()) {
+                    const SamplerConf& nx = S[e];
+                    if (nx.type != sc.type || !same_ctl(nx.ctl, sc.ctl)) break;
+                    std::vector<int> t2;
+                    try { t2 = expand_target(nx.target); } catch (const Error&) { break; }
+                    if (t2.size() != 1 || t2[0] != tgt[0] + (int)(e - s)) break;
+                    e++;
+                }
+                if (e - s >= 4) {
+                    bool ok = true;
+                    for (size_t m = s; m < e && ok; m++) {
+                        auto g = dependencies({tgt[0] + (int)(m - s)});
+                        for (auto& gg : g)
+                            if (gg.full && decls[gg.decl].ninst > 1) ok = false;
+                        if (!member_groups.empty()) {
+                            if (g.size() != member_groups[0].size()) ok = false;
+                            else
+                                for (size_t q = 0; q < g.size(); q++)
+                                    if (g[q].decl != member_groups[0][q].decl || g[q].prior != member_groups[0][q].prior) ok = false;
+                        }
+                        member_groups.push_back(std::move(g));
+                    }
+                    if (ok) {  // disjointness of the members' instance sets, declaration by declaration
+                        for (size_t q = 0; q < member_groups[0].size() && ok; q++) {
+                            std::vector<char> seen((size_t)decls[member_groups[0][q].decl].ninst, 0);
+                            // the same declaration may appear as prior and as dependent: share the marks
+                            for (size_t q2 = 0; q2 < member_groups[0].size(); q2++) {
+                                if (member_groups[0][q2].decl != member_groups[0][q].decl) continue;
+                                for (auto& mg : member_groups)
+                                    for (int inst : mg[q2].inst) {
+                                        if (seen[(size_t)inst] && q2 == q) ok = false;
+                                        if (q2 == q) seen[(size_t)inst] = 1;
+                                    }
+                            }
+                        }
+                    }
+                    if (!ok) { member_groups.clear(); e = s + 1; }
+                } else {
+                    e = s + 1;
+                }
+            }
+            if (!member_groups.empty()) {
+                u.count = (int)(e - s);
+                u.groups = member_groups[0];
+                for (size_t q = 0; q < u.groups.size(); q++) {
+                    std::vector<int> ptr = {0}, idx;
+                    for (auto& mg : member_groups) {
+                        for (int inst : mg[q].inst) idx.push_back(inst);
+                        ptr.push_back((int)idx.size());
+                    }
+                    u.groups[q].full = false;
+                    u.ia_ptr.push_back(add_iarray(ptr));
+                    u.ia_idx.push_back(add_iarray(idx));
+                }
+            } else {
+                u.groups = dependencies(tgt);
+                for (auto& g : u.groups) {
+                    int id = -1;
+                    if (!g.full && g.inst.size() > 1) {
+                        bool ap = true;
+                        int step = g.inst[1] - g.inst[0];
+                        for (size_t i = 2; i < g.inst.size(); i++) ap &= (g.inst[i] - g.inst[i - 1] == step);
+                        if (!(ap && decls[g.decl].loops.size() == 1)) id = add_iarray(g.inst);
+                    }
+                    u.ia_list.push_back(id);
+                }
+                if (kind == 0 && sc.ctl.reflective) set_bounds(u, tgt[0]);
+            }
+            if (u.groups.empty()) throw Error("sampler target '" + sc.target + "' has no stochastic dependencies");
+            unit += u.count;
+            units.push_back(std::move(u));
+            s = e;
+        }
+        NU = unit; BLKSZ = blkoff; EMPSZ = empoff;
+    }
+    int NU = 0, BLKSZ = 0, EMPSZ = 0;
+
+    // ------------------------------------------------------------------ expression code generation
+    using Env = std::map<std::string, std::string>;  // loop variable -> C int expression
+
+    int use_array(const Var& v) {
+        Var& mv = vars.at(v.name);
+        if (mv.arr_idx < 0) {
+            mv.arr_idx = (int)used_arrays.size();
+            used_arrays.push_back(mv.arr);
+        }
+        return mv.arr_idx;
+    }
+    bool const_indices(const EP& e, long* idx) const {
+        for (size_t k = 0; k < e->a.size(); k++) {
+            double v;
+            if (e->a[k]->k == Expr::RANGE || !try_ceval(e->a[k], {}, v)) return false;
+            idx[k] = (long)std::llround(v);
+        }
+        return true;
+    }
+    std::string gen_int(const EP& e, const Env& env) {
+        double cv;
+        if (try_ceval(e, {}, cv)) {
+            if (cv != std::floor(cv)) throw Error("non-integer index: " + to_string(e));
+            return std::to_string((long)cv);
+        }
+        switch (e->k) {
+            case Expr::VAR:
+                if (e->a.empty()) {
+                    auto it = env.find(e->name);
+                    if (it != env.end()) return it->second;
+                    throw Error("unknown index variable '" + e->name + "'");
+                } else {
+                    auto it = vars.find(e->name);
+                    if (it == vars.end() || (it->second.role != Var::CONST && it->second.role != Var::DATA))
+                        throw Error("index expressions may only use loop variables and constants: " + to_string(e));
+                    return "(int)" + gen_load(it->second, e, env);
+                }
+            case Expr::BIN:
+                if (e->op == '+' || e->op == '-' || e->op == '*')
+                    return "(" + gen_int(e->a[0], env) + " " + e->op + " " + gen_int(e->a[1], env) + ")";
+                break;
+            case Expr::NEG: return "(-" + gen_int(e->a[0], env) + ")";
+            default: break;
+        }
+        throw Error("unsupported index expression: " + to_string(e));
+    }
+    std::string gen_offset(const Var& v, const EP& e, const Env& env) {
+        if (e->a.empty()) {
+            if (v.size != 1) throw Error("whole-array use of '" + v.name + "' where a scalar is required");
+            return "0";
+        }
+        if (e->a.size() != v.dims.size()) throw Error("wrong number of indices: " + to_string(e));
+        long ci[4];
+        if (const_indices(e, ci)) {
+            int64_t off = 0, stride = 1;
+            for (size_t k = 0; k < e->a.size(); k++) {
+                if (ci[k] < 1 || ci[k] > v.dims[k]) throw Error("index out of range: " + to_string(e));
+                off += (ci[k] - 1) * stride;
+                stride *= v.dims[k];
+            }
+            return std::to_string(off);
+        }
+        std::string s;
+        int64_t stride = 1;
+        for (size_t k = 0; k < e->a.size(); k++) {
+            if (e->a[k]->k == Expr::RANGE) throw Error("vector slice used where a scalar is required: " + to_string(e));
+            std::string term = "(" + gen_int(e->a[k], env) + " - 1)";
+            if (stride != 1) term += " * " + std::to_string(stride);
+            s += (k ? " + " : "") + term;
+            stride *= v.dims[k];
+        }
+        return s;
+    }
+    std::string gen_load(const Var& v, const EP& e, const Env& env) {
+        if (v.role == Var::PARAM) {
+            std::string off = gen_offset(v, e, env);
+            return "th[" + std::to_string(v.theta_off) + " + " + off + "]";
+        }
+        if (v.role == Var::CONST && v.size <= 64) {  // small constants are folded into the code
+            long ci[4];
+            if (const_indices(e, ci)) return fmt_d(ceval(e, {}));
+        }
+        int ai = use_array(v);
+        return "D.a[" + std::to_string(ai) + "][" + gen_offset(v, e, env) + "]";
+    }
+    std::string gen_slice_elem(const EP& sl, const std::string& ev, const Env& env, int& len) {
+        // element `ev` (C int, 0-based) of the slice  v[.., lo:hi, ..]
+        if (sl->k != Expr::VAR) throw Error("inprod/sum arguments must be variable slices: " + to_string(sl));
+        auto it = vars.find(sl->name);
+        if (it == vars.end()) throw Error("unknown variable '" + sl->name + "'");
+        const Var& v = it->second;
+        if (v.role == Var::DET) throw Error("slices of deterministic nodes inside inprod/sum are not supported: " + to_string(sl));
+        auto ref = std::make_shared<Expr>(*sl);
+        int rdim = -1;
+        if (ref->a.empty()) {
+            if (v.dims.size() > 1) throw Error("whole-matrix argument in inprod/sum");
+            len = (int)v.size;
+            ref->a = {mk_bin('+', mk_var("_sl"), mk_num(1))};
+        } else {
+            for (size_t k = 0; k < ref->a.size(); k++)
+                if (ref->a[k]->k == Expr::RANGE) rdim = (int)k;
+            if (rdim < 0) throw Error("expected a slice: " + to_string(sl));
+            long lo = (long)std::llround(ceval(ref->a[rdim]->a[0], {})), hi = (long)std::llround(ceval(ref->a[rdim]->a[1], {}));
+            len = (int)(hi - lo + 1);
+            ref->a[rdim] = mk_bin('+', mk_var("_sl"), mk_num((double)lo));
+        }
+        Env e2 = env;
+        e2["_sl"] = ev;
+        return gen_load(v, ref, e2);
+    }
+    int tmp_id = 0;
+    std::string gen_dbl(const EP& e, const Env& env) {
+        double cv;
+        if (try_ceval(e, {}, cv)) return fmt_d(cv);
+        switch (e->k) {
+            case Expr::NUM: return fmt_d(e->num);
+            case Expr::NEG: return "(-" + gen_dbl(e->a[0], env) + ")";
+            case Expr::BIN: {
+                if (e->op == '^') {
+                    double ex;
+                    if (try_ceval(e->a[1], {}, ex) && ex == 2.0) return "apt_sq(" + gen_dbl(e->a[0], env) + ")";
+                    return "pow(" + gen_dbl(e->a[0], env) + ", " + gen_dbl(e->a[1], env) + ")";
+                }
+                return "(" + gen_dbl(e->a[0], env) + " " + e->op + " " + gen_dbl(e->a[1], env) + ")";
+            }
+            case Expr::VAR: {
+                if (e->a.empty()) {
+                    auto it = env.find(e->name);
+                    if (it != env.end()) return "(double)" + it->second;
+                }
+                auto it = vars.find(e->name);
+                if (it == vars.end()) throw Error("unknown variable '" + e->name + "'");
+                if (it->second.role == Var::DET) return gen_dbl(inline_det(e), env);
+                return gen_load(it->second, e, env);
+            }
+            case Expr::CALL: {
+                static const std::map<std::string, std::string> f1 = {
+                    {"exp", "exp"}, {"log", "log"}, {"abs", "fabs"}, {"sqrt", "sqrt"}, {"ilogit", "apt::ilogit"}, {"expit", "apt::ilogit"},
+                    {"logit", "apt::logit"}, {"phi", "apt::iprobit"}, {"iprobit", "apt::iprobit"}, {"icloglog", "apt::icloglog"},
+                    {"cloglog", "apt::cloglog"}, {"log1p", "log1p"}, {"step", "apt::stepfn"}, {"lgamma", "lgamma"}, {"loggam", "lgamma"}};
+                auto it = f1.find(e->name);
+                if (it != f1.end()) {
+                    if (e->a.size() != 1) throw Error(e->name + "() takes one argument");
+                    return it->second + "(" + gen_dbl(e->a[0], env) + ")";
+                }
+                if (e->name == "pow" && e->a.size() == 2) return "pow(" + gen_dbl(e->a[0], env) + ", " + gen_dbl(e->a[1], env) + ")";
+                if ((e->name == "min" || e->name == "max") && e->a.size() == 2)
+                    return "f" + e->name + "(" + gen_dbl(e->a[0], env) + ", " + gen_dbl(e->a[1], env) + ")";
+                if (e->name == "inprod" && e->a.size() == 2) {
+                    int la = 0, lb = 0;
+                    std::string ev = "e" + std::to_string(tmp_id++);
+                    std::string A = gen_slice_elem(e->a[0], ev, env, la), B = gen_slice_elem(e->a[1], ev, env, lb);
+                    if (la != lb) throw Error("inprod arguments have different lengths: " + to_string(e));
+                    return "[&]() { double s_ = 0.0;\n_Pragma(\"unroll 5\")\n for (int " + ev + " = 0; " + ev + " < " + std::to_string(la) + "; ++" + ev +
+                           ") s_ += " + A + " * " + B + "; return s_; }()";
+                }
+                if (e->name == "sum" && e->a.size() == 1) {
+                    int la = 0;
+                    std::string ev = "e" + std::to_string(tmp_id++);
+                    std::string A = gen_slice_elem(e->a[0], ev, env, la);
+                    return "[&]() { double s_ = 0.0; for (int " + ev + " = 0; " + ev + " < " + std::to_string(la) + "; ++" + ev + ") s_ += " + A +
+                           "; return s_; }()";
+                }
+                throw Error("unsupported function '" + e->name + "' in model code");
+            }
+            default: break;
+        }
+        throw Error("unsupported expression: " + to_string(e));
+    }
+
+    // ------------------------------------------------------------------ emission
+    Env decl_env(const CDecl& d) const {
+        Env env;
+        for (size_t l = 0; l < d.loops.size(); l++) env[d.loops[l].var] = "L" + std::to_string(l);
+        return env;
+    }
+    // call expression of lp_d<di> for linear instance expression `lin` (C int, 0-based)
+    std::string lp_call(int di, const std::string& lin) const {
+        const CDecl& d = decls[di];
+        std::string a[3] = {"0", "0", "0"};
+        if (d.loops.size() == 1) a[0] = "(" + std::to_string(d.loops[0].lo) + " + " + lin + ")";
+        else if (d.loops.size() >= 2) {
+            long n0 = d.loops[0].hi - d.loops[0].lo + 1;
+            a[0] = "(" + std::to_string(d.loops[0].lo) + " + (" + lin + ") % " + std::to_string(n0) + ")";
+            if (d.loops.size() == 2) a[1] = "(" + std::to_string(d.loops[1].lo) + " + (" + lin + ") / " + std::to_string(n0) + ")";
+            else {
+                long n1 = d.loops[1].hi - d.loops[1].lo + 1;
+                a[1] = "(" + std::to_string(d.loops[1].lo) + " + ((" + lin + ") / " + std::to_string(n0) + ") % " + std::to_string(n1) + ")";
+                a[2] = "(" + std::to_string(d.loops[2].lo) + " + (" + lin + ") / " + std::to_string(n0 * n1) + ")";
+            }
+        }
+        return "lp_d" + std::to_string(di) + "(D, th, " + a[0] + ", " + a[1] + ", " + a[2] + ")";
+    }
+
+    bool is_call(const EP& e, const char* name) const { return e->k == Expr::CALL && e->name == name && e->a.size() == 1; }
+
+    void emit_lp_functions() {
+        for (int di : stoch_decls) {
+            CDecl& d = decls[di];
+            Env env = decl_env(d);
+            out << "  // line " << d.line << ": " << to_string(d.lhs) << " ~ " << d.dist << "(...)";
+            for (auto& l : d.loops) out << "  for " << l.var << " in " << l.lo << ":" << l.hi;
+            out << "\n";
+            out << "  __device__ static __forceinline__ double lp_d" << di << "(const Data& D, const double* th, int L0, int L1, int L2) {\n";
+            if (d.dist == "dmnorm") {
+                const int n = d.mvn_n;
+                int rdim = -1;
+                for (size_t k = 0; k < d.lhs->a.size(); k++)
+                    if (d.lhs->a[k]->k == Expr::RANGE) rdim = (int)k;
+                long lo = (long)std::llround(ceval(d.lhs->a[rdim]->a[0], {}));
+                out << "    const double x_[" << n << "] = {";
+                for (int e = 0; e < n; e++) {
+                    auto ref = std::make_shared<Expr>(*d.lhs);
+                    ref->a[rdim] = mk_num((double)(lo + e));
+                    out << (e ? ", " : "") << gen_dbl(ref, env);
+                }
+                out << "};\n    const double mu_[" << n << "] = {";
+                for (int e = 0; e < n; e++) out << (e ? ", " : "") << gen_dbl(d.mean_elems[e], env);
+                out << "};\n    const double U_[" << n * n << "] = {";
+                for (int e = 0; e < n * n; e++) out << (e ? ", " : "") << gen_dbl(d.chol_elems[e], env);
+                out << "};\n    return apt::dmnorm_chol_log<" << n << ">(x_, mu_, U_, (" << gen_dbl(d.iargs[0], env) << ") != 0.0);\n";
+            } else {
+                std::string x = gen_dbl(d.lhs, env);
+                if (d.dist == "dbinom" && opts.fuse_links && (is_call(d.iargs[0], "ilogit") || is_call(d.iargs[0], "expit"))) {
+                    double sz;
+                    if (try_ceval(d.iargs[1], {}, sz) && sz == 1.0) {
+                        out << "    // fused: dbinom(prob = ilogit(eta), size = 1)\n";
+                        out << "    return apt::bern_logit_log(" << x << ", " << gen_dbl(d.iargs[0]->a[0], env) << ");\n  }\n";
+                        continue;
+                    }
+                }
+                std::string fn = d.dist == "dnorm" ? "apt::dnorm_log" : d.dist == "dunif" ? "apt::dunif_log" : d.dist == "dgamma" ? "apt::dgamma_log"
+                               : d.dist == "dbeta" ? "apt::dbeta_log" : d.dist == "dbinom" ? "apt::dbinom_log" : d.dist == "dpois" ? "apt::dpois_log"
+                               : "apt::dexp_log";
+                out << "    return " << fn << "(" << x;
+                for (auto& a : d.iargs) out << ", " << gen_dbl(a, env);
+                out << ");\n";
+            }
+            out << "  }\n";
+        }
+    }
+
+    void emit_inst_loop(int di, const std::string& acc) {
+        const CDecl& d = decls[di];
+        if (d.ninst == 1) out << "    if (c.rank == 0) " << acc << " += " << lp_call(di, "0") << ";\n";
+        else
+            out << "    for (int q = c.rank; q < " << d.ninst << "; q += C::W) " << acc << " += " << lp_call(di, "q") << ";\n";
+    }
+
+    void emit_unit(size_t ui) {
+        Unit& u = units[ui];
+        const apt_sampler_control& ctl = u.conf->ctl;
+        const bool has_partial = std::any_of(u.groups.begin(), u.groups.end(), [](const Group& g) { return !g.full; });
+        out << "  // sampler unit(s) " << u.unit0 << ".." << (u.unit0 + u.count - 1) << ": " << u.conf->type << " on " << u.conf->target
+            << (u.count > 1 ? " ... (family of " + std::to_string(u.count) + ")" : "") << "\n";
+        out << "  struct S" << ui << " {\n";
+        out << "    static constexpr int KIND = " << u.kind << ", D = " << u.d << ", NG = " << u.groups.size() << ", UNIT0 = " << u.unit0
+            << ", COUNT = " << u.count << ", AI = " << ctl.adaptInterval << ", BLKOFF = " << u.blkoff << ", EMPOFF = " << u.empoff << ";\n";
+        out << "    static constexpr bool LOG = " << (ctl.log ? "true" : "false") << ", REFL = " << (ctl.reflective ? "true" : "false")
+            << ", ADAPT = " << (ctl.adaptive ? "true" : "false") << ", SCALE_ONLY = " << (ctl.adaptScaleOnly ? "true" : "false")
+            << ", TEMPER_PRIORS = " << (ctl.temperPriors ? "true" : "false") << ", HAS_PARTIAL = " << (has_partial ? "true" : "false") << ";\n";
+        out << "    static constexpr double AEXP = " << fmt_d(ctl.adaptFactorExponent) << ";\n";
+        auto sw = [&](const char* name, const char* type, std::function<std::string(const Group&)> f) {
+            out << "    __device__ static constexpr " << type << " " << name << "(int g) { return ";
+            for (size_t g = 0; g + 1 < u.groups.size(); g++) out << "g == " << g << " ? " << f(u.groups[g]) << " : ";
+            out << f(u.groups.back()) << "; }\n";
+        };
+        sw("gdecl", "int", [&](const Group& g) { return std::to_string(decls[g.decl].lpidx); });
+        sw("gfull", "bool", [&](const Group& g) { return std::string(g.full ? "true" : "false"); });
+        sw("gprior", "bool", [&](const Group& g) { return std::string(g.prior ? "true" : "false"); });
+        // targets
+        out << "    __device__ static __forceinline__ int tgt(int m, int j) { ";
+        bool contiguous = true;
+        for (size_t j = 1; j < u.tgt.size(); j++) contiguous &= (u.tgt[j] == u.tgt[0] + (int)j);
+        if (contiguous) out << "return " << u.tgt[0] << " + m + j; }\n";
+        else {
+            out << "switch (j) {";
+            for (size_t j = 0; j < u.tgt.size(); j++) out << " case " << j << ": return " << u.tgt[j] << ";";
+            out << " } return 0; }\n";
+        }
+        // bounds
+        {
+            Env env;
+            EP lo = u.lower, hi = u.upper;
+            if (lo) {
+                std::map<std::string, EP> b;
+                for (auto& kv : u.bound_env) b[kv.first] = mk_num(kv.second);
+                lo = substitute(lo, b); hi = substitute(hi, b);
+            }
+            out << "    __device__ static __forceinline__ double lower(const Data& D, const double* th, int m) { return "
+                << (lo ? gen_dbl(lo, env) : std::string("(-CUDART_INF)")) << "; }\n";
+            out << "    __device__ static __forceinline__ double upper(const Data& D, const double* th, int m) { return "
+                << (hi ? gen_dbl(hi, env) : std::string("CUDART_INF")) << "; }\n";
+        }
+        // eval
+        out << "    template <class C> __device__ static __forceinline__ void eval(const Data& D, const double* th, int m, const C& c, double* acc, bool newpass) {\n";
+        for (size_t g = 0; g < u.groups.size(); g++) {
+            const Group& gr = u.groups[g];
+            const CDecl& d = decls[gr.decl];
+            std::string acc = "acc[" + std::to_string(g) + "]";
+            out << "      // group " << g << ": declaration " << gr.decl << " (" << to_string(d.lhs) << " ~ " << d.dist << "), "
+                << (gr.full ? "FULL" : "PARTIAL") << (gr.prior ? ", target's own node(s)" : "") << "\n";
+            if (u.count > 1) {
+                out << "      { const int* ptr_ = D.ia[" << u.ia_ptr[g] << "]; const int* ix_ = D.ia[" << u.ia_idx[g] << "];\n";
+                out << "        for (int q = ptr_[m] + c.rank; q < ptr_[m + 1]; q += C::W) " << acc << " += " << lp_call(gr.decl, "ix_[q]") << "; }\n";
+            } else if (gr.full) {
+                out << "      if (newpass) {\n  ";
+                emit_inst_loop(gr.decl, acc);
+                out << "      }\n";
+            } else if (gr.inst.size() == 1) {
+                out << "      if (c.rank == 0) " << acc << " += " << lp_call(gr.decl, std::to_string(gr.inst[0])) << ";\n";
+            } else if (u.ia_list[g] >= 0) {
+                out << "      { const int* ix_ = D.ia[" << u.ia_list[g] << "];\n";
+                out << "        for (int q = c.rank; q < " << gr.inst.size() << "; q += C::W) " << acc << " += " << lp_call(gr.decl, "ix_[q]") << "; }\n";
+            } else {
+                int step = gr.inst[1] - gr.inst[0];
+                out << "      for (int q = c.rank; q < " << gr.inst.size() << "; q += C::W) " << acc << " += "
+                    << lp_call(gr.decl, std::to_string(gr.inst[0]) + " + q * " + std::to_string(step)) << ";\n";
+            }
+        }
+        out << "    }\n  };\n";
+    }
+
+    void choose_shape(int& W, int& tiles, int& teams, bool& smem_state) {
+        long ndep = 1, items = K;
+        for (auto& u : units) {
+            items = std::max<long>(items, (long)K * u.count);
+            for (auto& g : u.groups) {
+                long n = g.full ? decls[g.decl].ninst : (long)g.inst.size();
+                ndep = std::max(ndep, n);
+            }
+        }
+        if (opts.lanes_per_chain > 0) W = opts.lanes_per_chain;
+        else {
+            W = 1;
+            while (W < 32 && (long)W * 32 < ndep) W *= 2;
+            int kp = 1;
+            while (kp < K) kp *= 2;
+            while (W < 32 && (long)kp * W < 32) W *= 2;
+        }
+        if (W < 1 || W > 32 || (W & (W - 1))) throw Error("lanes_per_chain must be a power of two <= 32");
+        int maxthreads = opts.cta_threads > 0 ? opts.cta_threads : 512;
+        tiles = (int)std::min<long>(items, std::max(1, maxthreads / W));
+        int team_threads = ((tiles * W + 31) / 32) * 32;
+        teams = team_threads == 32 ? 4 : 1;
+        size_t bytes = (size_t)K * (P + ND) * 8 * teams;
+        smem_state = bytes <= 96 * 1024;
+    }
+
+    Lowered run() {
+        canonicalise();
+        build_vars();
+        inline_all();
+        build_patterns();
+        build_units();
+        // monitors
+        std::vector<int> mon, mon2;
+        auto names = theta_names();
+        std::vector<std::string> mon_names, mon2_names;
+        auto expand_mon = [&](const std::vector<std::string>& src, std::vector<int>& dst, std::vector<std::string>& dn) {
+            for (auto& m : src) {
+                if (m.find("logProb") != std::string::npos) throw Error("logProb monitors are not supported by the device engine: " + m);
+                for (int t : expand_target(m)) { dst.push_back(t); dn.push_back(names[(size_t)t]); }
+            }
+        };
+        expand_mon(spec.monitors, mon, mon_names);
+        expand_mon(spec.monitors2, mon2, mon2_names);
+        int DMAX = 1;
+        bool has_family = false;
+        for (auto& u : units) {
+            DMAX = std::max(DMAX, u.d);
+            has_family |= u.count > 1;
+            if (u.count > 1 && u.groups.size() > 4) throw Error("sampler families with more than 4 dependent declarations are not supported");
+        }
+        int W, tiles, teams;
+        bool smem_state;
+        choose_shape(W, tiles, teams, smem_state);
+
+        std::ostringstream body;
+        std::swap(out, body);  // emit model body first to learn which arrays are used
+        emit_lp_functions();
+        out << "  template <class C> __device__ static __forceinline__ void logprob_all(const Data& D, const double* th, const C& c, double* acc) {\n";
+        for (int di : stoch_decls) {
+            out << "  ";
+            emit_inst_loop(di, "acc[" + std::to_string(decls[di].lpidx) + "]");
+        }
+        out << "  }\n";
+        for (size_t ui = 0; ui < units.size(); ui++) emit_unit(ui);
+        // sweep: stages
+        out << "  template <class C> __device__ static __forceinline__ void sweep(C& c, const Data& D, bool active) {\n";
+        size_t ui = 0;
+        bool first = true;
+        while (ui < units.size()) {
+            if (!first) out << "    c.team_sync();\n";
+            first = false;
+            if (units[ui].count > 1) {
+                out << "    if (active) for (int it_ = c.tile_id; it_ < K * " << units[ui].count << "; it_ += c.ntiles) apt::rw_update<Model, S" << ui
+                    << ">(c, D, it_ / " << units[ui].count << ", it_ % " << units[ui].count << ");\n";
+                out << "    c.team_sync();\n    if (active) apt::family_commit<Model, S" << ui << ">(c);\n";
+                ui++;
+            } else {
+                out << "    if (active) for (int k = c.tile_id; k < K; k += c.ntiles) {\n";
+                while (ui < units.size() && units[ui].count == 1) {
+                    out << "      apt::rw_update<Model, S" << ui << ">(c, D, k, 0);\n";
+                    ui++;
+                }
+                out << "    }\n";
+            }
+        }
+        out << "  }\n";
+        std::swap(out, body);  // `body` now holds the model body; `out` is the file
+
+        out << "// Generated by the aptb200 lowering step (nimbleapt_b200/csrc/lower.cpp). Do not edit.\n";
+        out << "#include \"apt_host.cuh\"\n";
+        out << "__device__ __forceinline__ double apt_sq(double x) { return x * x; }\n";
+        out << "// unnamed namespace: every lowered model defines a type called aptgen::Model; internal linkage keeps the\n// template instantiations of different modules loaded into one process apart.\nnamespace {\nnamespace aptgen {\nusing apt::Data;\n";
+        auto emit_tab = [&](const char* name, const std::vector<int>& v) {
+            out << "__device__ const int " << name << "[" << std::max<size_t>(v.size(), 1) << "] = {";
+            for (size_t i = 0; i < v.size(); i++) out << (i ? ", " : "") << v[i];
+            if (v.empty()) out << "0";
+            out << "};\n";
+        };
+        emit_tab("MON_TAB", mon);
+        emit_tab("MON2_TAB", mon2);
+        for (size_t i = 0; i < units.size(); i++)
+            if (units[i].kind == 1 && !units[i].conf->propCov.empty()) {
+                out << "static const double PROPCOV" << i << "[" << units[i].conf->propCov.size() << "] = {";
+                for (size_t q = 0; q < units[i].conf->propCov.size(); q++) out << (q ? ", " : "") << fmt_d(units[i].conf->propCov[q]);
+                out << "};\n";
+            }
+        out << "struct Model {\n";
+        out << "  static constexpr int P = " << P << ", ND = " << ND << ", NU = " << NU << ", NSAMP = " << units.size() << ", K = " << K
+            << ", NMON = " << mon.size() << ", NMON2 = " << mon2.size() << ", DMAX = " << DMAX << ", W = " << W << ";\n";
+        out << "  static constexpr int NARR = " << used_arrays.size() << ", NIARR = " << iarrays.size() << ", BLKSZ = " << BLKSZ << ", EMPSZ = " << EMPSZ << ";\n";
+        out << "  static constexpr int TILES_PER_LADDER = " << tiles << ", TEAMS_PER_CTA = " << teams << ";\n";
+        out << "  static constexpr bool STATE_IN_SMEM = " << (smem_state ? "true" : "false") << ", HAS_FAMILY = " << (has_family ? "true" : "false") << ";\n";
+        out << "  __device__ static __forceinline__ int mon(int c) { return MON_TAB[c]; }\n";
+        out << "  __device__ static __forceinline__ int mon2(int c) { return MON2_TAB[c]; }\n";
+        out << body.str();
+        out << "  static const apt::HostSamplerInfo& sampler_info(int s) {\n    static const apt::HostSamplerInfo info[" << units.size() << "] = {\n";
+        for (size_t i = 0; i < units.size(); i++) {
+            const Unit& u = units[i];
+            out << "      {" << u.kind << ", " << u.d << ", " << u.unit0 << ", " << u.count << ", " << u.blkoff << ", " << u.empoff << ", "
+                << u.conf->ctl.adaptInterval << ", " << fmt_d(u.conf->ctl.scale) << ", "
+                << ((u.kind == 1 && !u.conf->propCov.empty()) ? "PROPCOV" + std::to_string(i) : std::string("nullptr")) << "},\n";
+        }
+        out << "    };\n    return info[s];\n  }\n};\n}  // namespace aptgen\n}  // namespace\nAPT_DEFINE_MODULE(aptgen::Model)\n";
+
+        Lowered L;
+        L.source = out.str();
+        L.P = P; L.K = K; L.NU = NU; L.ND = ND; L.NMON = (int)mon.size(); L.NMON2 = (int)mon2.size(); L.DMAX = DMAX; L.W = W; L.engine = 1;
+        for (auto* a : used_arrays) { L.arrays.push_back(a); L.array_names.push_back(a->name); }
+        L.iarrays = iarrays;
+        L.theta0.assign((size_t)P, 0.0);
+        for (auto& n : param_order) {
+            const Var& v = vars.at(n);
+            for (int64_t e = 0; e < v.size; e++) L.theta0[(size_t)(v.theta_off + e)] = v.arr->v[(size_t)e];
+        }
+        L.param_names = names; L.mon_names = mon_names; L.mon2_names = mon2_names;
+        return L;
+    }
+};
+
+}  // namespace
+
+Lowered lower_model(const ModelSpec& spec, int n_temps, const apt_build_opts& opts) {
+    if (n_temps < 2) throw Error("need at least 2 temperatures");
+    if (n_temps > 1024) throw Error("at most 1024 temperatures are supported");
+    Lowerer lw(spec, n_temps, opts);
+    return lw.run();
+}
+
+}  // namespace aptf

@@ -1,0 +1,75 @@
+"""CPU: the C-ABI library loads, exports every symbol include/aptb200.h declares, parses/lowers/compiles models
+without a GPU, and fails loudly (never silently falls back) when asked to compute without one."""
+import ctypes as C
+import os
+import re
+import numpy as np
+import pytest
+
+import models
+import nimbleapt_b200 as nb
+from nimbleapt_b200 import _lib
+from helpers import build_engine
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_exports_match_header():
+    hdr = open(os.path.join(ROOT, "include", "aptb200.h")).read()
+    declared = set(re.findall(r"\b(apt_[a-z_0-9]+)\s*\(", hdr))
+    declared -= {"apt_model", "apt_engine"}
+    L = C.CDLL(_lib.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(L, name), "libaptb200.so does not export " + name
+    assert declared == set(_lib.EXPORTS)
+
+
+def test_lowering_emits_expected_cuda():
+    spec = models.c4_glmm(G=20, per=10, K=4)
+    m = nb.nimbleModel(spec["code"], spec["constants"], spec["data"], spec["inits"])
+    h = C.c_void_p()
+    L = _lib.lib()
+    _lib.check(L.apt_model_create(spec["code"].encode(), C.byref(h)))
+    L.apt_model_free(h)
+    with pytest.raises(nb.AptError, match="parse error"):
+        nb.nimbleModel("{ y ~ dnorm(0, 1 }")
+    with pytest.raises(nb.AptError) as ei:
+        build_engine(dict(spec, code=spec["code"].replace("dpois", "dweib")))
+    assert "unsupported distribution" in str(ei.value)
+
+
+def test_no_gpu_means_loud_failure():
+    import torch  # only to learn whether this host has a GPU
+    if torch.cuda.is_available():
+        pytest.skip("host has a GPU")
+    with pytest.raises(nb.AptError, match="no CUDA device|no CPU fallback"):
+        build_engine(models.c2_mixture(K=4))
+
+
+def test_control_validation_mirrors_reference():
+    spec = models.c2_mixture(K=4)
+    m = nb.nimbleModel(spec["code"], spec["constants"], spec["data"], spec["inits"])
+    conf = nb.configureMCMC(m, monitors="theta")
+    conf.addSampler("theta[1]", type="sampler_RW_tempered", control={})
+    with pytest.raises(nb.AptError, match="temperPriors unspecified in sampler_RW_tempered"):  # APT:660
+        nb.buildAPT(conf, Temps=[1, 2, 3])
+    conf.removeSamplers()
+    conf.addSampler("theta[1:2]", type="sampler_RW_tempered", control=dict(temperPriors=True))
+    with pytest.raises(nb.AptError, match="more than one target"):  # APT:682
+        nb.buildAPT(conf, Temps=[1, 2, 3])
+    conf.removeSamplers()
+    conf.addSampler("theta[1]", type="sampler_RW_tempered", control=dict(temperPriors=True, log=True, reflective=True))
+    with pytest.raises(nb.AptError, match="reflective RW sampler on a log scale"):  # APT:684
+        nb.buildAPT(conf, Temps=[1, 2, 3])
+    conf.removeSamplers()
+    conf.addSampler("theta[1:2]", type="sampler_RW_block_tempered", control=dict(temperPriors=True, propCov=np.eye(3)))
+    with pytest.raises(nb.AptError, match="propCov matrix must have dimension 2x2"):  # APT:816
+        nb.buildAPT(conf, Temps=[1, 2, 3])
+    conf.removeSamplers()
+    conf.addSampler("theta[1:2]", type="sampler_RW_block_tempered", control=dict(temperPriors=True, propCov=np.array([[1, 0.5], [0.1, 1]])))
+    with pytest.raises(nb.AptError, match="propCov matrix must be symmetric"):  # APT:817
+        nb.buildAPT(conf, Temps=[1, 2, 3])
+    with pytest.raises(ValueError, match="unsupported sampler type"):
+        conf.addSampler("theta[1]", type="sampler_slice_tempered", control=dict(temperPriors=True))
+    with pytest.raises(TypeError, match="conf must either be a nimbleModel or a MCMCconf"):  # APT:252
+        nb.buildAPT("not a conf", Temps=[1, 2])

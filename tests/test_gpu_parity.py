@@ -1,0 +1,74 @@
+"""-m gpu: parity of the CUDA engine (called through the C ABI) against the CPU oracle on identical inputs.
+
+The three north-star checks: (1) logProb on identical states within 1e-12 relative; (2) accept/reject and swap
+decisions bit-identical when both sides are fed the same uniforms/normals (and also with the shared slot-addressed
+Philox stream); (3) posterior summaries within 4 Monte-Carlo standard errors (test_gpu_posterior.py)."""
+import numpy as np
+import pytest
+
+import models
+import nimbleapt_b200 as nb
+from helpers import build_engine, build_oracle, run_pair
+
+pytestmark = pytest.mark.gpu
+
+SMALL = {
+    "c1": lambda: models.c1_vignette(nObs=100, K=8),
+    "c2": lambda: models.c2_mixture(n=20, K=32),
+    "c5": lambda: models.c5_small_logistic(N=256, p=8, K=8),
+    "c4": lambda: models.c4_glmm(G=20, per=10, K=4),
+    "c3s": lambda: models.logistic(2000, 5, 4),
+}
+
+
+@pytest.mark.parametrize("name", list(SMALL))
+def test_logprob_matches_oracle(name):
+    spec = SMALL[name]()
+    eng = build_engine(spec)
+    orc = build_oracle(spec)
+    rng = np.random.default_rng(5)
+    P = len(eng.paramNames)
+    th0 = np.concatenate([np.ravel(spec["inits"][k], order="F") for k in spec["inits"]])
+    assert th0.size == P
+    states = th0[None, :] + 0.3 * rng.standard_normal((17, P))
+    if name == "c4":
+        states[:, 20] = np.abs(states[:, 20]) + 0.1  # sigma inside its support
+    tot, grp = eng.calculate(states)
+    for i in range(states.shape[0]):
+        ref, ref_d = orc.logprob(states[i])
+        assert np.isclose(tot[i], ref, rtol=1e-12, atol=0), (name, i, tot[i], ref)
+        assert np.allclose(np.sort(grp[i]), np.sort(ref_d[ref_d != 0]), rtol=1e-12, atol=1e-12)
+
+
+@pytest.mark.parametrize("name", list(SMALL))
+@pytest.mark.parametrize("inject", [True, False])
+def test_decisions_bit_identical(name, inject):
+    spec = SMALL[name]()
+    niter, L = 450, 2  # crosses two sampler adaptations (adaptInterval = 200)
+    eng, orc, recs = run_pair(spec, niter, L=L, inject=inject)
+    for l in range(L):
+        dec_o, swap_o = recs[l]
+        dec_e = eng.decisions(l, niter)
+        swap_e = eng.swapRecord(l, niter)
+        assert dec_e.shape == dec_o.shape
+        nbad = int((dec_e != dec_o).sum())
+        assert nbad == 0, "%s ladder %d: %d accept decisions differ (first at %s)" % (name, l, nbad, np.argwhere(dec_e != dec_o)[:3])
+        # swap phase: accept/reject flags identical everywhere, partners identical wherever a swap was accepted.
+        # The partner of a REJECTED proposal may differ in a vanishing fraction of cases: when every
+        # exp(-|lp_i - lp_j|) of a row lies in the denormal range, CUDA's and glibc's exp() round differently
+        # and the normalised row (APT:560-569) is not reproducible across math libraries.
+        assert np.array_equal(swap_e >> 16, swap_o >> 16), "%s ladder %d: swap accept decisions differ" % (name, l)
+        tgt_bad = (swap_e & 0xffff) != (swap_o & 0xffff)
+        assert not np.any(tgt_bad & ((swap_o >> 16) == 1)), "%s ladder %d: accepted swap partners differ" % (name, l)
+        assert tgt_bad.mean() <= 1e-3, "%s ladder %d: %d proposed partners differ" % (name, l, tgt_bad.sum())
+        np.testing.assert_allclose(eng.rungStates(l), np.stack([orc.rung_state(l, k) for k in range(eng.nTemps)]), rtol=1e-8, atol=1e-10)
+        np.testing.assert_allclose(eng.TempsLadder(l), orc.Temps(l), rtol=1e-9)
+        np.testing.assert_allclose(eng.mvSamples.matrix(l), orc.samples(l), rtol=1e-8, atol=1e-10)
+        np.testing.assert_allclose(eng.mvSamplesTmax.matrix(l), orc.samplesTmax(l), rtol=1e-8, atol=1e-10)
+        np.testing.assert_allclose(eng.logProbsLadder(l), orc.logProbs(l), rtol=1e-10)
+        np.testing.assert_allclose(eng.tempTrajLadder(l), orc.tempTraj(l), rtol=1e-9)
+        np.testing.assert_array_equal(eng.accCountSwapLadder(l), orc.accCountSwap(l))
+        sc = eng.scales(l)
+        for k in range(eng.nTemps):
+            for s in range(sc.shape[1]):
+                assert np.isclose(sc[k, s], orc.scale(l, k, s), rtol=1e-9)

@@ -1,0 +1,101 @@
+"""CPU: pins the oracle's Rmath-style log-densities (oracle/rmath_port.c) against scipy.stats — an independent
+implementation — because the reference ships no golden vectors for this path."""
+import numpy as np
+import pytest
+from scipy import special, stats
+
+from oracle.oracle import lib
+
+RTOL = 1e-12
+
+
+def close(a, b, rtol=RTOL, atol=1e-13):
+    if np.isinf(b) or np.isinf(a):
+        return a == b
+    return abs(a - b) <= atol + rtol * abs(b)
+
+
+def test_dnorm_grid():
+    L = lib()
+    rng = np.random.default_rng(1)
+    for _ in range(2000):
+        x, mu, sd = rng.normal(0, 50), rng.normal(0, 50), np.exp(rng.normal(0, 3))
+        assert close(L.apt_dnorm_log(x, mu, sd), stats.norm.logpdf(x, mu, sd))
+    assert L.apt_dnorm_log(1.0, 1.0, 0.0) == np.inf and L.apt_dnorm_log(2.0, 1.0, 0.0) == -np.inf
+    assert np.isnan(L.apt_dnorm_log(0.0, 0.0, -1.0))
+
+
+def test_dunif_edges():
+    L = lib()
+    assert close(L.apt_dunif_log(0.3, 0.0, 5.0), -np.log(5.0))
+    assert L.apt_dunif_log(5.0, 0.0, 5.0) == -np.log(5.0)  # closed support like Rmath
+    assert L.apt_dunif_log(5.0000001, 0.0, 5.0) == -np.inf
+    assert np.isnan(L.apt_dunif_log(0.0, 1.0, 1.0))
+
+
+def test_dgamma_grid():
+    L = lib()
+    rng = np.random.default_rng(2)
+    for _ in range(3000):
+        shape, scale = np.exp(rng.normal(0, 2.5)), np.exp(rng.normal(0, 2))
+        x = stats.gamma.rvs(shape, scale=scale, random_state=rng) if rng.random() < 0.7 else np.exp(rng.normal(0, 4))
+        if x == 0 or not np.isfinite(x):
+            continue
+        ref = stats.gamma.logpdf(x, shape, scale=scale)
+        assert close(L.apt_dgamma_log(x, shape, scale), ref, rtol=2e-12), (x, shape, scale)
+    assert L.apt_dgamma_log(-1.0, 2.0, 1.0) == -np.inf
+    assert L.apt_dgamma_log(0.0, 0.5, 1.0) == np.inf and L.apt_dgamma_log(0.0, 2.0, 1.0) == -np.inf
+    assert close(L.apt_dgamma_log(0.0, 1.0, 3.0), -np.log(3.0))
+
+
+def test_dbeta_grid():
+    L = lib()
+    rng = np.random.default_rng(3)
+    for _ in range(3000):
+        a, b = np.exp(rng.normal(0, 2)), np.exp(rng.normal(0, 2))
+        x = rng.beta(a, b)
+        if x <= 0 or x >= 1:
+            continue
+        assert close(L.apt_dbeta_log(x, a, b), stats.beta.logpdf(x, a, b), rtol=5e-12, atol=5e-12), (x, a, b)
+    assert L.apt_dbeta_log(1.5, 2.0, 2.0) == -np.inf
+    assert L.apt_dbeta_log(0.0, 2.0, 2.0) == -np.inf and L.apt_dbeta_log(0.0, 0.5, 2.0) == np.inf
+
+
+def test_dbinom_grid_and_edges():
+    L = lib()
+    rng = np.random.default_rng(4)
+    for _ in range(3000):
+        n = int(rng.integers(0, 500))
+        p = rng.random() if rng.random() < 0.8 else rng.random() * 1e-6
+        x = int(rng.integers(0, n + 1))
+        assert close(L.apt_dbinom_log(float(x), float(n), p), stats.binom.logpmf(x, n, p), rtol=5e-12), (x, n, p)
+    for p in (1e-12, 0.05, 0.5, 0.95, 1 - 1e-12):  # Bernoulli edge cases used by the logistic workloads
+        assert close(L.apt_dbinom_log(0.0, 1.0, p), np.log1p(-p))
+        assert close(L.apt_dbinom_log(1.0, 1.0, p), np.log(p))
+    assert L.apt_dbinom_log(0.0, 5.0, 0.0) == 0.0 and L.apt_dbinom_log(1.0, 5.0, 0.0) == -np.inf
+    assert L.apt_dbinom_log(5.0, 5.0, 1.0) == 0.0 and L.apt_dbinom_log(6.0, 5.0, 0.5) == -np.inf
+    assert L.apt_dbinom_log(0.5, 5.0, 0.5) == -np.inf and np.isnan(L.apt_dbinom_log(1.0, 5.0, 1.5))
+
+
+def test_dpois_grid_and_edges():
+    L = lib()
+    rng = np.random.default_rng(5)
+    for _ in range(3000):
+        lam = np.exp(rng.normal(1, 3))
+        x = float(rng.poisson(min(lam, 1e6))) if rng.random() < 0.7 else float(rng.integers(0, 2000))
+        assert close(L.apt_dpois_log(x, lam), stats.poisson.logpmf(x, lam), rtol=5e-12), (x, lam)
+    assert L.apt_dpois_log(0.0, 0.0) == 0.0 and L.apt_dpois_log(3.0, 0.0) == -np.inf
+    assert L.apt_dpois_log(-1.0, 2.0) == -np.inf and np.isnan(L.apt_dpois_log(1.0, -2.0))
+    assert close(L.apt_dpois_log(1e7, 1e7), stats.poisson.logpmf(1e7, 1e7), rtol=1e-10)
+
+
+def test_dexp_stirlerr_bd0_lbeta():
+    L = lib()
+    assert close(L.apt_dexp_log(2.0, 4.0), stats.expon.logpdf(2.0, scale=4.0))
+    for n in (0.5, 1.0, 7.5, 15.0, 16.0, 40.0, 90.0, 600.0, 3.3):
+        ref = special.gammaln(n + 1) - (n + 0.5) * np.log(n) + n - 0.5 * np.log(2 * np.pi)
+        assert abs(L.apt_stirlerr(n) - ref) < 2e-14 + 1e-10 * abs(ref) * (n > 15)
+    for x, np_ in ((3.0, 3.1), (10.0, 2.0), (1.0, 0.95), (1e5, 1e5 + 7)):
+        assert close(L.apt_bd0(x, np_), x * np.log(x / np_) + np_ - x, rtol=1e-9, atol=1e-15)
+    for a, b in ((0.5, 0.7), (3.0, 12.0), (20.0, 30.0), (1e-3, 400.0)):
+        assert close(L.apt_lbeta(a, b), special.betaln(a, b), rtol=1e-12, atol=1e-12)

@@ -1,0 +1,88 @@
+"""CPU: known-answer and invariant tests of the oracle itself (Philox vectors, reference-code invariants,
+analytic posteriors), since the reference pins nothing (SURVEY.md §8c "What pins results instead")."""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+import pytest
+
+import models
+from helpers import build_oracle
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def test_philox_known_answers(tmp_path):
+    """Random123 kat_vectors for philox4x32-10."""
+    src = tmp_path / "kat.c"
+    src.write_text('#include <stdio.h>\n#include "philox.h"\nint main(){uint32_t c[3][4]={{0,0,0,0},{0xffffffff,0xffffffff,0xffffffff,0xffffffff},'
+                   '{0x243f6a88,0x85a308d3,0x13198a2e,0x03707344}};uint32_t k[3][2]={{0,0},{0xffffffff,0xffffffff},{0xa4093822,0x299f31d0}};'
+                   'for(int i=0;i<3;i++){uint32_t o[4];apt_philox4x32_10(c[i],k[i],o);printf("%08x %08x %08x %08x\\n",o[0],o[1],o[2],o[3]);}'
+                   'printf("%.17g %.17g\\n", apt_u53(0,0), apt_u53(0xffffffffu,0xffffffffu));return 0;}')
+    exe = tmp_path / "kat"
+    subprocess.check_call(["gcc", "-O1", "-I", os.path.join(HERE, "..", "oracle"), str(src), "-o", str(exe), "-lm"])
+    out = subprocess.check_output([str(exe)]).decode().split("\n")
+    assert out[0] == "6627e8d5 e169c58d bc57ac4c 9b00dbd8"
+    assert out[1] == "408f276d 41c83b0e a20bc7c6 6d5451fd"
+    assert out[2] == "d16cfe09 94fdcceb 5001e420 24126ea1"
+    lo, hi = (float(x) for x in out[3].split())
+    assert 0.0 < lo < 1e-15 and 1.0 - 1e-15 < hi < 1.0
+
+
+def test_ladder_invariants_c1():
+    """Temps[1] never changes (APT:494-496), ladder stays sorted, ULT clamp (APT:497-498), trace shapes (APT:386-393)."""
+    spec = models.c1_vignette(K=5)
+    o = build_oracle(spec)
+    o.run(1500, thin=3)
+    tt = o.tempTraj()
+    assert tt.shape == (500, 5) and o.samples().shape == (500, 2) and o.logProbs().shape == (500,)
+    assert np.all(tt[:, 0] == 1.0)
+    assert np.all(np.diff(tt, axis=1) > 0)
+    assert np.all(tt <= spec["ULT"] + 5)
+    # continuation appends (APT:378-385); resetMV restarts the sample store
+    o.run(300, reset=False, thin=3)
+    assert o.samples().shape == (600, 2) and o.tempTraj().shape == (100, 5)
+    o.run(300, reset=False, resetMV=True, thin=3)
+    assert o.samples().shape == (100, 2)
+
+
+def test_fixed_ladder_keeps_temps():
+    spec = models.c2_mixture(K=6)
+    o = build_oracle(spec)
+    o.run(400, adaptTemps=False)
+    assert np.array_equal(o.Temps(), np.sort(spec["Temps"]))
+    acc = o.accCountSwap()
+    assert np.all(np.diag(acc) == 0) and acc.sum() > 0
+
+
+def test_c2_analytic_posterior():
+    """C2's posterior is the exact mixture 1/2 N((-ybar1, ybar2), I/n) + 1/2 N((ybar1, ybar2), I/n) (flat-ish prior)."""
+    spec = models.c2_mixture(n=20, K=8, tmax=200.0)
+    L = 8
+    o = build_oracle(spec, nLadders=L)
+    o.run(6000, thin=2, nthreads=8)
+    y = spec["data"]["y"]
+    n = y.shape[0]
+    yb = y.mean(0)
+    s = np.concatenate([o.samples(l)[500:] for l in range(L)])
+    shrink = 1.0 / (1.0 + 1.0 / (n * 100.0 ** 2))
+    # |theta1| ~ N(ybar1, 1/n) folded (modes are far from 0), theta2 ~ N(ybar2, 1/n)
+    per_ladder_abs = np.array([np.abs(o.samples(l)[500:, 0]).mean() for l in range(L)])
+    per_ladder_t2 = np.array([o.samples(l)[500:, 1].mean() for l in range(L)])
+    for est, truth in ((per_ladder_abs, yb[0] * shrink), (per_ladder_t2, yb[1] * shrink)):
+        mcse = est.std(ddof=1) / np.sqrt(L)
+        assert abs(est.mean() - truth) < 4 * mcse + 1e-3, (est.mean(), truth, mcse)
+    assert abs(np.var(s[:, 1]) - 1.0 / n) < 0.15 / n
+    frac_pos = np.array([(o.samples(l)[500:, 0] > 0).mean() for l in range(L)])
+    assert abs(frac_pos.mean() - 0.5) < 4 * frac_pos.std(ddof=1) / np.sqrt(L) + 0.02  # both modes visited equally
+
+
+def test_sampler_validation_errors():
+    spec = models.c2_mixture(K=4)
+    bad = dict(spec)
+    bad["samplers"] = [dict(target="theta[1]", type="sampler_RW_tempered", control={})]
+    with pytest.raises(ValueError, match="temperPriors unspecified"):  # APT:660
+        build_oracle(bad)
+    bad["samplers"] = [dict(target="theta[1:2]", type="sampler_RW_tempered", control=dict(temperPriors=True))]
+    with pytest.raises(ValueError, match="more than one target"):  # APT:682
+        build_oracle(bad)
