@@ -166,6 +166,10 @@ int apt_model_names(apt_model* m, int which, char* buf, int64_t buflen);
 /* the CUDA source the lowering step emits for this model and ladder size (for inspection / tests) */
 int apt_model_lower(apt_model* m, int n_temps, const apt_build_opts* opts, char* buf, int64_t buflen, int64_t* needed);
 
+/* lower + compile the module for this model and ladder size without touching a GPU (nvcc cross-compiles for
+ * sm_100a); the path of the cached module is written into path_buf.  apt_build reuses it. */
+int apt_model_compile(apt_model* m, int n_temps, const apt_build_opts* opts, char* path_buf, int64_t buflen);
+
 /* ---- buildAPT + compileNimble */
 int apt_build(apt_model* m, const double* temps, int n_temps, const apt_build_opts* opts, apt_engine** out);
 void apt_free(apt_engine* e);

@@ -143,7 +143,7 @@ class APT:
 
     def __init__(self, conf, Temps, monitorTmax=True, ULT=1e6, thinPrintTemps=1, nLadders=1, seed=11, ladder0=0,
                  device=0, record=False, fuseLinks=True, lanesPerChain=0, ctaThreads=0, engine=0, rungsPerPass=0,
-                 verbose=False, **dots):
+                 verbose=False, compileOnly=False, **dots):
         if isinstance(conf, NimbleModel):  # APT:249-250
             conf = configureMCMC(conf, **dots)
         elif not isinstance(conf, MCMCconf):  # APT:251-253
@@ -204,6 +204,11 @@ class APT:
         self.paramNames = self._names(0)
         self.monitorNames = self._names(1)
         self.monitorNames2 = self._names(2)
+        if compileOnly:  # lower + nvcc only (works without a GPU): used by __graft_entry__.build()
+            buf = C.create_string_buffer(4096)
+            check(L.apt_model_compile(self._m, len(temps), C.byref(o), buf, len(buf)))
+            self.modulePath = buf.value.decode()
+            return
         check(L.apt_build(self._m, _dp(temps), len(temps), C.byref(o), C.byref(self._h)))
         self.mvSamples = _Samples(self, APT_SAMPLES, self.monitorNames)
         self.mvSamples2 = _Samples(self, APT_SAMPLES2, self.monitorNames2)

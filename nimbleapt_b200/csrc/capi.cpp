@@ -192,6 +192,17 @@ int apt_model_lower(apt_model* m, int n_temps, const apt_build_opts* opts, char*
     API_END
 }
 
+int apt_model_compile(apt_model* m, int n_temps, const apt_build_opts* opts, char* path_buf, int64_t buflen) {
+    API_BEGIN
+    apt_build_opts o;
+    if (opts) o = *opts; else apt_build_opts_default(&o);
+    const ModelSpec spec = with_default_monitors(m->spec);
+    Lowered L = lower_model(spec, n_temps, o);
+    std::string so = jit_compile(L.source, o.verbose != 0);
+    copy_out(so, path_buf, buflen, nullptr);
+    API_END
+}
+
 int apt_build(apt_model* m, const double* temps, int n_temps, const apt_build_opts* opts, apt_engine** out) {
     API_BEGIN
     if (!m || !temps || !out) throw Error("null argument");

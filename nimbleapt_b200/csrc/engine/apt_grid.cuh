@@ -1,0 +1,252 @@
+// apt_grid.cuh — the grid-wide engine: likelihoods too large for one CTA per chain (config 3: N = 1e6 rows,
+// p = 50, 16 rungs; /root/reference/nimbleAPT/R/APT_functions.R:825 makes every tempered update its own serial
+// pass over all N data nodes).
+//
+// Here ONE kernel launch per sampler stage serves the tempered update of up to TB chains (all 16 rungs):
+//   1. every CTA stages the TB proposed parameter vectors in shared memory (param-major, chain-minor);
+//   2. the grid streams the data once — coalesced, vectorised (double2, ld.global.cs) fp64 loads, R rows per
+//      thread — and each thread accumulates the log-likelihood of its rows for all TB chains in registers
+//      (inner products interchanged by the lowering so that a data element is loaded once for all chains);
+//   3. warp-shuffle + shared-memory reduction per CTA, partial sums to global memory, a ticket decides which
+//      CTA finishes; that CTA reduces the partials in CTA order (deterministic, no fp atomics) and then runs
+//      the control step out of global memory: tempered accept/reject, Robbins-Monro adaptation, (after the
+//      last stage) the swap phase, ladder adaptation and trace write, and finally the proposals of the NEXT
+//      launch ("propose-ahead"), so that an iteration costs exactly one launch per stage and pass.
+// Bounding roofline: HBM — 8 N (p+1) algorithmic bytes per pass.
+#pragma once
+#include "apt_engine.cuh"
+
+namespace apt {
+
+struct GArgs {
+    KArgs k;
+    double* partial;      // [grid][2][TB] per-CTA partial sums
+    unsigned int* ticket; // arrival counter
+    double* pend;         // [L*K][APT_PEND_DOUBLES] pending proposals (old log-probs, Jacobian, old scalar value)
+    double* scratch;      // [L*K][2*DMAX]  normals / old block values per chain
+    long long it;         // iteration (0-based within the run) this launch finishes
+    int stage, pass, npass;
+    int next_stage, next_pass;  // what to propose ahead (-1: nothing, the run ends or is interrupted)
+    long long next_it;
+    int last_of_iter;     // this launch completes the iteration: swap phase, ladder adaptation, output
+};
+
+#define APT_PEND_DOUBLES 12
+
+template <int NG>
+__device__ __forceinline__ void store_pend(double* dst, const Pend<NG>& p, int rank) {
+    static_assert(NG + 2 <= APT_PEND_DOUBLES, "too many dependent groups for the grid engine");
+    if (rank == 0) {
+#pragma unroll
+        for (int g = 0; g < NG; g++) dst[g] = p.od[g];
+        dst[NG] = p.propLogScale;
+        dst[NG + 1] = p.cur0;
+    }
+}
+template <int NG>
+__device__ __forceinline__ void load_pend(const double* src, Pend<NG>& p) {
+#pragma unroll
+    for (int g = 0; g < NG; g++) p.od[g] = src[g];
+    p.propLogScale = src[NG];
+    p.cur0 = src[NG + 1];
+}
+
+// context of chain q = (ladder l, rung kk) working on global memory, for control tile `tile`
+template <class G>
+__device__ __forceinline__ Ctx<G> grid_ctx(const GArgs& a, int l, int q, long long it, int tid) {
+    constexpr int K = G::K, W = G::W;
+    Ctx<G> c;
+    c.rank = tid % W;
+    c.tile_id = tid / W;
+    c.ntiles = G::GRID_THREADS / W;
+    c.tmask = (W == 32) ? 0xffffffffu : (((1u << W) - 1u) << ((tid & 31) & ~(W - 1)));
+    c.theta = a.k.theta + (size_t)l * K * G::P;
+    c.lpd = a.k.lpd + (size_t)l * K * G::ND;
+    c.slot = a.k.slot + (size_t)l * K;
+    c.T = a.k.temps + (size_t)l * K;
+    c.scale = a.k.scale + (size_t)l * K * G::NU;
+    c.cnt = a.k.cnt + (size_t)l * K * G::NU * 3;
+    c.blk = a.k.blk + (size_t)l * K * G::BLKSZ;
+    c.empir = a.k.empir + (size_t)l * K * G::EMPSZ;
+    c.famdelta = nullptr;
+    c.scratch = a.scratch + (size_t)q * 2 * G::DMAX;
+    c.rng.seed = a.k.seed;
+    c.rng.ladder = a.k.ladder0 + (uint32_t)l;
+    c.rng.iter = a.k.rng_iter0 + (uint64_t)it;
+    c.tabZ = a.k.tabZ ? a.k.tabZ + ((size_t)it * a.k.L + l) * K * G::NU * G::DMAX : nullptr;
+    c.tabU = a.k.tabU ? a.k.tabU + ((size_t)it * a.k.L + l) * K * G::NU : nullptr;
+    c.rec = a.k.rec ? a.k.rec + ((size_t)it * a.k.L + l) * K * G::NU : nullptr;
+    return c;
+}
+
+template <class G>
+__device__ __forceinline__ void grid_propose_ahead(const GArgs& a, int tid) {
+    constexpr int K = G::K, W = G::W, TB = G::TB;
+    if (a.next_stage < 0) return;
+    const int tile = tid / W;
+    if (tile >= TB) return;
+    const int q = a.next_pass * TB + tile;
+    if (q >= a.k.L * K) return;
+    const int l = q / K, kk = q % K;
+    Ctx<G> c = grid_ctx<G>(a, l, q, a.next_it, tid);
+    G::propose_stage(a.next_stage, c, a.k.D, kk, a.pend + (size_t)q * APT_PEND_DOUBLES);
+}
+
+// first launch of a run: only the proposals of (stage 0, pass 0)
+template <class G>
+__global__ void __launch_bounds__(G::GRID_THREADS) grid_prologue_kernel(const __grid_constant__ GArgs a) {
+    grid_propose_ahead<G>(a, threadIdx.x);
+}
+
+// swap phase + ladder adaptation + output for ladder l by one warp, state in global memory, staged through smem
+template <class G>
+__device__ __forceinline__ void grid_ladder_step(const GArgs& a, int l, double* sm /* 4K doubles + K ints */, int lane) {
+    constexpr int K = G::K, P = G::P, ND = G::ND;
+    double* s_lp = sm;
+    double* s_rs = sm + K;
+    double* s_T = sm + 2 * K;
+    double* s_invT = sm + 3 * K;
+    int* s_slot = reinterpret_cast<int*>(sm + 4 * K);
+    const double* lpd = a.k.lpd + (size_t)l * K * ND;
+    for (int j = lane; j < K; j += 32) {
+        s_T[j] = a.k.temps[(size_t)l * K + j];
+        s_invT[j] = 1.0 / s_T[j];
+        s_slot[j] = a.k.slot[(size_t)l * K + j];
+        const double* q = lpd + s_slot[j] * ND;
+        double s = 0.0;
+#pragma unroll
+        for (int dd = 0; dd < ND; dd++) s += q[dd];
+        s_lp[j] = s;  // logProbTemps[tt] <- model$getLogProb()  (APT:447)
+    }
+    __syncwarp();
+    RngKey rng;
+    rng.seed = a.k.seed;
+    rng.ladder = a.k.ladder0 + (uint32_t)l;
+    rng.iter = a.k.rng_iter0 + (uint64_t)a.it;
+    swap_phase<G>(a.k, l, a.it, s_lp, s_rs, s_invT, s_slot, lane, rng);
+    const long long totalIters = a.k.total_iters0 + a.it + 1;  // APT:489
+    if (a.k.adapt_temps) ladder_adapt<G>(a.k, totalIters, s_lp, s_T, s_invT, lane);
+    write_traces<G>(a.k, l, a.it, a.k.theta + (size_t)l * K * P, s_slot, s_T, s_lp, lane);
+    for (int j = lane; j < K; j += 32) {
+        a.k.temps[(size_t)l * K + j] = s_T[j];
+        a.k.slot[(size_t)l * K + j] = s_slot[j];
+        a.k.lp[(size_t)l * K + j] = s_lp[j];
+    }
+    __syncwarp();
+}
+
+template <class G, class S>
+__global__ void __launch_bounds__(G::GRID_THREADS, 1) grid_pass_kernel(const __grid_constant__ GArgs a) {
+    constexpr int TB = G::TB, R = G::R, NB = S::NBIG, K = G::K, P = G::P, THREADS = G::GRID_THREADS, NWARP = THREADS / 32, W = G::W;
+    static_assert(NB >= 1 && NB <= 2, "grid kernel needs 1 or 2 large declarations");
+    extern __shared__ __align__(16) double gsm[];
+    double* thT = gsm;                    // [P][TB]
+    double* red = gsm + P * TB;           // [NWARP][NB*TB]
+    double* s_new = red + NWARP * NB * TB;  // [NB*TB]
+    double* s_lad = s_new + NB * TB;      // [NWARP][5K] ladder-step staging
+    __shared__ int s_last;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nch = a.k.L * K;
+    const int q0 = a.pass * TB;
+    // ---- 1. proposed states of this pass's chains -> shared memory, param-major / chain-minor
+    for (int idx = tid; idx < P * TB; idx += THREADS) {
+        const int p = idx / TB, cc = idx % TB;
+        int q = q0 + cc;
+        if (q >= nch) q = nch - 1;
+        const int l = q / K, kk = q % K;
+        const int sl = a.k.slot[(size_t)l * K + kk];
+        thT[idx] = a.k.theta[((size_t)l * K + sl) * P + p];
+    }
+    __syncthreads();
+    // ---- 2. one pass over the data
+    double acc[NB][TB];
+#pragma unroll
+    for (int g = 0; g < NB; g++)
+#pragma unroll
+        for (int cc = 0; cc < TB; cc++) acc[g][cc] = 0.0;
+    {
+        const long n = S::big_n(0);
+        const long ngrp = n / R;
+        for (long grp = (long)blockIdx.x * THREADS + tid; grp < ngrp; grp += (long)gridDim.x * THREADS)
+            S::template big_eval<0, TB, R>(a.k.D, thT, (int)(grp * R), acc[0]);
+        if (blockIdx.x == 0 && tid < (int)(n - ngrp * R)) S::template big_eval<0, TB, 1>(a.k.D, thT, (int)(ngrp * R + tid), acc[0]);
+    }
+    if constexpr (NB == 2) {
+        const long n = S::big_n(1);
+        const long ngrp = n / R;
+        for (long grp = (long)blockIdx.x * THREADS + tid; grp < ngrp; grp += (long)gridDim.x * THREADS)
+            S::template big_eval<1, TB, R>(a.k.D, thT, (int)(grp * R), acc[NB - 1]);
+        if (blockIdx.x == 0 && tid < (int)(n - ngrp * R)) S::template big_eval<1, TB, 1>(a.k.D, thT, (int)(ngrp * R + tid), acc[NB - 1]);
+    }
+    // ---- 3. CTA reduction (fixed order: lanes by butterfly, warps ascending)
+#pragma unroll
+    for (int g = 0; g < NB; g++)
+#pragma unroll
+        for (int cc = 0; cc < TB; cc++) {
+            double v = acc[g][cc];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) red[warp * NB * TB + g * TB + cc] = v;
+        }
+    __syncthreads();
+    if (tid < NB * TB) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < NWARP; w++) s += red[w * NB * TB + tid];
+        a.partial[(size_t)blockIdx.x * NB * TB + tid] = s;
+    }
+    // ---- 4. ticket: the last CTA to arrive finishes the stage
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = (atomicAdd(a.ticket, 1u) == gridDim.x - 1) ? 1 : 0;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    for (int v = warp; v < NB * TB; v += NWARP) {
+        double s = 0.0;
+        for (int b = lane; b < (int)gridDim.x; b += 32) s += __ldcg(&a.partial[(size_t)b * NB * TB + v]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) s_new[v] = s;
+    }
+    __syncthreads();
+    // ---- 5. control step: finish the tempered update of each chain of this pass (one tile of W lanes per chain)
+    {
+        const int tile = tid / W;
+        const int q = q0 + tile;
+        if (tile < TB && q < nch) {
+            const int l = q / K, kk = q % K;
+            Ctx<G> c = grid_ctx<G>(a, l, q, a.it, tid);
+            Pend<S::NG> p;
+            load_pend<S::NG>(a.pend + (size_t)q * APT_PEND_DOUBLES, p);
+            const double* th = c.theta + c.slot[kk] * P;
+            double nw[S::NG];
+#pragma unroll
+            for (int g = 0; g < S::NG; g++) nw[g] = 0.0;
+            S::eval(a.k.D, th, 0, c, nw, true, true);  // small groups only (priors, ...)
+#pragma unroll
+            for (int g = 0; g < S::NG; g++) nw[g] = c.sum(nw[g]);
+#pragma unroll
+            for (int gi = 0; gi < NB; gi++) nw[S::big_group(gi)] = s_new[gi * TB + tile];
+            rw_finish<G, S>(c, a.k.D, kk, 0, p, nw);
+        }
+    }
+    __threadfence_block();
+    __syncthreads();
+    if (a.last_of_iter) {
+        for (int l = warp; l < a.k.L; l += NWARP) grid_ladder_step<G>(a, l, s_lad + (size_t)warp * 5 * K, lane);
+        __syncthreads();
+    }
+    // ---- 6. propose ahead for the next launch
+    grid_propose_ahead<G>(a, tid);
+    if (tid == 0) *a.ticket = 0u;
+}
+
+template <class G>
+struct GridShape {
+    static constexpr size_t smem_bytes(int nbig) {
+        return (size_t)(G::P * G::TB + (G::GRID_THREADS / 32) * nbig * G::TB + nbig * G::TB + (G::GRID_THREADS / 32) * 5 * G::K) * sizeof(double);
+    }
+};
+
+}  // namespace apt

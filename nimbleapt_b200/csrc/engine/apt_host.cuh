@@ -10,6 +10,7 @@
 #include <string>
 #include <vector>
 #include "apt_engine.cuh"
+#include "apt_grid.cuh"
 #include "apt_module_abi.h"
 
 namespace apt {
@@ -81,6 +82,9 @@ struct Engine {
     Data D{};
     DevBuf<double> theta, lpd, temps, lp, scale, blk, empir, famdelta, model_theta, scale0, blk0;
     DevBuf<int> slot, cnt, accswap;
+    DevBuf<double> g_partial, g_pend, g_scratch;  // grid engine
+    DevBuf<unsigned int> g_ticket;
+    int num_sms = 148, grid_occ = 1;
     DevBuf<double> samples, samples2, samplesT, samples2T, logprobs, temptraj;
     DevBuf<double> tabZ, tabU, tabS;
     DevBuf<unsigned char> rec;
@@ -160,8 +164,16 @@ struct Engine {
         scale0.alloc(G::NU); blk0.alloc(b0.size());
         APT_CUDA(cudaMemcpyAsync(scale0.p, s0.data(), s0.size() * sizeof(double), cudaMemcpyHostToDevice, stream));
         APT_CUDA(cudaMemcpyAsync(blk0.p, b0.data(), b0.size() * sizeof(double), cudaMemcpyHostToDevice, stream));
-        if (SH::SM_BYTES > 48 * 1024)
-            APT_CUDA(cudaFuncSetAttribute(ladder_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SH::SM_BYTES));
+        num_sms = prop.multiProcessorCount;
+        if constexpr (G::ENGINE == 2) {
+            g_partial.alloc((size_t)num_sms * 8 * 2 * G::TB);
+            g_ticket.alloc(1); g_ticket.zero(stream);
+            g_pend.alloc(nch * APT_PEND_DOUBLES); g_pend.zero(stream);
+            g_scratch.alloc(nch * 2 * G::DMAX); g_scratch.zero(stream);
+        } else {
+            if (SH::SM_BYTES > 48 * 1024)
+                APT_CUDA(cudaFuncSetAttribute(ladder_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SH::SM_BYTES));
+        }
         APT_CUDA(cudaStreamSynchronize(stream));
     }
 
@@ -268,23 +280,27 @@ struct Engine {
         a.logprobs = logprobs.p; a.temptraj = temptraj.p;
         a.tabZ = ra->tabZ ? tabZ.p : nullptr; a.tabU = ra->tabU ? tabU.p : nullptr; a.tabS = ra->tabS ? tabS.p : nullptr;
         a.rec = record ? rec.p : nullptr; a.recswap = record ? recswap.p : nullptr;
-        long long chunk = ra->iters_per_launch > 0 ? ra->iters_per_launch : 4096;
-        const int grid = (L + SH::TEAMS - 1) / SH::TEAMS;
         bool aborted = false;
-        for (long long it0 = 0; it0 < ra->niter; it0 += chunk) {
-            if (ra->should_abort && ra->should_abort(ra->abort_arg)) { aborted = true; break; }
-            a.it0 = it0; a.it1 = std::min<long long>(ra->niter, it0 + chunk);
-            a.rng_iter0 = rngIter; a.total_iters0 = totalIters;
-            APT_CUDA(cudaEventRecord(ev0, stream));
-            ladder_kernel<G><<<grid, SH::CTA, SH::SM_BYTES, stream>>>(a);
-            APT_CUDA(cudaGetLastError());
-            APT_CUDA(cudaEventRecord(ev1, stream));
-            APT_CUDA(cudaEventSynchronize(ev1));
-            float ms = 0;
-            APT_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
-            timing.kernel_ms += ms; timing.main_kernel_ms += ms; timing.launches++; timing.main_launches++;
-            rngIter += (uint64_t)(a.it1 - a.it0);
-            totalIters += (a.it1 - a.it0);
+        if constexpr (G::ENGINE == 2) {
+            aborted = run_grid(a, ra);
+        } else {
+            long long chunk = ra->iters_per_launch > 0 ? ra->iters_per_launch : 4096;
+            const int grid = (L + SH::TEAMS - 1) / SH::TEAMS;
+            for (long long it0 = 0; it0 < ra->niter; it0 += chunk) {
+                if (ra->should_abort && ra->should_abort(ra->abort_arg)) { aborted = true; break; }
+                a.it0 = it0; a.it1 = std::min<long long>(ra->niter, it0 + chunk);
+                a.rng_iter0 = rngIter; a.total_iters0 = totalIters;
+                APT_CUDA(cudaEventRecord(ev0, stream));
+                ladder_kernel<G><<<grid, SH::CTA, SH::SM_BYTES, stream>>>(a);
+                APT_CUDA(cudaGetLastError());
+                APT_CUDA(cudaEventRecord(ev1, stream));
+                APT_CUDA(cudaEventSynchronize(ev1));
+                float ms = 0;
+                APT_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
+                timing.kernel_ms += ms; timing.main_kernel_ms += ms; timing.launches++; timing.main_launches++;
+                rngIter += (uint64_t)(a.it1 - a.it0);
+                totalIters += (a.it1 - a.it0);
+            }
         }
         // APT:548: the model is left parameterised with the T=1 state
         model_from_rung1_kernel<G><<<std::min(L, 65535), 64, 0, stream>>>(L, theta.p, slot.p, model_theta.p);
@@ -294,6 +310,63 @@ struct Engine {
         launches_total += timing.launches;
         if (aborted) throw ApiError{"run interrupted by the caller"};
     }
+
+    // grid engine: one launch per (iteration, stage, pass); chunks of iterations are self-contained (prologue
+    // launch proposes, the last launch of the chunk does not propose ahead) so that a run can be interrupted
+    // between chunks with the state consistent.  Returns true when interrupted.
+    bool run_grid(KArgs& a, const aptmod_run_args* ra) {
+        if constexpr (G::ENGINE == 2) {
+            GArgs g{};
+            const int nchain = L * K;
+            const int npass = (nchain + G::TB - 1) / G::TB;
+            size_t smem = GridShape<G>::smem_bytes(2);
+            if (grid_occ_known == 0) {
+                grid_occ = std::max(1, G::stage_occupancy(0, smem));
+                grid_occ_known = 1;
+            }
+            const int grid = num_sms * std::min(grid_occ, 8);
+            long long chunk = ra->iters_per_launch > 0 ? ra->iters_per_launch : 256;
+            const uint64_t rng0 = rngIter;
+            const long long tot0 = totalIters;
+            for (long long it0 = 0; it0 < ra->niter; it0 += chunk) {
+                if (ra->should_abort && ra->should_abort(ra->abort_arg)) return true;
+                const long long it1 = std::min<long long>(ra->niter, it0 + chunk);
+                // iterations are addressed by their index within the RUN (thinning, swap direction, random slots,
+                // injected tables all depend on it); the counters at run start are the bases
+                a.rng_iter0 = rng0; a.total_iters0 = tot0;
+                a.it0 = it0; a.it1 = it1;
+                g.k = a;
+                g.partial = g_partial.p; g.ticket = g_ticket.p; g.pend = g_pend.p; g.scratch = g_scratch.p;
+                g.npass = npass;
+                APT_CUDA(cudaEventRecord(ev0, stream));
+                g.next_stage = 0; g.next_pass = 0; g.next_it = it0;
+                G::launch_prologue(g, stream);
+                long long nl = 1;
+                for (long long it = it0; it < it1; ++it)
+                    for (int st = 0; st < G::NSTAGE; ++st)
+                        for (int ps = 0; ps < npass; ++ps) {
+                            g.it = it; g.stage = st; g.pass = ps;
+                            g.last_of_iter = (st == G::NSTAGE - 1 && ps == npass - 1) ? 1 : 0;
+                            if (ps + 1 < npass) { g.next_stage = st; g.next_pass = ps + 1; g.next_it = it; }
+                            else if (st + 1 < G::NSTAGE) { g.next_stage = st + 1; g.next_pass = 0; g.next_it = it; }
+                            else if (it + 1 < it1) { g.next_stage = 0; g.next_pass = 0; g.next_it = it + 1; }
+                            else { g.next_stage = -1; g.next_pass = 0; g.next_it = 0; }
+                            G::launch_stage(st, g, grid, smem, stream);
+                            nl++;
+                        }
+                APT_CUDA(cudaGetLastError());
+                APT_CUDA(cudaEventRecord(ev1, stream));
+                APT_CUDA(cudaEventSynchronize(ev1));
+                float ms = 0;
+                APT_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
+                timing.kernel_ms += ms; timing.main_kernel_ms += ms; timing.launches += nl; timing.main_launches += nl - 1;
+                rngIter += (uint64_t)(it1 - it0);
+                totalIters += (it1 - it0);
+            }
+        }
+        return false;
+    }
+    int grid_occ_known = 0;
 
     // whole-model logProb of caller-provided states (host pointers): out_lpd [n][ND]
     void logprob(const double* th, int n, double* out_lpd) {
@@ -306,6 +379,29 @@ struct Engine {
         APT_CUDA(cudaGetLastError());
         APT_CUDA(cudaMemcpyAsync(out_lpd, dout.p, (size_t)n * G::ND * 8, cudaMemcpyDeviceToHost, stream));
         APT_CUDA(cudaStreamSynchronize(stream));
+    }
+
+    // device-resident, compact [L][rows][cols] view of a trace for collectives (NCCL all-gather); no host staging
+    DevBuf<double> compact;
+    void device_ptr(int what, void** ptr, int64_t* n, void** strm) {
+        APT_CUDA(cudaSetDevice(device));
+        const DevBuf<double>* b; long long capr, nrows; int cols;
+        switch (what) {
+            case APTMOD_SAMPLES: b = &samples; capr = cap; nrows = rows; cols = G::NMON; break;
+            case APTMOD_SAMPLES_TMAX: b = &samplesT; capr = cap; nrows = rows; cols = G::NMON; break;
+            case APTMOD_SAMPLES2: b = &samples2; capr = cap2; nrows = rows2; cols = G::NMON2; break;
+            case APTMOD_LOGPROBS: b = &logprobs; capr = cap; nrows = rows; cols = 1; break;
+            case APTMOD_TEMPTRAJ: b = &temptraj; capr = ttcap; nrows = ttrows; cols = K; break;
+            default: throw ApiError{"this item is not available as a device trace"};
+        }
+        *n = (int64_t)L * nrows * cols;
+        *strm = (void*)stream;
+        if (capr == nrows) { *ptr = b->p; return; }
+        compact.alloc((size_t)std::max<int64_t>(*n, 1));
+        if (*n)
+            APT_CUDA(cudaMemcpy2DAsync(compact.p, (size_t)nrows * cols * 8, b->p, (size_t)capr * cols * 8, (size_t)nrows * cols * 8, L,
+                                       cudaMemcpyDeviceToDevice, stream));
+        *ptr = compact.p;
     }
 
     long long info(int what) const {
@@ -495,4 +591,7 @@ inline void set_err(char* err, int errlen, const std::string& m) {
         APT_GUARD(static_cast<apt::Engine<G>*>(h)->set_array(idx, v, n))                                            \
     }                                                                                                               \
     APT_EXPORT void aptmod_timing_get(void* h, aptmod_timing* t) { *t = static_cast<apt::Engine<G>*>(h)->timing; }             \
+    APT_EXPORT int aptmod_device_ptr(void* h, int what, void** ptr, int64_t* n, void** strm) {                                 \
+        try { static_cast<apt::Engine<G>*>(h)->device_ptr(what, ptr, n, strm); return 0; } catch (...) { return 1; }            \
+    }                                                                                                               \
     }

@@ -66,6 +66,7 @@ struct Group {
     int decl;
     bool full, prior;
     std::vector<int> inst;  // linear instance indices when !full
+    bool big = false;       // grid engine: evaluated by the grid-wide pass over the data
 };
 struct Unit {  // one generated sampler struct: a single sampler or a family
     int kind = 0, d = 1, unit0 = 0, count = 1;
@@ -942,9 +943,13 @@ struct Lowerer {
         }
         return s;
     }
+    // chain-vectorised mode (grid engine): parameters of TB chains live in shared memory as thT[param][chain]
+    bool cv_mode = false;
+    std::map<const Expr*, std::string> hoisted;  // inprod nodes already emitted as per-(row, chain) arrays
     std::string gen_load(const Var& v, const EP& e, const Env& env) {
         if (v.role == Var::PARAM) {
             std::string off = gen_offset(v, e, env);
+            if (cv_mode) return "thT[(" + std::to_string(v.theta_off) + " + " + off + ") * TB + c_]";
             return "th[" + std::to_string(v.theta_off) + " + " + off + "]";
         }
         if (v.role == Var::CONST && v.size <= 64) {  // small constants are folded into the code
@@ -1018,6 +1023,8 @@ struct Lowerer {
                 if ((e->name == "min" || e->name == "max") && e->a.size() == 2)
                     return "f" + e->name + "(" + gen_dbl(e->a[0], env) + ", " + gen_dbl(e->a[1], env) + ")";
                 if (e->name == "inprod" && e->a.size() == 2) {
+                    auto hit = hoisted.find(e.get());
+                    if (hit != hoisted.end()) return hit->second;
                     int la = 0, lb = 0;
                     std::string ev = "e" + std::to_string(tmp_id++);
                     std::string A = gen_slice_elem(e->a[0], ev, env, la), B = gen_slice_elem(e->a[1], ev, env, lb);
@@ -1065,6 +1072,109 @@ struct Lowerer {
 
     bool is_call(const EP& e, const char* name) const { return e->k == Expr::CALL && e->name == name && e->a.size() == 1; }
 
+    // C expression of the log-density of a (non-multivariate) stochastic declaration at value expression `x`
+    std::string density_expr(const CDecl& d, const std::string& x, const Env& env) {
+        if (d.dist == "dbinom" && opts.fuse_links && (is_call(d.iargs[0], "ilogit") || is_call(d.iargs[0], "expit"))) {
+            double sz;
+            if (try_ceval(d.iargs[1], {}, sz) && sz == 1.0)  // fused: dbinom(prob = ilogit(eta), size = 1)
+                return "apt::bern_logit_log(" + x + ", " + gen_dbl(d.iargs[0]->a[0], env) + ")";
+        }
+        std::string fn = d.dist == "dnorm" ? "apt::dnorm_log" : d.dist == "dunif" ? "apt::dunif_log" : d.dist == "dgamma" ? "apt::dgamma_log"
+                       : d.dist == "dbeta" ? "apt::dbeta_log" : d.dist == "dbinom" ? "apt::dbinom_log" : d.dist == "dpois" ? "apt::dpois_log"
+                       : "apt::dexp_log";
+        std::string r = fn + "(" + x;
+        for (auto& a : d.iargs) r += ", " + gen_dbl(a, env);
+        return r + ")";
+    }
+
+    void collect_inprods(const EP& e, std::vector<EP>& acc) const {
+        if (e->k == Expr::CALL && e->name == "inprod" && e->a.size() == 2) { acc.push_back(e); return; }
+        for (auto& x : e->a) collect_inprods(x, acc);
+    }
+    bool slice_is_param(const EP& sl) const {
+        if (sl->k != Expr::VAR) return false;
+        auto it = vars.find(sl->name);
+        return it != vars.end() && it->second.role == Var::PARAM;
+    }
+
+    // Grid engine: evaluate R consecutive instances of a big declaration for TB chains at once.  Inner products of
+    // a parameter slice with a data row are interchanged so that each data element is loaded once and reused by
+    // all chains (the loop over the TB chains is innermost and fully unrolled into registers).
+    void emit_big_eval(Unit& u) {
+        std::vector<size_t> bigs;
+        for (size_t g = 0; g < u.groups.size(); g++)
+            if (u.groups[g].big) bigs.push_back(g);
+        out << "    static constexpr int NBIG = " << bigs.size() << ";\n";
+        if (bigs.empty()) {
+            out << "    __device__ static constexpr int big_group(int gi) { return 0; }\n";
+            out << "    __host__ __device__ static constexpr long big_n(int gi) { return 0; }\n";
+            out << "    template <int GI, int TB, int R> __device__ static __forceinline__ void big_eval(const Data& D, const double* __restrict__ thT, int i0, double (&acc)[TB]) {}\n";
+            return;
+        }
+        out << "    __device__ static constexpr int big_group(int gi) { return ";
+        for (size_t i = 0; i + 1 < bigs.size(); i++) out << "gi == " << i << " ? " << bigs[i] << " : ";
+        out << bigs.back() << "; }\n";
+        out << "    __host__ __device__ static constexpr long big_n(int gi) { return ";
+        for (size_t i = 0; i + 1 < bigs.size(); i++) out << "gi == " << i << " ? " << decls[u.groups[bigs[i]].decl].ninst << "L : ";
+        out << decls[u.groups[bigs.back()].decl].ninst << "L; }\n";
+        out << "    template <int GI, int TB, int R> __device__ static __forceinline__ void big_eval(const Data& D, const double* __restrict__ thT, int i0, double (&acc)[TB]) {\n";
+        for (size_t bi = 0; bi < bigs.size(); bi++) {
+            CDecl& d = decls[u.groups[bigs[bi]].decl];
+            if (d.loops.size() != 1 || d.dist == "dmnorm") throw Error("grid engine: big declarations must be univariate with exactly one loop");
+            out << "      if constexpr (GI == " << bi << ") {  // " << to_string(d.lhs) << " ~ " << d.dist << ", " << d.ninst << " instances\n";
+            Env env;
+            env[d.loops[0].var] = "(" + std::to_string(d.loops[0].lo) + " + i0 + r_)";
+            std::vector<EP> ips;
+            for (auto& a : d.iargs) collect_inprods(a, ips);
+            cv_mode = true;
+            hoisted.clear();
+            int nh = 0;
+            for (auto& ip : ips) {
+                const bool pa = slice_is_param(ip->a[0]), pb = slice_is_param(ip->a[1]);
+                if (pa == pb) continue;  // not (parameter slice x data slice): evaluated per chain in place
+                const EP& ps = pa ? ip->a[0] : ip->a[1];
+                const EP& ds = pa ? ip->a[1] : ip->a[0];
+                int lp_ = 0, ld_ = 0;
+                std::string pe = gen_slice_elem(ps, "e_", env, lp_);
+                Env env0 = env, env1 = env;
+                std::string de = gen_slice_elem(ds, "e_", env, ld_);
+                if (lp_ != ld_) throw Error("inprod arguments have different lengths: " + to_string(ip));
+                // vector-load eligibility: data slice is X[loopvar, lo:hi] with an even leading dimension
+                bool vec = false;
+                auto dv = vars.find(ds->name);
+                if (dv != vars.end() && ds->a.size() == 2 && ds->a[1]->k == Expr::RANGE && ds->a[0]->k == Expr::VAR && ds->a[0]->a.empty() &&
+                    ds->a[0]->name == d.loops[0].var && dv->second.dims[0] % 2 == 0 && d.loops[0].lo % 2 == 1)
+                    vec = true;
+                std::string nm = "ip" + std::to_string(nh++) + "_";
+                out << "        double " << nm << "[R][TB];\n";
+                out << "        _Pragma(\"unroll\") for (int r_ = 0; r_ < R; ++r_) { _Pragma(\"unroll\") for (int c_ = 0; c_ < TB; ++c_) " << nm << "[r_][c_] = 0.0; }\n";
+                out << "        _Pragma(\"unroll 2\") for (int e_ = 0; e_ < " << lp_ << "; ++e_) {\n";
+                out << "          double xr_[R];\n";
+                if (vec) {
+                    Env envv = env;
+                    envv[d.loops[0].var] = "(" + std::to_string(d.loops[0].lo) + " + i0)";
+                    int tmp;
+                    std::string de0 = gen_slice_elem(ds, "e_", envv, tmp);
+                    out << "          if constexpr (R == 2) { const double2 v2_ = __ldcs(reinterpret_cast<const double2*>(&" << de0 << ")); xr_[0] = v2_.x; xr_[1] = v2_.y; }\n";
+                    out << "          else { _Pragma(\"unroll\") for (int r_ = 0; r_ < R; ++r_) xr_[r_] = __ldcs(&" << de << "); }\n";
+                } else {
+                    out << "          _Pragma(\"unroll\") for (int r_ = 0; r_ < R; ++r_) xr_[r_] = __ldcs(&" << de << ");\n";
+                }
+                out << "          _Pragma(\"unroll\") for (int c_ = 0; c_ < TB; ++c_) { const double b_ = " << pe << "; _Pragma(\"unroll\") for (int r_ = 0; r_ < R; ++r_) "
+                    << nm << "[r_][c_] = fma(xr_[r_], b_, " << nm << "[r_][c_]); }\n";
+                out << "        }\n";
+                hoisted[ip.get()] = nm + "[r_][c_]";
+            }
+            out << "        _Pragma(\"unroll\") for (int r_ = 0; r_ < R; ++r_) {\n";
+            out << "          const double x_ = " << gen_dbl(d.lhs, env) << ";\n";
+            out << "          _Pragma(\"unroll\") for (int c_ = 0; c_ < TB; ++c_) acc[c_] += " << density_expr(d, "x_", env) << ";\n";
+            out << "        }\n      }\n";
+            cv_mode = false;
+            hoisted.clear();
+        }
+        out << "    }\n";
+    }
+
     void emit_lp_functions() {
         for (int di : stoch_decls) {
             CDecl& d = decls[di];
@@ -1091,21 +1201,7 @@ struct Lowerer {
                 for (int e = 0; e < n * n; e++) out << (e ? ", " : "") << gen_dbl(d.chol_elems[e], env);
                 out << "};\n    return apt::dmnorm_chol_log<" << n << ">(x_, mu_, U_, (" << gen_dbl(d.iargs[0], env) << ") != 0.0);\n";
             } else {
-                std::string x = gen_dbl(d.lhs, env);
-                if (d.dist == "dbinom" && opts.fuse_links && (is_call(d.iargs[0], "ilogit") || is_call(d.iargs[0], "expit"))) {
-                    double sz;
-                    if (try_ceval(d.iargs[1], {}, sz) && sz == 1.0) {
-                        out << "    // fused: dbinom(prob = ilogit(eta), size = 1)\n";
-                        out << "    return apt::bern_logit_log(" << x << ", " << gen_dbl(d.iargs[0]->a[0], env) << ");\n  }\n";
-                        continue;
-                    }
-                }
-                std::string fn = d.dist == "dnorm" ? "apt::dnorm_log" : d.dist == "dunif" ? "apt::dunif_log" : d.dist == "dgamma" ? "apt::dgamma_log"
-                               : d.dist == "dbeta" ? "apt::dbeta_log" : d.dist == "dbinom" ? "apt::dbinom_log" : d.dist == "dpois" ? "apt::dpois_log"
-                               : "apt::dexp_log";
-                out << "    return " << fn << "(" << x;
-                for (auto& a : d.iargs) out << ", " << gen_dbl(a, env);
-                out << ");\n";
+                out << "    return " << density_expr(d, gen_dbl(d.lhs, env), env) << ";\n";
             }
             out << "  }\n";
         }
@@ -1164,7 +1260,7 @@ struct Lowerer {
                 << (hi ? gen_dbl(hi, env) : std::string("CUDART_INF")) << "; }\n";
         }
         // eval
-        out << "    template <class C> __device__ static __forceinline__ void eval(const Data& D, const double* th, int m, const C& c, double* acc, bool newpass) {\n";
+        out << "    template <class C> __device__ static __forceinline__ void eval(const Data& D, const double* th, int m, const C& c, double* acc, bool newpass, bool skipbig) {\n";
         for (size_t g = 0; g < u.groups.size(); g++) {
             const Group& gr = u.groups[g];
             const CDecl& d = decls[gr.decl];
@@ -1175,7 +1271,7 @@ struct Lowerer {
                 out << "      { const int* ptr_ = D.ia[" << u.ia_ptr[g] << "]; const int* ix_ = D.ia[" << u.ia_idx[g] << "];\n";
                 out << "        for (int q = ptr_[m] + c.rank; q < ptr_[m + 1]; q += C::W) " << acc << " += " << lp_call(gr.decl, "ix_[q]") << "; }\n";
             } else if (gr.full) {
-                out << "      if (newpass) {\n  ";
+                out << "      if (newpass" << (gr.big ? " && !skipbig" : "") << ") {\n  ";
                 emit_inst_loop(gr.decl, acc);
                 out << "      }\n";
             } else if (gr.inst.size() == 1) {
@@ -1189,7 +1285,9 @@ struct Lowerer {
                     << lp_call(gr.decl, std::to_string(gr.inst[0]) + " + q * " + std::to_string(step)) << ";\n";
             }
         }
-        out << "    }\n  };\n";
+        out << "    }\n";
+        emit_big_eval(u);
+        out << "  };\n";
     }
 
     void choose_shape(int& W, int& tiles, int& teams, bool& smem_state) {
@@ -1246,6 +1344,34 @@ struct Lowerer {
         int W, tiles, teams;
         bool smem_state;
         choose_shape(W, tiles, teams, smem_state);
+        // ---- engine selection.  Grid engine: few chains, at least one declaration too large for one CTA per
+        // chain (config 3: N = 1e6 rows): every tempered update of all chains is served by ONE pass over the data.
+        int engine = 1, TB = 1, R = 1;
+        {
+            long maxfull = 0;
+            for (auto& u : units)
+                for (auto& g : u.groups)
+                    if (g.full) maxfull = std::max(maxfull, decls[g.decl].ninst);
+            const long nchains = (long)std::max(1, opts.n_ladders) * K;
+            if (opts.engine == 2 || (opts.engine == 0 && !has_family && nchains <= 256 && maxfull >= 65536)) engine = 2;
+            if (engine == 2) {
+                if (has_family) throw Error("grid engine: sampler families are not supported yet (use engine = 1)");
+                const long big_min = opts.engine == 2 ? 256 : 8192;
+                bool any = false;
+                for (auto& u : units) {
+                    int nb = 0;
+                    for (auto& g : u.groups)
+                        if (g.full && decls[g.decl].ninst >= big_min && decls[g.decl].loops.size() == 1 && decls[g.decl].dist != "dmnorm") { g.big = true; nb++; any = true; }
+                    if (nb > 2) throw Error("grid engine: at most 2 large declarations per sampler are supported");
+                }
+                if (!any) throw Error("grid engine requested but no declaration is large enough to be evaluated grid-wide");
+                TB = opts.rungs_per_pass > 0 ? opts.rungs_per_pass : 16;
+                while (TB > 1 && TB / 2 >= nchains) TB /= 2;
+                if (TB < 1 || TB > 32 || (TB & (TB - 1))) throw Error("rungs_per_pass must be a power of two <= 32");
+                R = 2;
+                W = std::min(32, 256 / TB);  // control lanes per chain inside the finishing CTA
+            }
+        }
 
         std::ostringstream body;
         std::swap(out, body);  // emit model body first to learn which arrays are used
@@ -1257,7 +1383,29 @@ struct Lowerer {
         }
         out << "  }\n";
         for (size_t ui = 0; ui < units.size(); ui++) emit_unit(ui);
+        if (engine == 2) {
+            // dispatchers used by the grid kernels: propose-ahead for an arbitrary stage, stage launch on the host
+            out << "  template <class C> __device__ static __forceinline__ void propose_stage(int s, C& c, const Data& D, int k, double* pend) {\n    switch (s) {\n";
+            for (size_t i = 0; i < units.size(); i++)
+                out << "      case " << i << ": { apt::Pend<S" << i << "::NG> p_; apt::rw_propose<Model, S" << i << ">(c, D, k, 0, p_); apt::store_pend<S" << i
+                    << "::NG>(pend, p_, c.rank); break; }\n";
+            out << "    }\n  }\n";
+            out << "  static void launch_stage(int s, const apt::GArgs& a, int grid, size_t smem, cudaStream_t st) {\n    switch (s) {\n";
+            for (size_t i = 0; i < units.size(); i++)
+                out << "      case " << i << ": apt::grid_pass_kernel<Model, S" << i << "><<<grid, GRID_THREADS, smem, st>>>(a); break;\n";
+            out << "    }\n  }\n";
+            out << "  static void launch_prologue(const apt::GArgs& a, cudaStream_t st) { apt::grid_prologue_kernel<Model><<<1, GRID_THREADS, 0, st>>>(a); }\n";
+            out << "  static int stage_occupancy(int s, size_t smem) {\n    int n = 1;\n    switch (s) {\n";
+            for (size_t i = 0; i < units.size(); i++)
+                out << "      case " << i << ": cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, apt::grid_pass_kernel<Model, S" << i << ">, GRID_THREADS, smem); break;\n";
+            out << "    }\n    return n;\n  }\n";
+        }
         // sweep: stages
+        if (engine != 2) {
+            out << "  template <class C> __device__ static __forceinline__ void propose_stage(int, C&, const Data&, int, double*) {}\n";
+            out << "  static void launch_stage(int, const apt::GArgs&, int, size_t, cudaStream_t) {}\n";
+            out << "  static void launch_prologue(const apt::GArgs&, cudaStream_t) {}\n  static int stage_occupancy(int, size_t) { return 1; }\n";
+        }
         out << "  template <class C> __device__ static __forceinline__ void sweep(C& c, const Data& D, bool active) {\n";
         size_t ui = 0;
         bool first = true;
@@ -1282,7 +1430,7 @@ struct Lowerer {
         std::swap(out, body);  // `body` now holds the model body; `out` is the file
 
         out << "// Generated by the aptb200 lowering step (nimbleapt_b200/csrc/lower.cpp). Do not edit.\n";
-        out << "#include \"apt_host.cuh\"\n";
+        out << "#include \"apt_grid.cuh\"\n#include \"apt_host.cuh\"\n";
         out << "__device__ __forceinline__ double apt_sq(double x) { return x * x; }\n";
         out << "// unnamed namespace: every lowered model defines a type called aptgen::Model; internal linkage keeps the\n// template instantiations of different modules loaded into one process apart.\nnamespace {\nnamespace aptgen {\nusing apt::Data;\n";
         auto emit_tab = [&](const char* name, const std::vector<int>& v) {
@@ -1304,7 +1452,8 @@ struct Lowerer {
             << ", NMON = " << mon.size() << ", NMON2 = " << mon2.size() << ", DMAX = " << DMAX << ", W = " << W << ";\n";
         out << "  static constexpr int NARR = " << used_arrays.size() << ", NIARR = " << iarrays.size() << ", BLKSZ = " << BLKSZ << ", EMPSZ = " << EMPSZ << ";\n";
         out << "  static constexpr int TILES_PER_LADDER = " << tiles << ", TEAMS_PER_CTA = " << teams << ";\n";
-        out << "  static constexpr bool STATE_IN_SMEM = " << (smem_state ? "true" : "false") << ", HAS_FAMILY = " << (has_family ? "true" : "false") << ";\n";
+        out << "  static constexpr bool STATE_IN_SMEM = " << (smem_state && engine == 1 ? "true" : "false") << ", HAS_FAMILY = " << (has_family ? "true" : "false") << ";\n";
+        out << "  static constexpr int ENGINE = " << engine << ", TB = " << TB << ", R = " << R << ", GRID_THREADS = 256, NSTAGE = " << units.size() << ";\n";
         out << "  __device__ static __forceinline__ int mon(int c) { return MON_TAB[c]; }\n";
         out << "  __device__ static __forceinline__ int mon2(int c) { return MON2_TAB[c]; }\n";
         out << body.str();
@@ -1319,7 +1468,7 @@ struct Lowerer {
 
         Lowered L;
         L.source = out.str();
-        L.P = P; L.K = K; L.NU = NU; L.ND = ND; L.NMON = (int)mon.size(); L.NMON2 = (int)mon2.size(); L.DMAX = DMAX; L.W = W; L.engine = 1;
+        L.P = P; L.K = K; L.NU = NU; L.ND = ND; L.NMON = (int)mon.size(); L.NMON2 = (int)mon2.size(); L.DMAX = DMAX; L.W = W; L.engine = engine;
         for (auto* a : used_arrays) { L.arrays.push_back(a); L.array_names.push_back(a->name); }
         L.iarrays = iarrays;
         L.theta0.assign((size_t)P, 0.0);

@@ -28,9 +28,9 @@ def make_tables(niter, L, K, NU, DMAX, seed=1):
     return Z, U, S
 
 
-def run_pair(spec, niter, L=1, inject=True, seed=11, thin=1, record=True, **run_kw):
+def run_pair(spec, niter, L=1, inject=True, seed=11, thin=1, record=True, build_kw=None, **run_kw):
     """Run engine and oracle on identical inputs; returns (engine, oracle, records)."""
-    eng = build_engine(spec, nLadders=L, seed=seed, record=record)
+    eng = build_engine(spec, nLadders=L, seed=seed, record=record, **(build_kw or {}))
     orc = build_oracle(spec, nLadders=L, seed=seed)
     K, NU, DMAX = eng.nTemps, eng.info(nb.api.INFO_N_UNITS), eng.info(nb.api.INFO_DMAX)
     recs = []

@@ -18,13 +18,15 @@ SMALL = {
     "c5": lambda: models.c5_small_logistic(N=256, p=8, K=8),
     "c4": lambda: models.c4_glmm(G=20, per=10, K=4),
     "c3s": lambda: models.logistic(2000, 5, 4),
+    "c3grid": lambda: models.logistic(2000, 5, 4),  # same model through the grid-wide engine (engine = 2)
 }
+BUILD_KW = {"c3grid": dict(engine=2)}
 
 
 @pytest.mark.parametrize("name", list(SMALL))
 def test_logprob_matches_oracle(name):
     spec = SMALL[name]()
-    eng = build_engine(spec)
+    eng = build_engine(spec, **BUILD_KW.get(name, {}))
     orc = build_oracle(spec)
     rng = np.random.default_rng(5)
     P = len(eng.paramNames)
@@ -45,7 +47,7 @@ def test_logprob_matches_oracle(name):
 def test_decisions_bit_identical(name, inject):
     spec = SMALL[name]()
     niter, L = 450, 2  # crosses two sampler adaptations (adaptInterval = 200)
-    eng, orc, recs = run_pair(spec, niter, L=L, inject=inject)
+    eng, orc, recs = run_pair(spec, niter, L=L, inject=inject, build_kw=BUILD_KW.get(name))
     for l in range(L):
         dec_o, swap_o = recs[l]
         dec_e = eng.decisions(l, niter)
