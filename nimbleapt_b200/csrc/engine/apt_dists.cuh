@@ -205,16 +205,21 @@ __device__ __forceinline__ double dexp_log(double x, double scale) {
 // |eta| > 36.74 (p rounds to 1).  To give the SAME accept/reject decisions as the reference even for hot chains
 // that wander there, the fused form is used only for |eta| <= 8, where both agree to < 3.3e-13 absolute per
 // term; beyond that the literal chain is evaluated (a rare, divergent branch: < 4e-6 of rows at the posterior).
-__device__ __forceinline__ double bern_logit_log(double y, double eta) {
+// (kept out of line: it is rare, and inlining it next to every fused term multiplies the code size of the
+//  grid kernel's epilogue beyond the instruction cache)
+__device__ __noinline__ double bern_logit_literal(double y, double eta) {
     if (!(y == 0.0 || y == 1.0)) return isnan(y) ? y : APT_NEG_INF;
-    if (fabs(eta) <= 8.0) {
-        double t = (y == 1.0) ? -eta : eta;  // log p = -log(1 + exp(t))
-        double l = log1p(exp(-fabs(t)));
-        return -(fmax(t, 0.0) + l);
-    }
     if (isnan(eta)) return eta;
     const double p = 1.0 / (1.0 + exp(-eta));
     return dbinom_raw_log(y, 1.0, p, 1.0 - p);
+}
+__device__ __forceinline__ double bern_logit_log(double y, double eta) {
+    if (fabs(eta) <= 8.0 && (y == 0.0 || y == 1.0)) {
+        const double t = (y == 1.0) ? -eta : eta;  // log p = -log(1 + exp(t)) = -(max(t,0) + log(1 + exp(-|t|)))
+        // log(1 + u), u in (3e-4, 1]: the absolute error of forming 1 + u (<= 1.1e-16) is all a SUM of terms needs
+        return -(fmax(t, 0.0) + log(1.0 + exp(-fabs(t))));
+    }
+    return bern_logit_literal(y, eta);
 }
 
 __device__ __forceinline__ double ilogit(double x) { return 1.0 / (1.0 + exp(-x)); }

@@ -98,52 +98,42 @@ __global__ void __launch_bounds__(G::GRID_THREADS) grid_prologue_kernel(const __
     grid_propose_ahead<G>(a, threadIdx.x);
 }
 
-// swap phase + ladder adaptation + output for ladder l by one warp, state in global memory, staged through smem
+// swap phase + ladder adaptation + output for ladder l by the whole finishing CTA, state staged through smem
 template <class G>
-__device__ __forceinline__ void grid_ladder_step(const GArgs& a, int l, double* sm /* 4K doubles + K ints */, int lane) {
-    constexpr int K = G::K, P = G::P, ND = G::ND;
-    double* s_lp = sm;
-    double* s_rs = sm + K;
-    double* s_T = sm + 2 * K;
-    double* s_invT = sm + 3 * K;
-    int* s_slot = reinterpret_cast<int*>(sm + 4 * K);
-    const double* lpd = a.k.lpd + (size_t)l * K * ND;
-    for (int j = lane; j < K; j += 32) {
-        s_T[j] = a.k.temps[(size_t)l * K + j];
-        s_invT[j] = 1.0 / s_T[j];
-        s_slot[j] = a.k.slot[(size_t)l * K + j];
-        const double* q = lpd + s_slot[j] * ND;
-        double s = 0.0;
-#pragma unroll
-        for (int dd = 0; dd < ND; dd++) s += q[dd];
-        s_lp[j] = s;  // logProbTemps[tt] <- model$getLogProb()  (APT:447)
+__device__ __forceinline__ void grid_ladder_step(const GArgs& a, int l, double* sm, int tid) {
+    constexpr int K = G::K, P = G::P, ND = G::ND, THREADS = G::GRID_THREADS;
+    LadderWS<K> ws;
+    ws.carve(sm, reinterpret_cast<int*>(sm + LadderWS<K>::DOUBLES));
+    for (int j = tid; j < K; j += THREADS) {
+        ws.T[j] = a.k.temps[(size_t)l * K + j];
+        ws.invT[j] = 1.0 / ws.T[j];
+        ws.slot[j] = a.k.slot[(size_t)l * K + j];
     }
-    __syncwarp();
+    __syncthreads();
     RngKey rng;
     rng.seed = a.k.seed;
     rng.ladder = a.k.ladder0 + (uint32_t)l;
     rng.iter = a.k.rng_iter0 + (uint64_t)a.it;
-    swap_phase<G>(a.k, l, a.it, s_lp, s_rs, s_invT, s_slot, lane, rng);
-    const long long totalIters = a.k.total_iters0 + a.it + 1;  // APT:489
-    if (a.k.adapt_temps) ladder_adapt<G>(a.k, totalIters, s_lp, s_T, s_invT, lane);
-    write_traces<G>(a.k, l, a.it, a.k.theta + (size_t)l * K * P, s_slot, s_T, s_lp, lane);
-    for (int j = lane; j < K; j += 32) {
-        a.k.temps[(size_t)l * K + j] = s_T[j];
-        a.k.slot[(size_t)l * K + j] = s_slot[j];
-        a.k.lp[(size_t)l * K + j] = s_lp[j];
+    ladder_step<G, THREADS, false>(a.k, l, a.it, a.k.total_iters0 + a.it + 1, tid, ws, a.k.lpd + (size_t)l * K * ND, rng);
+    if (tid < 32) write_traces<G>(a.k, l, a.it, a.k.theta + (size_t)l * K * P, ws.slot, ws.T, ws.lp, tid);
+    __syncthreads();
+    for (int j = tid; j < K; j += THREADS) {
+        a.k.temps[(size_t)l * K + j] = ws.T[j];
+        a.k.slot[(size_t)l * K + j] = ws.slot[j];
+        a.k.lp[(size_t)l * K + j] = ws.lp[j];
     }
-    __syncwarp();
+    __syncthreads();
 }
 
 template <class G, class S>
-__global__ void __launch_bounds__(G::GRID_THREADS, 1) grid_pass_kernel(const __grid_constant__ GArgs a) {
+__global__ void __launch_bounds__(G::GRID_THREADS, G::GRID_MINB) grid_pass_kernel(const __grid_constant__ GArgs a) {
     constexpr int TB = G::TB, R = G::R, NB = S::NBIG, K = G::K, P = G::P, THREADS = G::GRID_THREADS, NWARP = THREADS / 32, W = G::W;
     static_assert(NB >= 1 && NB <= 2, "grid kernel needs 1 or 2 large declarations");
     extern __shared__ __align__(16) double gsm[];
     double* thT = gsm;                    // [P][TB]
     double* red = gsm + P * TB;           // [NWARP][NB*TB]
     double* s_new = red + NWARP * NB * TB;  // [NB*TB]
-    double* s_lad = s_new + NB * TB;      // [NWARP][5K] ladder-step staging
+    double* s_lad = s_new + NB * TB;      // ladder workspace (LadderWS<K>)
     __shared__ int s_last;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nch = a.k.L * K;
@@ -234,8 +224,7 @@ __global__ void __launch_bounds__(G::GRID_THREADS, 1) grid_pass_kernel(const __g
     __threadfence_block();
     __syncthreads();
     if (a.last_of_iter) {
-        for (int l = warp; l < a.k.L; l += NWARP) grid_ladder_step<G>(a, l, s_lad + (size_t)warp * 5 * K, lane);
-        __syncthreads();
+        for (int l = 0; l < a.k.L; l++) grid_ladder_step<G>(a, l, s_lad, tid);
     }
     // ---- 6. propose ahead for the next launch
     grid_propose_ahead<G>(a, tid);
@@ -245,7 +234,7 @@ __global__ void __launch_bounds__(G::GRID_THREADS, 1) grid_pass_kernel(const __g
 template <class G>
 struct GridShape {
     static constexpr size_t smem_bytes(int nbig) {
-        return (size_t)(G::P * G::TB + (G::GRID_THREADS / 32) * nbig * G::TB + nbig * G::TB + (G::GRID_THREADS / 32) * 5 * G::K) * sizeof(double);
+        return (size_t)(G::P * G::TB + (G::GRID_THREADS / 32) * nbig * G::TB + nbig * G::TB + LadderWS<G::K>::DOUBLES + LadderWS<G::K>::INTS) * sizeof(double);
     }
 };
 

@@ -1148,7 +1148,7 @@ struct Lowerer {
                 std::string nm = "ip" + std::to_string(nh++) + "_";
                 out << "        double " << nm << "[R][TB];\n";
                 out << "        _Pragma(\"unroll\") for (int r_ = 0; r_ < R; ++r_) { _Pragma(\"unroll\") for (int c_ = 0; c_ < TB; ++c_) " << nm << "[r_][c_] = 0.0; }\n";
-                out << "        _Pragma(\"unroll 2\") for (int e_ = 0; e_ < " << lp_ << "; ++e_) {\n";
+                out << "        _Pragma(\"unroll 10\") for (int e_ = 0; e_ < " << lp_ << "; ++e_) {\n";
                 out << "          double xr_[R];\n";
                 if (vec) {
                     Env envv = env;
@@ -1160,8 +1160,12 @@ struct Lowerer {
                 } else {
                     out << "          _Pragma(\"unroll\") for (int r_ = 0; r_ < R; ++r_) xr_[r_] = __ldcs(&" << de << ");\n";
                 }
-                out << "          _Pragma(\"unroll\") for (int c_ = 0; c_ < TB; ++c_) { const double b_ = " << pe << "; _Pragma(\"unroll\") for (int r_ = 0; r_ < R; ++r_) "
-                    << nm << "[r_][c_] = fma(xr_[r_], b_, " << nm << "[r_][c_]); }\n";
+                // parameters of two chains per shared-memory load (thT rows are 16-byte aligned when TB is even)
+                out << "          if constexpr (TB % 2 == 0) {\n            _Pragma(\"unroll\") for (int c_ = 0; c_ < TB; c_ += 2) { const double2 b2_ = *reinterpret_cast<const double2*>(&" << pe
+                    << "); _Pragma(\"unroll\") for (int r_ = 0; r_ < R; ++r_) { " << nm << "[r_][c_] = fma(xr_[r_], b2_.x, " << nm << "[r_][c_]); " << nm
+                    << "[r_][c_ + 1] = fma(xr_[r_], b2_.y, " << nm << "[r_][c_ + 1]); } }\n          } else {\n";
+                out << "            _Pragma(\"unroll\") for (int c_ = 0; c_ < TB; ++c_) { const double b_ = " << pe << "; _Pragma(\"unroll\") for (int r_ = 0; r_ < R; ++r_) "
+                    << nm << "[r_][c_] = fma(xr_[r_], b_, " << nm << "[r_][c_]); }\n          }\n";
                 out << "        }\n";
                 hoisted[ip.get()] = nm + "[r_][c_]";
             }
@@ -1368,7 +1372,7 @@ struct Lowerer {
                 TB = opts.rungs_per_pass > 0 ? opts.rungs_per_pass : 16;
                 while (TB > 1 && TB / 2 >= nchains) TB /= 2;
                 if (TB < 1 || TB > 32 || (TB & (TB - 1))) throw Error("rungs_per_pass must be a power of two <= 32");
-                R = 2;
+                R = opts.cta_threads == 2 ? 2 : 1;  // rows per thread (cta_threads doubles as the tuning knob of the grid engine)
                 W = std::min(32, 256 / TB);  // control lanes per chain inside the finishing CTA
             }
         }
@@ -1453,7 +1457,7 @@ struct Lowerer {
         out << "  static constexpr int NARR = " << used_arrays.size() << ", NIARR = " << iarrays.size() << ", BLKSZ = " << BLKSZ << ", EMPSZ = " << EMPSZ << ";\n";
         out << "  static constexpr int TILES_PER_LADDER = " << tiles << ", TEAMS_PER_CTA = " << teams << ";\n";
         out << "  static constexpr bool STATE_IN_SMEM = " << (smem_state && engine == 1 ? "true" : "false") << ", HAS_FAMILY = " << (has_family ? "true" : "false") << ";\n";
-        out << "  static constexpr int ENGINE = " << engine << ", TB = " << TB << ", R = " << R << ", GRID_THREADS = 256, NSTAGE = " << units.size() << ";\n";
+        out << "  static constexpr int ENGINE = " << engine << ", TB = " << TB << ", R = " << R << ", GRID_THREADS = 256, GRID_MINB = " << (engine == 2 && opts.lanes_per_chain > 0 ? opts.lanes_per_chain : 2) << ", NSTAGE = " << units.size() << ";\n";
         out << "  __device__ static __forceinline__ int mon(int c) { return MON_TAB[c]; }\n";
         out << "  __device__ static __forceinline__ int mon2(int c) { return MON2_TAB[c]; }\n";
         out << body.str();
