@@ -11,6 +11,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include "apt_sferr_table.cuh"
+#include "apt_softplus.cuh"
 
 namespace apt {
 
@@ -216,8 +217,7 @@ __device__ __noinline__ double bern_logit_literal(double y, double eta) {
 __device__ __forceinline__ double bern_logit_log(double y, double eta) {
     if (fabs(eta) <= 8.0 && (y == 0.0 || y == 1.0)) {
         const double t = (y == 1.0) ? -eta : eta;  // log p = -log(1 + exp(t)) = -(max(t,0) + log(1 + exp(-|t|)))
-        // log(1 + u), u in (3e-4, 1]: the absolute error of forming 1 + u (<= 1.1e-16) is all a SUM of terms needs
-        return -(fmax(t, 0.0) + log(1.0 + exp(-fabs(t))));
+        return -(fmax(t, 0.0) + apt_softplus_neg(fabs(t)));
     }
     return bern_logit_literal(y, eta);
 }

@@ -18,6 +18,16 @@
 
 namespace apt {
 
+// software prefetch of streamed data one row-step ahead (L2 by default; -DAPT_PREFETCH_L1 pulls into L1)
+__device__ __forceinline__ void prefetch_data(const void* p) {
+#ifdef APT_PREFETCH_L1
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#else
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#endif
+}
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
 struct GArgs {
     KArgs k;
     double* partial;      // [grid][2][TB] per-CTA partial sums
@@ -29,6 +39,7 @@ struct GArgs {
     int next_stage, next_pass;  // what to propose ahead (-1: nothing, the run ends or is interrupted)
     long long next_it;
     int last_of_iter;     // this launch completes the iteration: swap phase, ladder adaptation, output
+    long long* dbg;       // optional phase timestamps of the finishing CTA (APTB200_DEBUG_TIMING=1)
 };
 
 #define APT_PEND_DOUBLES 12
@@ -156,17 +167,17 @@ __global__ void __launch_bounds__(G::GRID_THREADS, G::GRID_MINB) grid_pass_kerne
         for (int cc = 0; cc < TB; cc++) acc[g][cc] = 0.0;
     {
         const long n = S::big_n(0);
-        const long ngrp = n / R;
-        for (long grp = (long)blockIdx.x * THREADS + tid; grp < ngrp; grp += (long)gridDim.x * THREADS)
-            S::template big_eval<0, TB, R>(a.k.D, thT, (int)(grp * R), acc[0]);
-        if (blockIdx.x == 0 && tid < (int)(n - ngrp * R)) S::template big_eval<0, TB, 1>(a.k.D, thT, (int)(ngrp * R + tid), acc[0]);
+        const long ngrp = n / R, step = (long)gridDim.x * THREADS;
+        for (long grp = (long)blockIdx.x * THREADS + tid; grp < ngrp; grp += step)
+            S::template big_eval<0, TB, R>(a.k.D, thT, (int)(grp * R), grp + step < ngrp ? (int)((grp + step) * R) : -1, acc[0]);
+        if (blockIdx.x == 0 && tid < (int)(n - ngrp * R)) S::template big_eval<0, TB, 1>(a.k.D, thT, (int)(ngrp * R + tid), -1, acc[0]);
     }
     if constexpr (NB == 2) {
         const long n = S::big_n(1);
-        const long ngrp = n / R;
-        for (long grp = (long)blockIdx.x * THREADS + tid; grp < ngrp; grp += (long)gridDim.x * THREADS)
-            S::template big_eval<1, TB, R>(a.k.D, thT, (int)(grp * R), acc[NB - 1]);
-        if (blockIdx.x == 0 && tid < (int)(n - ngrp * R)) S::template big_eval<1, TB, 1>(a.k.D, thT, (int)(ngrp * R + tid), acc[NB - 1]);
+        const long ngrp = n / R, step = (long)gridDim.x * THREADS;
+        for (long grp = (long)blockIdx.x * THREADS + tid; grp < ngrp; grp += step)
+            S::template big_eval<1, TB, R>(a.k.D, thT, (int)(grp * R), grp + step < ngrp ? (int)((grp + step) * R) : -1, acc[NB - 1]);
+        if (blockIdx.x == 0 && tid < (int)(n - ngrp * R)) S::template big_eval<1, TB, 1>(a.k.D, thT, (int)(ngrp * R + tid), -1, acc[NB - 1]);
     }
     // ---- 3. CTA reduction (fixed order: lanes by butterfly, warps ascending)
 #pragma unroll
@@ -192,14 +203,47 @@ __global__ void __launch_bounds__(G::GRID_THREADS, G::GRID_MINB) grid_pass_kerne
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    for (int v = warp; v < NB * TB; v += NWARP) {
-        double s = 0.0;
-        for (int b = lane; b < (int)gridDim.x; b += 32) s += __ldcg(&a.partial[(size_t)b * NB * TB + v]);
+    if (a.dbg && tid == 0) a.dbg[0] = clock64();
+    {
+        // NB*TB values, each summed over the CTAs' partials in a fixed order by a group of 16 lanes
+        constexpr int GRP = 16;
+        for (int v = tid / GRP; v < NB * TB; v += THREADS / GRP) {
+            const int sub = tid % GRP;
+            double s = 0.0;
+#pragma unroll 4
+            for (int b = sub; b < (int)gridDim.x; b += GRP) s += __ldcg(&a.partial[(size_t)b * NB * TB + v]);
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane == 0) s_new[v] = s;
+            for (int o = GRP / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (sub == 0) s_new[v] = s;
+        }
+    }
+    // pull the control state of this pass's chains into L1 with one wave of independent prefetches: the control
+    // step below is a chain of dependent global loads (slot -> state -> ...), each an L2 round trip otherwise
+    {
+        const int nchl = min(TB, nch - q0);
+        for (int i = tid; i < nchl * 8; i += THREADS) {
+            const int q = q0 + i / 8, part = i % 8;
+            const int l = q / K, kk = q % K;
+            const char* base = nullptr;
+            switch (part) {
+                case 0: base = (const char*)(a.k.slot + (size_t)l * K + kk); break;
+                case 1: base = (const char*)(a.k.lpd + ((size_t)l * K + kk) * G::ND); break;
+                case 2: base = (const char*)(a.k.scale + ((size_t)l * K + kk) * G::NU); break;
+                case 3: base = (const char*)(a.k.cnt + ((size_t)l * K + kk) * G::NU * 3); break;
+                case 4: base = (const char*)(a.pend + (size_t)q * APT_PEND_DOUBLES); break;
+                case 5: base = (const char*)(a.k.temps + (size_t)l * K + kk); break;
+                case 6: base = (const char*)(a.scratch + (size_t)q * 2 * G::DMAX); break;
+                case 7: base = (const char*)(a.scratch + (size_t)q * 2 * G::DMAX + G::DMAX); break;
+            }
+            prefetch_l1(base);
+        }
+        for (int i = tid; i < nchl * ((P * 8 + 127) / 128); i += THREADS) {
+            const int q = q0 + i / ((P * 8 + 127) / 128), line = i % ((P * 8 + 127) / 128);
+            prefetch_l1((const char*)(a.k.theta + (size_t)q * P) + line * 128);
+        }
     }
     __syncthreads();
+    if (a.dbg && tid == 0) a.dbg[1] = clock64();
     // ---- 5. control step: finish the tempered update of each chain of this pass (one tile of W lanes per chain)
     {
         const int tile = tid / W;
@@ -223,11 +267,14 @@ __global__ void __launch_bounds__(G::GRID_THREADS, G::GRID_MINB) grid_pass_kerne
     }
     __threadfence_block();
     __syncthreads();
+    if (a.dbg && tid == 0) a.dbg[2] = clock64();
     if (a.last_of_iter) {
         for (int l = 0; l < a.k.L; l++) grid_ladder_step<G>(a, l, s_lad, tid);
     }
+    if (a.dbg && tid == 0 && a.next_stage >= 0) a.dbg[3] = clock64();
     // ---- 6. propose ahead for the next launch
     grid_propose_ahead<G>(a, tid);
+    if (a.dbg) { __syncthreads(); if (tid == 0 && a.next_stage >= 0) a.dbg[4] = clock64(); }
     if (tid == 0) *a.ticket = 0u;
 }
 

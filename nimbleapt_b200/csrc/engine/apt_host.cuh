@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -84,6 +85,7 @@ struct Engine {
     DevBuf<int> slot, cnt, accswap;
     DevBuf<double> g_partial, g_pend, g_scratch;  // grid engine
     DevBuf<unsigned int> g_ticket;
+    DevBuf<long long> g_dbg;
     int num_sms = 148, grid_occ = 1;
     DevBuf<double> samples, samples2, samplesT, samples2T, logprobs, temptraj;
     DevBuf<double> tabZ, tabU, tabS;
@@ -168,6 +170,7 @@ struct Engine {
         if constexpr (G::ENGINE == 2) {
             g_partial.alloc((size_t)num_sms * 8 * 2 * G::TB);
             g_ticket.alloc(1); g_ticket.zero(stream);
+            g_dbg.alloc(8); g_dbg.zero(stream);
             g_pend.alloc(nch * APT_PEND_DOUBLES); g_pend.zero(stream);
             g_scratch.alloc(nch * 2 * G::DMAX); g_scratch.zero(stream);
         } else {
@@ -338,6 +341,7 @@ struct Engine {
                 g.k = a;
                 g.partial = g_partial.p; g.ticket = g_ticket.p; g.pend = g_pend.p; g.scratch = g_scratch.p;
                 g.npass = npass;
+                g.dbg = getenv("APTB200_DEBUG_TIMING") ? g_dbg.p : nullptr;
                 APT_CUDA(cudaEventRecord(ev0, stream));
                 g.next_stage = 0; g.next_pass = 0; g.next_it = it0;
                 G::launch_prologue(g, stream);
@@ -362,6 +366,10 @@ struct Engine {
                 timing.kernel_ms += ms; timing.main_kernel_ms += ms; timing.launches += nl; timing.main_launches += nl - 1;
                 rngIter += (uint64_t)(it1 - it0);
                 totalIters += (it1 - it0);
+                if (g.dbg) {
+                    auto v = d2h(g_dbg.p, 5);
+                    fprintf(stderr, "[aptb200] finishing CTA cycles: reduce %lld finish %lld ladder %lld propose %lld\n", v[1] - v[0], v[2] - v[1], v[3] - v[2], v[4] - v[3]);
+                }
             }
         }
         return false;

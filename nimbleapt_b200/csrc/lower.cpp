@@ -1108,7 +1108,7 @@ struct Lowerer {
         if (bigs.empty()) {
             out << "    __device__ static constexpr int big_group(int gi) { return 0; }\n";
             out << "    __host__ __device__ static constexpr long big_n(int gi) { return 0; }\n";
-            out << "    template <int GI, int TB, int R> __device__ static __forceinline__ void big_eval(const Data& D, const double* __restrict__ thT, int i0, double (&acc)[TB]) {}\n";
+            out << "    template <int GI, int TB, int R> __device__ static __forceinline__ void big_eval(const Data& D, const double* __restrict__ thT, int i0, int i_next, double (&acc)[TB]) {}\n";
             return;
         }
         out << "    __device__ static constexpr int big_group(int gi) { return ";
@@ -1117,7 +1117,7 @@ struct Lowerer {
         out << "    __host__ __device__ static constexpr long big_n(int gi) { return ";
         for (size_t i = 0; i + 1 < bigs.size(); i++) out << "gi == " << i << " ? " << decls[u.groups[bigs[i]].decl].ninst << "L : ";
         out << decls[u.groups[bigs.back()].decl].ninst << "L; }\n";
-        out << "    template <int GI, int TB, int R> __device__ static __forceinline__ void big_eval(const Data& D, const double* __restrict__ thT, int i0, double (&acc)[TB]) {\n";
+        out << "    template <int GI, int TB, int R> __device__ static __forceinline__ void big_eval(const Data& D, const double* __restrict__ thT, int i0, int i_next, double (&acc)[TB]) {\n";
         for (size_t bi = 0; bi < bigs.size(); bi++) {
             CDecl& d = decls[u.groups[bigs[bi]].decl];
             if (d.loops.size() != 1 || d.dist == "dmnorm") throw Error("grid engine: big declarations must be univariate with exactly one loop");
@@ -1146,6 +1146,13 @@ struct Lowerer {
                     ds->a[0]->name == d.loops[0].var && dv->second.dims[0] % 2 == 0 && d.loops[0].lo % 2 == 1)
                     vec = true;
                 std::string nm = "ip" + std::to_string(nh++) + "_";
+                {   // the rows this thread evaluates next are pulled towards the SM while the current ones are computed
+                    Env envn = env;
+                    envn[d.loops[0].var] = "(" + std::to_string(d.loops[0].lo) + " + i_next)";
+                    int tmp;
+                    std::string dn = gen_slice_elem(ds, "e_", envn, tmp);
+                    out << "        if (i_next >= 0) { _Pragma(\"unroll\") for (int e_ = 0; e_ < " << lp_ << "; ++e_) apt::prefetch_data(&" << dn << "); }\n";
+                }
                 out << "        double " << nm << "[R][TB];\n";
                 out << "        _Pragma(\"unroll\") for (int r_ = 0; r_ < R; ++r_) { _Pragma(\"unroll\") for (int c_ = 0; c_ < TB; ++c_) " << nm << "[r_][c_] = 0.0; }\n";
                 out << "        _Pragma(\"unroll 10\") for (int e_ = 0; e_ < " << lp_ << "; ++e_) {\n";

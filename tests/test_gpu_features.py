@@ -1,0 +1,140 @@
+"""-m gpu: the rest of the reference's run()/control surface against the oracle: continuation (reset=FALSE,
+resetMV, APT:378-385), thin/thin2 + monitors2 (APT:514-539), temperPriors=FALSE (APT:713-718, 827-830),
+log=TRUE and reflective=TRUE proposals (APT:694-708), adaptScaleOnly / adaptive=FALSE (APT:726, 852-868),
+fixed ladder (adaptTemps=FALSE), resetTempering (APT:365-367), and posterior summaries within 4 MCSE."""
+import numpy as np
+import pytest
+
+import models
+import nimbleapt_b200 as nb
+from helpers import build_engine, build_oracle, make_tables
+
+pytestmark = pytest.mark.gpu
+
+
+def _both(spec, L=1, **kw):
+    return build_engine(spec, nLadders=L, record=True, **kw), build_oracle(spec, nLadders=L)
+
+
+def _run_both(eng, orc, niter, seed, **kw):
+    K, NU, DMAX = eng.nTemps, eng.info(nb.api.INFO_N_UNITS), eng.info(nb.api.INFO_DMAX)
+    L = eng.nLadders
+    Z, U, S = make_tables(niter, L, K, NU, DMAX, seed=seed)
+    recs = [orc.set_tables(l, Z[:, l].copy(), U[:, l].copy(), S[:, l].copy(), record=True, niter=niter) for l in range(L)]
+    eng.run(niter, _inject=dict(Z=Z, U=U, S=S), **kw)
+    orc.run(niter, **{k: v for k, v in kw.items()})
+    for l in range(L):
+        assert np.array_equal(eng.decisions(l, niter), recs[l][0])
+        assert np.array_equal(eng.swapRecord(l, niter) >> 16, recs[l][1] >> 16)
+    return recs
+
+
+def test_continuation_and_thinning():
+    spec = dict(models.c2_mixture(n=20, K=8, tmax=200.0))
+    spec["monitors2"] = ["theta[2]"]
+    eng, orc = _both(spec, L=2)
+    _run_both(eng, orc, 300, 1, thin=3, thin2=7)
+    _run_both(eng, orc, 250, 2, reset=False, thin=5, thin2=7)            # appends (APT:378-380)
+    for l in range(2):
+        assert eng.mvSamples.matrix(l).shape == orc.samples(l).shape == (100 + 50, 2)
+        np.testing.assert_allclose(eng.mvSamples.matrix(l), orc.samples(l), rtol=1e-8, atol=1e-10)
+        np.testing.assert_allclose(eng.mvSamples2.matrix(l), orc.samples2(l), rtol=1e-8, atol=1e-10)
+        assert eng.mvSamples2.matrix(l).shape == (300 // 7 + 250 // 7, 1)
+        assert eng.tempTrajLadder(l).shape == (50, 8)                     # tempTraj only covers the last run (APT:386)
+        np.testing.assert_allclose(eng.logProbsLadder(l), orc.logProbs(l), rtol=1e-10)
+    _run_both(eng, orc, 120, 3, reset=False, resetMV=True, thin=4)        # sample store restarts (APT:381-384)
+    assert eng.mvSamples.matrix(0).shape == (30, 2)
+    np.testing.assert_allclose(eng.mvSamples.matrix(1), orc.samples(1), rtol=1e-8, atol=1e-10)
+    _run_both(eng, orc, 100, 4, reset=True, resetTempering=True, adaptTemps=False)  # fixed ladder after reset
+    np.testing.assert_allclose(eng.TempsLadder(0), orc.Temps(0), rtol=1e-9)
+    np.testing.assert_allclose(eng.modelState(0), orc.rung_state(0, 0), rtol=1e-8)  # APT:548
+
+
+@pytest.mark.parametrize("variant", ["temperPriorsFalse", "logScale", "reflective", "scaleOnly", "nonAdaptive", "identityPropCov"])
+def test_control_options(variant):
+    if variant in ("temperPriorsFalse", "logScale", "reflective"):
+        spec = models.c4_glmm(G=6, per=8, K=4)
+        samplers = [dict(target="u[%d]" % (k + 1), type="sampler_RW_tempered", control=dict(temperPriors=variant != "temperPriorsFalse")) for k in range(6)]
+        samplers.append(dict(target="b[1:2]", type="sampler_RW_block_tempered", control=dict(temperPriors=variant != "temperPriorsFalse")))
+        ctl = dict(temperPriors=variant != "temperPriorsFalse")
+        if variant == "logScale":
+            ctl["log"] = True
+        if variant == "reflective":
+            ctl["reflective"] = True
+        samplers.append(dict(target="sigma", type="sampler_RW_tempered", control=ctl))
+        spec = dict(spec, samplers=samplers)
+    else:
+        spec = models.logistic(300, 4, 4, propcov=variant != "identityPropCov")
+        ctl = dict(spec["samplers"][0]["control"])
+        if variant == "scaleOnly":
+            ctl["adaptScaleOnly"] = True
+        if variant == "nonAdaptive":
+            ctl["adaptive"] = False
+        ctl["adaptInterval"] = 50
+        spec = dict(spec, samplers=[dict(spec["samplers"][0], control=ctl)])
+    eng, orc = _both(spec)
+    _run_both(eng, orc, 220, 7)
+    np.testing.assert_allclose(eng.mvSamples.matrix(0), orc.samples(0), rtol=1e-8, atol=1e-10)
+    sc = eng.scales(0)
+    for k in range(eng.nTemps):
+        for s in range(sc.shape[1]):
+            assert np.isclose(sc[k, s], orc.scale(0, k, s), rtol=1e-9)
+
+
+def test_posterior_within_4_mcse_c2():
+    """Exact posterior of config 2: |theta1| ~ N(ybar1 s, s/n), theta2 ~ N(ybar2 s, s/n), both signs equally likely."""
+    spec = models.c2_mixture(n=20, K=8, tmax=200.0)
+    L, niter = 256, 6000
+    eng = build_engine(spec, nLadders=L)
+    eng.run(niter, thin=2)
+    s = eng.mvSamples.matrix(-1)[:, 500:, :]
+    y = spec["data"]["y"]
+    n = y.shape[0]
+    shrink = 1.0 / (1.0 + 1.0 / (n * 100.0 ** 2))
+    for est, truth in ((np.abs(s[:, :, 0]).mean(1), y[:, 0].mean() * shrink), (s[:, :, 1].mean(1), y[:, 1].mean() * shrink),
+                       ((s[:, :, 0] > 0).mean(1), 0.5), (s[:, :, 1].var(1, ddof=1), shrink / n)):
+        mcse = est.std(ddof=1) / np.sqrt(L)
+        assert abs(est.mean() - truth) < 4 * mcse, (est.mean(), truth, mcse)
+    q = np.quantile(s[:, :, 1].reshape(-1), [0.05, 0.5, 0.95])
+    from scipy import stats
+    ref = stats.norm.ppf([0.05, 0.5, 0.95], y[:, 1].mean() * shrink, np.sqrt(shrink / n))
+    np.testing.assert_allclose(q, ref, atol=0.01)
+
+
+def test_posterior_matches_oracle_within_4_mcse_c1():
+    """Config 1 (vignette model): engine vs oracle posterior summaries from independent ladders (different ladder ids)."""
+    spec = models.c1_vignette(nObs=100, K=8)
+    Lg, Lo, niter = 128, 8, 4000
+    eng = build_engine(spec, nLadders=Lg, ladder0=1000)
+    eng.run(niter, thin=2)
+    orc = build_oracle(spec, nLadders=Lo)
+    orc.run(niter, thin=2, nthreads=8)
+    g = eng.mvSamples.matrix(-1)[:, 500:, :]
+    o = np.stack([orc.samples(l)[500:] for l in range(Lo)])
+    for f in (lambda a: np.abs(a[:, :, 0]).mean(1), lambda a: np.abs(a[:, :, 1]).mean(1), lambda a: (a[:, :, 0] > 0).mean(1),
+              lambda a: a[:, :, 0].var(1)):
+        eg, eo = f(g), f(o)
+        se = np.sqrt(eg.var(ddof=1) / Lg + eo.var(ddof=1) / Lo)
+        assert abs(eg.mean() - eo.mean()) < 4 * se, (eg.mean(), eo.mean(), se)
+
+
+def test_c4_family_medium():
+    """Mixed scalar family / block / log-scale samplers at a size where the family spans several tiles."""
+    spec = models.c4_glmm(G=60, per=20, K=6)
+    eng, orc = _both(spec)
+    _run_both(eng, orc, 210, 9)
+    np.testing.assert_allclose(eng.mvSamples.matrix(0), orc.samples(0), rtol=1e-7, atol=1e-9)
+    np.testing.assert_allclose(eng.logProbsLadder(0), orc.logProbs(0), rtol=1e-9)
+
+
+def test_grid_engine_mid_size_against_oracle():
+    """Grid engine on a 100k-row logistic model, 16 rungs in one pass: decisions vs the oracle for 30 iterations."""
+    spec = models.logistic(100000, 50, 16, seed_off=3)
+    eng, orc = _both(spec, engine=2)
+    _run_both(eng, orc, 30, 11)
+    np.testing.assert_allclose(eng.logProbsLadder(0), orc.logProbs(0), rtol=1e-11)
+    th = eng.rungStates(0)
+    tot, _ = eng.calculate(th)
+    for k in (0, 7, 15):
+        ref, _ = orc.logprob(th[k])
+        assert abs(tot[k] - ref) <= 1e-12 * abs(ref)
