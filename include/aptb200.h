@@ -38,7 +38,7 @@
  *     block 0x8000       -> acceptance uniform U(w0,w1) (only consumed when 0 >= logMHR, nimble `decide`)
  *   swap proposal ii (0-based) of the iteration: unit = 0xFFFFFFFF, rung field = ii, block 0:
  *     rcat uniform U(w0,w1), acceptance uniform U(w2,w3)
- *   U(hi,lo) = ((hi >> 5) * 2^26 + (lo >> 6) + 0.5) * 2^-53, strictly inside (0,1).
+ *   U(hi,lo) = ((hi >> 6) * 2^26 + (lo >> 6) + 0.5) * 2^-52: 52 random bits, strictly inside (0,1).
  * A sampler "unit" is the 0-based position of the sampler in conf$samplerConfs (APT:283 `ss`).
  */
 #ifndef APTB200_H

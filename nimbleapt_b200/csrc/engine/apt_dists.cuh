@@ -222,6 +222,28 @@ __device__ __forceinline__ double bern_logit_log(double y, double eta) {
     return bern_logit_literal(y, eta);
 }
 
+// N chains at once (grid engine): acc[c] += log p(y | eta[c]); fused terms in batches of 8 in lock step
+template <int N>
+__device__ __forceinline__ void bern_logit_acc(double y, const double (&eta)[N], double (&acc)[N]) {
+    constexpr int M = N >= 8 ? 8 : N;
+    const bool yok = (y == 0.0 || y == 1.0);
+    const double sgn = (y == 1.0) ? -1.0 : 1.0;
+#pragma unroll
+    for (int h = 0; h < N; h += M) {
+        double a[M], sp[M];
+#pragma unroll
+        for (int j = 0; j < M; j++) a[j] = fmin(fabs(eta[h + j]), 8.0);  // keeps the fast path's domain; out-of-range terms are replaced below
+        apt_softplus_neg_batch<M>(a, sp);
+#pragma unroll
+        for (int j = 0; j < M; j++) {
+            const double t = sgn * eta[h + j];
+            double v = -(fmax(t, 0.0) + sp[j]);
+            if (!(yok && fabs(eta[h + j]) <= 8.0)) v = bern_logit_literal(y, eta[h + j]);
+            acc[h + j] += v;
+        }
+    }
+}
+
 __device__ __forceinline__ double ilogit(double x) { return 1.0 / (1.0 + exp(-x)); }
 __device__ __forceinline__ double logit(double p) { return log(p / (1.0 - p)); }
 __device__ __forceinline__ double iprobit(double x) { return 0.5 * erfc(-x * 0.70710678118654752440); }

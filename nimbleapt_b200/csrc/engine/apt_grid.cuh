@@ -27,6 +27,14 @@ __device__ __forceinline__ void prefetch_data(const void* p) {
 #endif
 }
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+// Ampere-style asynchronous global -> shared copies (LDGSTS); each thread only ever waits for its own copies
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 struct GArgs {
     KArgs k;
@@ -145,6 +153,7 @@ __global__ void __launch_bounds__(G::GRID_THREADS, G::GRID_MINB) grid_pass_kerne
     double* red = gsm + P * TB;           // [NWARP][NB*TB]
     double* s_new = red + NWARP * NB * TB;  // [NB*TB]
     double* s_lad = s_new + NB * TB;      // ladder workspace (LadderWS<K>)
+    double* xbuf = s_lad + LadderWS<K>::DOUBLES + LadderWS<K>::INTS;  // [RING_SLOTS][THREADS] private cp.async rings
     __shared__ int s_last;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nch = a.k.L * K;
@@ -168,16 +177,21 @@ __global__ void __launch_bounds__(G::GRID_THREADS, G::GRID_MINB) grid_pass_kerne
     {
         const long n = S::big_n(0);
         const long ngrp = n / R, step = (long)gridDim.x * THREADS;
-        for (long grp = (long)blockIdx.x * THREADS + tid; grp < ngrp; grp += step)
-            S::template big_eval<0, TB, R>(a.k.D, thT, (int)(grp * R), grp + step < ngrp ? (int)((grp + step) * R) : -1, acc[0]);
-        if (blockIdx.x == 0 && tid < (int)(n - ngrp * R)) S::template big_eval<0, TB, 1>(a.k.D, thT, (int)(ngrp * R + tid), -1, acc[0]);
+        int ring_pos = 0;
+        long grp = (long)blockIdx.x * THREADS + tid;
+        if (S::RING && grp < ngrp) S::template ring_prime<0>(a.k.D, xbuf, tid, (int)(grp * R));
+        for (; grp < ngrp; grp += step)
+            S::template big_eval<0, TB, R>(a.k.D, thT, (int)(grp * R), grp + step < ngrp ? (int)((grp + step) * R) : -1, acc[0], xbuf, ring_pos, tid);
+        if (S::RING) cp_async_wait<0>();
+        if (!S::RING && blockIdx.x == 0 && tid < (int)(n - ngrp * R)) S::template big_eval<0, TB, 1>(a.k.D, thT, (int)(ngrp * R + tid), -1, acc[0], xbuf, ring_pos, tid);
     }
     if constexpr (NB == 2) {
+        int ring_pos2 = 0;
         const long n = S::big_n(1);
         const long ngrp = n / R, step = (long)gridDim.x * THREADS;
         for (long grp = (long)blockIdx.x * THREADS + tid; grp < ngrp; grp += step)
-            S::template big_eval<1, TB, R>(a.k.D, thT, (int)(grp * R), grp + step < ngrp ? (int)((grp + step) * R) : -1, acc[NB - 1]);
-        if (blockIdx.x == 0 && tid < (int)(n - ngrp * R)) S::template big_eval<1, TB, 1>(a.k.D, thT, (int)(ngrp * R + tid), -1, acc[NB - 1]);
+            S::template big_eval<1, TB, R>(a.k.D, thT, (int)(grp * R), grp + step < ngrp ? (int)((grp + step) * R) : -1, acc[NB - 1], xbuf, ring_pos2, tid);
+        if (blockIdx.x == 0 && tid < (int)(n - ngrp * R)) S::template big_eval<1, TB, 1>(a.k.D, thT, (int)(ngrp * R + tid), -1, acc[NB - 1], xbuf, ring_pos2, tid);
     }
     // ---- 3. CTA reduction (fixed order: lanes by butterfly, warps ascending)
 #pragma unroll
@@ -281,7 +295,7 @@ __global__ void __launch_bounds__(G::GRID_THREADS, G::GRID_MINB) grid_pass_kerne
 template <class G>
 struct GridShape {
     static constexpr size_t smem_bytes(int nbig) {
-        return (size_t)(G::P * G::TB + (G::GRID_THREADS / 32) * nbig * G::TB + nbig * G::TB + LadderWS<G::K>::DOUBLES + LadderWS<G::K>::INTS) * sizeof(double);
+        return (size_t)(G::P * G::TB + (G::GRID_THREADS / 32) * nbig * G::TB + nbig * G::TB + LadderWS<G::K>::DOUBLES + LadderWS<G::K>::INTS + (size_t)G::RING_SLOTS * G::GRID_THREADS) * sizeof(double);
     }
 };
 

@@ -212,14 +212,30 @@ struct Engine {
         std::swap(b.n, nb.n);
     }
 
-    void refresh_lpd() {  // initializeModel / calculate(): recompute every chain's per-declaration logProbs
-        const int nst = L * K;
-        const int threads = 128;
-        const int blocks = (int)(((size_t)nst * G::W + threads - 1) / threads);
-        logprob_kernel<G><<<blocks, threads, 0, stream>>>(D, theta.p, nst, lpd.p);
-        APT_CUDA(cudaGetLastError());
-        timing.launches++;
+    // whole-model per-declaration logProbs of `nst` states on the device (initializeModel / calculate())
+    void eval_lpd(const double* d_theta, int nst, double* d_out) {
+        if constexpr (G::ENGINE == 2) {
+            constexpr int NBLK = 128, THREADS = 256;
+            DevBuf<double> part;
+            part.alloc((size_t)nst * NBLK * G::ND);
+            for (int s0 = 0; s0 < nst; s0 += 32768) {
+                const int n = std::min(32768, nst - s0);
+                logprob_wide_kernel<G, NBLK, THREADS><<<dim3(NBLK, n), THREADS, 0, stream>>>(D, d_theta + (size_t)s0 * P, part.p + (size_t)s0 * NBLK * G::ND);
+            }
+            APT_CUDA(cudaGetLastError());
+            logprob_wide_reduce<G, NBLK><<<(nst * G::ND + 127) / 128, 128, 0, stream>>>(part.p, nst, d_out);
+            APT_CUDA(cudaGetLastError());
+            APT_CUDA(cudaStreamSynchronize(stream));
+            timing.launches += 2;
+        } else {
+            const int threads = 128;
+            const int blocks = (int)(((size_t)nst * G::W + threads - 1) / threads);
+            logprob_kernel<G><<<blocks, threads, 0, stream>>>(D, d_theta, nst, d_out);
+            APT_CUDA(cudaGetLastError());
+            timing.launches++;
+        }
     }
+    void refresh_lpd() { eval_lpd(theta.p, L * K, lpd.p); }
 
     void run(const aptmod_run_args* ra) {
         APT_CUDA(cudaSetDevice(device));
@@ -323,6 +339,7 @@ struct Engine {
             const int nchain = L * K;
             const int npass = (nchain + G::TB - 1) / G::TB;
             size_t smem = GridShape<G>::smem_bytes(2);
+            if (grid_occ_known == 0 && smem > 48 * 1024) G::set_stage_smem(smem);
             if (grid_occ_known == 0) {
                 grid_occ = std::max(1, G::stage_occupancy(0, smem));
                 grid_occ_known = 1;
@@ -382,9 +399,7 @@ struct Engine {
         DevBuf<double> dth, dout;
         dth.alloc((size_t)n * P); dout.alloc((size_t)n * G::ND);
         APT_CUDA(cudaMemcpyAsync(dth.p, th, (size_t)n * P * 8, cudaMemcpyHostToDevice, stream));
-        const int threads = 128;
-        logprob_kernel<G><<<(int)(((size_t)n * G::W + threads - 1) / threads), threads, 0, stream>>>(D, dth.p, n, dout.p);
-        APT_CUDA(cudaGetLastError());
+        eval_lpd(dth.p, n, dout.p);
         APT_CUDA(cudaMemcpyAsync(out_lpd, dout.p, (size_t)n * G::ND * 8, cudaMemcpyDeviceToHost, stream));
         APT_CUDA(cudaStreamSynchronize(stream));
     }

@@ -16,6 +16,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <set>
@@ -1108,7 +1109,9 @@ struct Lowerer {
         if (bigs.empty()) {
             out << "    __device__ static constexpr int big_group(int gi) { return 0; }\n";
             out << "    __host__ __device__ static constexpr long big_n(int gi) { return 0; }\n";
-            out << "    template <int GI, int TB, int R> __device__ static __forceinline__ void big_eval(const Data& D, const double* __restrict__ thT, int i0, int i_next, double (&acc)[TB]) {}\n";
+            out << "    template <int GI, int TB, int R> __device__ static __forceinline__ void big_eval(const Data& D, const double* __restrict__ thT, int i0, int i_next, double (&acc)[TB], double* xbuf, int& ring_pos, int tid_) {}\n";
+            out << "    template <int GI> __device__ static __forceinline__ void ring_prime(const Data& D, double* xbuf, int tid_, int i0) {}\n";
+            out << "    static constexpr bool RING = false;\n";
             return;
         }
         out << "    __device__ static constexpr int big_group(int gi) { return ";
@@ -1117,7 +1120,9 @@ struct Lowerer {
         out << "    __host__ __device__ static constexpr long big_n(int gi) { return ";
         for (size_t i = 0; i + 1 < bigs.size(); i++) out << "gi == " << i << " ? " << decls[u.groups[bigs[i]].decl].ninst << "L : ";
         out << decls[u.groups[bigs.back()].decl].ninst << "L; }\n";
-        out << "    template <int GI, int TB, int R> __device__ static __forceinline__ void big_eval(const Data& D, const double* __restrict__ thT, int i0, int i_next, double (&acc)[TB]) {\n";
+        out << "    template <int GI, int TB, int R> __device__ static __forceinline__ void big_eval(const Data& D, const double* __restrict__ thT, int i0, int i_next, double (&acc)[TB], double* xbuf, int& ring_pos, int tid_) {\n";
+        std::ostringstream prime;  // ring_prime<GI> bodies
+        bool any_ring = false;
         for (size_t bi = 0; bi < bigs.size(); bi++) {
             CDecl& d = decls[u.groups[bigs[bi]].decl];
             if (d.loops.size() != 1 || d.dist == "dmnorm") throw Error("grid engine: big declarations must be univariate with exactly one loop");
@@ -1146,6 +1151,47 @@ struct Lowerer {
                     ds->a[0]->name == d.loops[0].var && dv->second.dims[0] % 2 == 0 && d.loops[0].lo % 2 == 1)
                     vec = true;
                 std::string nm = "ip" + std::to_string(nh++) + "_";
+                const int BW = 5, RD = 5, RS = 6;
+                const bool ring = vec && !any_ring && bigs.size() == 1 && lp_ % BW == 0 && lp_ / BW >= RD && ring_ok;
+                if (ring) {
+                    // cp.async ring: every thread streams its own rows through a private shared-memory ring, RD blocks
+                    // of BW columns ahead (half a row), so the HBM latency never reaches the FMA chain
+                    any_ring = true;
+                    const int NBR = lp_ / BW;
+                    auto xaddr = [&](const std::string& row, const std::string& col) {
+                        Env e2 = env;
+                        e2[d.loops[0].var] = "(" + std::to_string(d.loops[0].lo) + " + " + row + ")";
+                        int tmp;
+                        return gen_slice_elem(ds, col, e2, tmp);
+                    };
+                    out << "        double " << nm << "[R][TB];\n";
+                    out << "        _Pragma(\"unroll\") for (int c_ = 0; c_ < TB; ++c_) " << nm << "[0][c_] = 0.0;\n";
+                    out << "        _Pragma(\"unroll\") for (int b_ = 0; b_ < " << NBR << "; ++b_) {\n";
+                    out << "          apt::cp_async_wait<" << RD - 1 << ">();\n          double xr_[" << BW << "];\n";
+                    out << "          _Pragma(\"unroll\") for (int e_ = 0; e_ < " << BW << "; ++e_) xr_[e_] = xbuf[(ring_pos * " << BW << " + e_) * GRID_THREADS + tid_];\n";
+                    out << "          { const int nb_ = b_ + " << RD << "; int slot_ = ring_pos + " << RD << "; if (slot_ >= " << RS << ") slot_ -= " << RS << ";\n";
+                    out << "            if (nb_ < " << NBR << ") { _Pragma(\"unroll\") for (int e_ = 0; e_ < " << BW << "; ++e_) apt::cp_async8(&xbuf[(slot_ * " << BW
+                        << " + e_) * GRID_THREADS + tid_], &" << xaddr("i0", "(nb_ * " + std::to_string(BW) + " + e_)") << "); }\n";
+                    out << "            else if (i_next >= 0) { _Pragma(\"unroll\") for (int e_ = 0; e_ < " << BW << "; ++e_) apt::cp_async8(&xbuf[(slot_ * " << BW
+                        << " + e_) * GRID_THREADS + tid_], &" << xaddr("i_next", "((nb_ - " + std::to_string(NBR) + ") * " + std::to_string(BW) + " + e_)") << "); }\n";
+                    out << "            apt::cp_async_commit(); }\n";
+                    {
+                        Env e3 = env;
+                        int tmp;
+                        cv_mode = true;
+                        std::string pe2 = gen_slice_elem(ps, "(b_ * " + std::to_string(BW) + " + e_)", e3, tmp);
+                        out << "          _Pragma(\"unroll\") for (int e_ = 0; e_ < " << BW << "; ++e_) {\n";
+                        out << "            _Pragma(\"unroll\") for (int c_ = 0; c_ < TB; c_ += 2) { const double2 b2_ = *reinterpret_cast<const double2*>(&" << pe2 << "); "
+                            << nm << "[0][c_] = fma(xr_[e_], b2_.x, " << nm << "[0][c_]); " << nm << "[0][c_ + 1] = fma(xr_[e_], b2_.y, " << nm << "[0][c_ + 1]); }\n          }\n";
+                    }
+                    out << "          ring_pos = (ring_pos + 1 == " << RS << ") ? 0 : ring_pos + 1;\n        }\n";
+                    prime << "      if constexpr (GI == " << bi << ") {\n        _Pragma(\"unroll\") for (int b_ = 0; b_ < " << RD << "; ++b_) {\n"
+                          << "          _Pragma(\"unroll\") for (int e_ = 0; e_ < " << BW << "; ++e_) apt::cp_async8(&xbuf[(b_ * " << BW << " + e_) * GRID_THREADS + tid_], &"
+                          << xaddr("i0", "(b_ * " + std::to_string(BW) + " + e_)") << ");\n          apt::cp_async_commit();\n        }\n      }\n";
+                    ring_slots = RS * BW;
+                    hoisted[ip.get()] = nm + "[r_][c_]";
+                    continue;
+                }
                 {   // the rows this thread evaluates next are pulled towards the SM while the current ones are computed
                     Env envn = env;
                     envn[d.loops[0].var] = "(" + std::to_string(d.loops[0].lo) + " + i_next)";
@@ -1178,13 +1224,24 @@ struct Lowerer {
             }
             out << "        _Pragma(\"unroll\") for (int r_ = 0; r_ < R; ++r_) {\n";
             out << "          const double x_ = " << gen_dbl(d.lhs, env) << ";\n";
-            out << "          _Pragma(\"unroll\") for (int c_ = 0; c_ < TB; ++c_) acc[c_] += " << density_expr(d, "x_", env) << ";\n";
+            double sz_;
+            if (d.dist == "dbinom" && opts.fuse_links && (is_call(d.iargs[0], "ilogit") || is_call(d.iargs[0], "expit")) && try_ceval(d.iargs[1], {}, sz_) && sz_ == 1.0) {
+                // fused Bernoulli-logit terms of all chains evaluated in lock step (explicit ILP across chains)
+                out << "          double eta_[TB];\n          _Pragma(\"unroll\") for (int c_ = 0; c_ < TB; ++c_) eta_[c_] = " << gen_dbl(d.iargs[0]->a[0], env) << ";\n";
+                out << "          apt::bern_logit_acc<TB>(x_, eta_, acc);\n";
+            } else {
+                out << "          _Pragma(\"unroll\") for (int c_ = 0; c_ < TB; ++c_) acc[c_] += " << density_expr(d, "x_", env) << ";\n";
+            }
             out << "        }\n      }\n";
             cv_mode = false;
             hoisted.clear();
         }
         out << "    }\n";
+        out << "    template <int GI> __device__ static __forceinline__ void ring_prime(const Data& D, double* xbuf, int tid_, int i0) {\n" << prime.str() << "    }\n";
+        out << "    static constexpr bool RING = " << (any_ring ? "true" : "false") << ";\n";
     }
+    int ring_slots = 0;
+    bool ring_ok = true;
 
     void emit_lp_functions() {
         for (int di : stoch_decls) {
@@ -1381,6 +1438,7 @@ struct Lowerer {
                 if (TB < 1 || TB > 32 || (TB & (TB - 1))) throw Error("rungs_per_pass must be a power of two <= 32");
                 R = opts.cta_threads == 2 ? 2 : 1;  // rows per thread (cta_threads doubles as the tuning knob of the grid engine)
                 W = std::min(32, 256 / TB);  // control lanes per chain inside the finishing CTA
+                ring_ok = (R == 1) && !getenv("APTB200_NO_RING");
             }
         }
 
@@ -1406,6 +1464,10 @@ struct Lowerer {
                 out << "      case " << i << ": apt::grid_pass_kernel<Model, S" << i << "><<<grid, GRID_THREADS, smem, st>>>(a); break;\n";
             out << "    }\n  }\n";
             out << "  static void launch_prologue(const apt::GArgs& a, cudaStream_t st) { apt::grid_prologue_kernel<Model><<<1, GRID_THREADS, 0, st>>>(a); }\n";
+            out << "  static void set_stage_smem(size_t smem) {\n";
+            for (size_t i = 0; i < units.size(); i++)
+                out << "    cudaFuncSetAttribute(apt::grid_pass_kernel<Model, S" << i << ">, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);\n";
+            out << "  }\n";
             out << "  static int stage_occupancy(int s, size_t smem) {\n    int n = 1;\n    switch (s) {\n";
             for (size_t i = 0; i < units.size(); i++)
                 out << "      case " << i << ": cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, apt::grid_pass_kernel<Model, S" << i << ">, GRID_THREADS, smem); break;\n";
@@ -1415,7 +1477,7 @@ struct Lowerer {
         if (engine != 2) {
             out << "  template <class C> __device__ static __forceinline__ void propose_stage(int, C&, const Data&, int, double*) {}\n";
             out << "  static void launch_stage(int, const apt::GArgs&, int, size_t, cudaStream_t) {}\n";
-            out << "  static void launch_prologue(const apt::GArgs&, cudaStream_t) {}\n  static int stage_occupancy(int, size_t) { return 1; }\n";
+            out << "  static void launch_prologue(const apt::GArgs&, cudaStream_t) {}\n  static int stage_occupancy(int, size_t) { return 1; }\n  static void set_stage_smem(size_t) {}\n";
         }
         out << "  template <class C> __device__ static __forceinline__ void sweep(C& c, const Data& D, bool active) {\n";
         size_t ui = 0;
@@ -1464,7 +1526,7 @@ struct Lowerer {
         out << "  static constexpr int NARR = " << used_arrays.size() << ", NIARR = " << iarrays.size() << ", BLKSZ = " << BLKSZ << ", EMPSZ = " << EMPSZ << ";\n";
         out << "  static constexpr int TILES_PER_LADDER = " << tiles << ", TEAMS_PER_CTA = " << teams << ";\n";
         out << "  static constexpr bool STATE_IN_SMEM = " << (smem_state && engine == 1 ? "true" : "false") << ", HAS_FAMILY = " << (has_family ? "true" : "false") << ";\n";
-        out << "  static constexpr int ENGINE = " << engine << ", TB = " << TB << ", R = " << R << ", GRID_THREADS = 256, GRID_MINB = " << (engine == 2 && opts.lanes_per_chain > 0 ? opts.lanes_per_chain : 2) << ", NSTAGE = " << units.size() << ";\n";
+        out << "  static constexpr int ENGINE = " << engine << ", TB = " << TB << ", R = " << R << ", GRID_THREADS = 256, RING_SLOTS = " << ring_slots << ", GRID_MINB = " << (engine == 2 && opts.lanes_per_chain > 0 ? opts.lanes_per_chain : 2) << ", NSTAGE = " << units.size() << ";\n";
         out << "  __device__ static __forceinline__ int mon(int c) { return MON_TAB[c]; }\n";
         out << "  __device__ static __forceinline__ int mon2(int c) { return MON2_TAB[c]; }\n";
         out << body.str();

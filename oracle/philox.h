@@ -25,9 +25,9 @@ static inline void apt_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-/* 53-bit uniform strictly inside (0,1) from two 32-bit words */
+/* 52-bit uniform strictly inside (0,1) from two 32-bit words (2^52 - 1/2 is representable, 2^53 - 1/2 is not) */
 static inline double apt_u53(uint32_t hi, uint32_t lo) {
-    return ((double)(hi >> 5) * 67108864.0 + (double)(lo >> 6) + 0.5) * (1.0 / 9007199254740992.0);
+    return ((double)(hi >> 6) * 67108864.0 + (double)(lo >> 6) + 0.5) * (1.0 / 4503599627370496.0);
 }
 
 #define APT_SLOT_ACCEPT 0x8000u
