@@ -121,8 +121,8 @@ __global__ void __launch_bounds__(G::GRID_THREADS) grid_prologue_kernel(const __
 template <class G>
 __device__ __forceinline__ void grid_ladder_step(const GArgs& a, int l, double* sm, int tid) {
     constexpr int K = G::K, P = G::P, ND = G::ND, THREADS = G::GRID_THREADS;
-    LadderWS<K> ws;
-    ws.carve(sm, reinterpret_cast<int*>(sm + LadderWS<K>::DOUBLES));
+    LadderWS<K, true> ws;
+    ws.carve(sm, reinterpret_cast<int*>(sm + LadderWS<K, true>::DOUBLES));
     for (int j = tid; j < K; j += THREADS) {
         ws.T[j] = a.k.temps[(size_t)l * K + j];
         ws.invT[j] = 1.0 / ws.T[j];
@@ -133,7 +133,7 @@ __device__ __forceinline__ void grid_ladder_step(const GArgs& a, int l, double* 
     rng.seed = a.k.seed;
     rng.ladder = a.k.ladder0 + (uint32_t)l;
     rng.iter = a.k.rng_iter0 + (uint64_t)a.it;
-    ladder_step<G, THREADS, false>(a.k, l, a.it, a.k.total_iters0 + a.it + 1, tid, ws, a.k.lpd + (size_t)l * K * ND, rng);
+    ladder_step<G, THREADS, false, true>(a.k, l, a.it, a.k.total_iters0 + a.it + 1, tid, ws, a.k.lpd + (size_t)l * K * ND, rng);
     if (tid < 32) write_traces<G>(a.k, l, a.it, a.k.theta + (size_t)l * K * P, ws.slot, ws.T, ws.lp, tid);
     __syncthreads();
     for (int j = tid; j < K; j += THREADS) {
@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(G::GRID_THREADS, G::GRID_MINB) grid_pass_kerne
     double* red = gsm + P * TB;           // [NWARP][NB*TB]
     double* s_new = red + NWARP * NB * TB;  // [NB*TB]
     double* s_lad = s_new + NB * TB;      // ladder workspace (LadderWS<K>)
-    double* xbuf = s_lad + LadderWS<K>::DOUBLES + LadderWS<K>::INTS;  // [RING_SLOTS][THREADS] private cp.async rings
+    double* xbuf = s_lad + LadderWS<K, true>::DOUBLES + LadderWS<K, true>::INTS;  // [RING_SLOTS][THREADS] private cp.async rings
     __shared__ int s_last;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nch = a.k.L * K;
@@ -168,40 +168,43 @@ __global__ void __launch_bounds__(G::GRID_THREADS, G::GRID_MINB) grid_pass_kerne
         thT[idx] = a.k.theta[((size_t)l * K + sl) * P + p];
     }
     __syncthreads();
-    // ---- 2. one pass over the data
-    double acc[NB][TB];
+    // ---- 2. one pass over the data.  CS threads share a row, each owning TBT = TB / CS of the chains (fewer
+    //         accumulators per thread -> more resident warps to cover the FP64 dependent-issue latency)
+    constexpr int CS = G::CSPLIT, TBT = TB / CS, RPC = THREADS / CS;
+    const int half = tid % CS, coff = half * TBT;
+    double acc[NB][TBT];
 #pragma unroll
     for (int g = 0; g < NB; g++)
 #pragma unroll
-        for (int cc = 0; cc < TB; cc++) acc[g][cc] = 0.0;
+        for (int cc = 0; cc < TBT; cc++) acc[g][cc] = 0.0;
     {
         const long n = S::big_n(0);
-        const long ngrp = n / R, step = (long)gridDim.x * THREADS;
+        const long ngrp = n / R, step = (long)gridDim.x * RPC;
         int ring_pos = 0;
-        long grp = (long)blockIdx.x * THREADS + tid;
+        long grp = (long)blockIdx.x * RPC + tid / CS;
         if (S::RING && grp < ngrp) S::template ring_prime<0>(a.k.D, xbuf, tid, (int)(grp * R));
         for (; grp < ngrp; grp += step)
-            S::template big_eval<0, TB, R>(a.k.D, thT, (int)(grp * R), grp + step < ngrp ? (int)((grp + step) * R) : -1, acc[0], xbuf, ring_pos, tid);
+            S::template big_eval<0, TBT, R>(a.k.D, thT + coff, (int)(grp * R), grp + step < ngrp ? (int)((grp + step) * R) : -1, acc[0], xbuf, ring_pos, tid);
         if (S::RING) cp_async_wait<0>();
-        if (!S::RING && blockIdx.x == 0 && tid < (int)(n - ngrp * R)) S::template big_eval<0, TB, 1>(a.k.D, thT, (int)(ngrp * R + tid), -1, acc[0], xbuf, ring_pos, tid);
+        if (!S::RING && blockIdx.x == 0 && tid / CS < (int)(n - ngrp * R)) S::template big_eval<0, TBT, 1>(a.k.D, thT + coff, (int)(ngrp * R + tid / CS), -1, acc[0], xbuf, ring_pos, tid);
     }
     if constexpr (NB == 2) {
         int ring_pos2 = 0;
         const long n = S::big_n(1);
-        const long ngrp = n / R, step = (long)gridDim.x * THREADS;
-        for (long grp = (long)blockIdx.x * THREADS + tid; grp < ngrp; grp += step)
-            S::template big_eval<1, TB, R>(a.k.D, thT, (int)(grp * R), grp + step < ngrp ? (int)((grp + step) * R) : -1, acc[NB - 1], xbuf, ring_pos2, tid);
-        if (blockIdx.x == 0 && tid < (int)(n - ngrp * R)) S::template big_eval<1, TB, 1>(a.k.D, thT, (int)(ngrp * R + tid), -1, acc[NB - 1], xbuf, ring_pos2, tid);
+        const long ngrp = n / R, step = (long)gridDim.x * RPC;
+        for (long grp = (long)blockIdx.x * RPC + tid / CS; grp < ngrp; grp += step)
+            S::template big_eval<1, TBT, R>(a.k.D, thT + coff, (int)(grp * R), grp + step < ngrp ? (int)((grp + step) * R) : -1, acc[NB - 1], xbuf, ring_pos2, tid);
+        if (blockIdx.x == 0 && tid / CS < (int)(n - ngrp * R)) S::template big_eval<1, TBT, 1>(a.k.D, thT + coff, (int)(ngrp * R + tid / CS), -1, acc[NB - 1], xbuf, ring_pos2, tid);
     }
-    // ---- 3. CTA reduction (fixed order: lanes by butterfly, warps ascending)
+    // ---- 3. CTA reduction (fixed order: lanes of equal `half` by butterfly, warps ascending)
 #pragma unroll
     for (int g = 0; g < NB; g++)
 #pragma unroll
-        for (int cc = 0; cc < TB; cc++) {
+        for (int cc = 0; cc < TBT; cc++) {
             double v = acc[g][cc];
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if (lane == 0) red[warp * NB * TB + g * TB + cc] = v;
+            for (int o = 16; o >= CS; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane < CS) red[warp * NB * TB + g * TB + coff + cc] = v;
         }
     __syncthreads();
     if (tid < NB * TB) {
@@ -295,7 +298,7 @@ __global__ void __launch_bounds__(G::GRID_THREADS, G::GRID_MINB) grid_pass_kerne
 template <class G>
 struct GridShape {
     static constexpr size_t smem_bytes(int nbig) {
-        return (size_t)(G::P * G::TB + (G::GRID_THREADS / 32) * nbig * G::TB + nbig * G::TB + LadderWS<G::K>::DOUBLES + LadderWS<G::K>::INTS + (size_t)G::RING_SLOTS * G::GRID_THREADS) * sizeof(double);
+        return (size_t)(G::P * G::TB + (G::GRID_THREADS / 32) * nbig * G::TB + nbig * G::TB + LadderWS<G::K, true>::DOUBLES + LadderWS<G::K, true>::INTS + (size_t)G::RING_SLOTS * G::GRID_THREADS) * sizeof(double);
     }
 };
 

@@ -950,7 +950,7 @@ struct Lowerer {
     std::string gen_load(const Var& v, const EP& e, const Env& env) {
         if (v.role == Var::PARAM) {
             std::string off = gen_offset(v, e, env);
-            if (cv_mode) return "thT[(" + std::to_string(v.theta_off) + " + " + off + ") * TB + c_]";
+            if (cv_mode) return "thT[(" + std::to_string(v.theta_off) + " + " + off + ") * TBS + c_]";
             return "th[" + std::to_string(v.theta_off) + " + " + off + "]";
         }
         if (v.role == Var::CONST && v.size <= 64) {  // small constants are folded into the code
@@ -1121,6 +1121,7 @@ struct Lowerer {
         for (size_t i = 0; i + 1 < bigs.size(); i++) out << "gi == " << i << " ? " << decls[u.groups[bigs[i]].decl].ninst << "L : ";
         out << decls[u.groups[bigs.back()].decl].ninst << "L; }\n";
         out << "    template <int GI, int TB, int R> __device__ static __forceinline__ void big_eval(const Data& D, const double* __restrict__ thT, int i0, int i_next, double (&acc)[TB], double* xbuf, int& ring_pos, int tid_) {\n";
+        out << "      constexpr int TBS = Model::TB;  // chain stride of thT (a thread may own only TB of the TBS chains)\n";
         std::ostringstream prime;  // ring_prime<GI> bodies
         bool any_ring = false;
         for (size_t bi = 0; bi < bigs.size(); bi++) {
@@ -1414,7 +1415,7 @@ struct Lowerer {
         choose_shape(W, tiles, teams, smem_state);
         // ---- engine selection.  Grid engine: few chains, at least one declaration too large for one CTA per
         // chain (config 3: N = 1e6 rows): every tempered update of all chains is served by ONE pass over the data.
-        int engine = 1, TB = 1, R = 1;
+        int engine = 1, TB = 1, R = 1, csplit = 1;
         {
             long maxfull = 0;
             for (auto& u : units)
@@ -1437,6 +1438,7 @@ struct Lowerer {
                 while (TB > 1 && TB / 2 >= nchains) TB /= 2;
                 if (TB < 1 || TB > 32 || (TB & (TB - 1))) throw Error("rungs_per_pass must be a power of two <= 32");
                 R = opts.cta_threads == 2 ? 2 : 1;  // rows per thread (cta_threads doubles as the tuning knob of the grid engine)
+                csplit = (opts.cta_threads == 12 && TB >= 2) ? 2 : 1;  // threads per row, each owning TB / csplit chains (measured slower on B200: off by default)
                 W = std::min(32, 256 / TB);  // control lanes per chain inside the finishing CTA
                 ring_ok = (R == 1) && !getenv("APTB200_NO_RING");
             }
@@ -1526,7 +1528,7 @@ struct Lowerer {
         out << "  static constexpr int NARR = " << used_arrays.size() << ", NIARR = " << iarrays.size() << ", BLKSZ = " << BLKSZ << ", EMPSZ = " << EMPSZ << ";\n";
         out << "  static constexpr int TILES_PER_LADDER = " << tiles << ", TEAMS_PER_CTA = " << teams << ";\n";
         out << "  static constexpr bool STATE_IN_SMEM = " << (smem_state && engine == 1 ? "true" : "false") << ", HAS_FAMILY = " << (has_family ? "true" : "false") << ";\n";
-        out << "  static constexpr int ENGINE = " << engine << ", TB = " << TB << ", R = " << R << ", GRID_THREADS = 256, RING_SLOTS = " << ring_slots << ", GRID_MINB = " << (engine == 2 && opts.lanes_per_chain > 0 ? opts.lanes_per_chain : 2) << ", NSTAGE = " << units.size() << ";\n";
+        out << "  static constexpr int ENGINE = " << engine << ", TB = " << TB << ", R = " << R << ", GRID_THREADS = 256, RING_SLOTS = " << ring_slots << ", CSPLIT = " << csplit << ", GRID_MINB = " << (engine == 2 && opts.lanes_per_chain > 0 ? opts.lanes_per_chain : (csplit == 2 ? 3 : 2)) << ", NSTAGE = " << units.size() << ";\n";
         out << "  __device__ static __forceinline__ int mon(int c) { return MON_TAB[c]; }\n";
         out << "  __device__ static __forceinline__ int mon2(int c) { return MON2_TAB[c]; }\n";
         out << body.str();
