@@ -197,50 +197,80 @@ __device__ __forceinline__ double dexp_log(double x, double scale) {
 }
 
 // Fused form of  y ~ dbinom(prob = ilogit(eta), size = 1)  (lowering peephole, build option fuse_links):
-//   log p(y | eta) = y*eta - log(1 + exp(eta)),  evaluated as  -(softplus(-s*eta)) with s = 2y-1.
-// One exp + one log1p instead of exp + divide + (log | bd0 series); more accurate than the literal
-// ilogit -> 1-p -> dbinom_raw chain, and equal to it to ~1e-16 absolute per term.
-//
-// The reference's own chain p = 1/(1+exp(-eta)); q = 1-p; dbinom_raw(y, 1, p, q) loses accuracy as |eta| grows
-// (q carries an absolute error of ~1.1e-16, i.e. a relative error 1.1e-16 * e^|eta|) and saturates to -Inf for
-// |eta| > 36.74 (p rounds to 1).  To give the SAME accept/reject decisions as the reference even for hot chains
-// that wander there, the fused form is used only for |eta| <= 8, where both agree to < 3.3e-13 absolute per
-// term; beyond that the literal chain is evaluated (a rare, divergent branch: < 4e-6 of rows at the posterior).
-// (kept out of line: it is rare, and inlining it next to every fused term multiplies the code size of the
-//  grid kernel's epilogue beyond the instruction cache)
-__device__ __noinline__ double bern_logit_literal(double y, double eta) {
-    if (!(y == 0.0 || y == 1.0)) return isnan(y) ? y : APT_NEG_INF;
+//   log p(y | eta) = -(max(t, 0) + log(1 + exp(-|t|))),  t = (1 - 2y) eta          (apt_softplus.cuh)
+// instead of the reference's chain  p = 1/(1+exp(-eta)); q = 1-p; dbinom_raw(y, 1, p, q).  Walking through
+// dbinom_raw for n = 1 shows that the chain equals the exact value to ~1e-16 ABSOLUTE in every branch but one:
+//   * "good sign" (y=1, eta>0 | y=0, eta<0): -bd0(1, big) - small = -small - small^2/2 - ..., small = 1-big known to
+//     1.1e-16 absolute  -> equals -log1p(exp(-|eta|)) to 1e-16;
+//   * y=1, eta<0: log(p), p = 1/(1+exp(|eta|)) computed directly -> relative 2e-16;  -Inf once exp(-eta) overflows;
+//   * y=0, eta>0: log(q), q = 1 - 1/(1+exp(-eta)): q carries an absolute error 1.1e-16, i.e. the term is wrong by
+//     1.1e-16 e^eta, and saturates to -Inf beyond eta = 36.74 (p rounds to 1).
+// To give the SAME accept/reject decisions as the reference even for hot chains that wander there, that one branch
+// is reproduced literally for eta > 8 (below 8 both agree to < 3.3e-13); everything else takes the fused form.
+__device__ __noinline__ double bern_logit_invalid(double y, double eta) {
+    if (isnan(y) || isnan(eta)) return y + eta;
+    return APT_NEG_INF;  // dbinom: non-integer or out-of-range x
+}
+// the reference's chain verbatim; only reached for NaN / Inf / |eta| > 709 (exp about to overflow)
+__device__ __noinline__ double bern_logit_generic(double y, double eta) {
     if (isnan(eta)) return eta;
     const double p = 1.0 / (1.0 + exp(-eta));
     return dbinom_raw_log(y, 1.0, p, 1.0 - p);
 }
+__device__ __forceinline__ double bern_logit_literal_q(double eta) {  // y = 0, eta > 8
+    const double e = apt_exp_neg(eta);
+    const double p = 1.0 / (1.0 + e);
+    const double q = 1.0 - p;
+    return apt_log_pos(q);  // q == 0 -> -Inf
+}
 __device__ __forceinline__ double bern_logit_log(double y, double eta) {
-    if (fabs(eta) <= 8.0 && (y == 0.0 || y == 1.0)) {
-        const double t = (y == 1.0) ? -eta : eta;  // log p = -log(1 + exp(t)) = -(max(t,0) + log(1 + exp(-|t|)))
-        return -(fmax(t, 0.0) + apt_softplus_neg(fabs(t)));
-    }
-    return bern_logit_literal(y, eta);
+    if (!(y == 0.0 || y == 1.0)) return bern_logit_invalid(y, eta);
+    if (!(fabs(eta) <= 709.0)) return bern_logit_generic(y, eta);
+    const double t = (y == 1.0) ? -eta : eta;
+    double r = -(fmax(t, 0.0) + apt_softplus_neg(fmin(fabs(t), 64.0)));
+    if (y == 0.0 && eta > 8.0) r = bern_logit_literal_q(eta);
+    return r;
 }
 
-// N chains at once (grid engine): acc[c] += log p(y | eta[c]); fused terms in batches of 8 in lock step
+// N chains at once (grid engine): acc[c] += log p(y | eta[c]); fused terms in batches of 8 in lock step.  The two
+// fix-ups (literal q branch, non-finite / overflowing eta) are tested once per batch, not once per term.
 template <int N>
 __device__ __forceinline__ void bern_logit_acc(double y, const double (&eta)[N], double (&acc)[N]) {
     constexpr int M = N >= 8 ? 8 : N;
-    const bool yok = (y == 0.0 || y == 1.0);
-    const double sgn = (y == 1.0) ? -1.0 : 1.0;
+    const bool y0 = (y == 0.0);
+    if (!(y0 || y == 1.0)) {
+#pragma unroll
+        for (int j = 0; j < N; j++) acc[j] += bern_logit_invalid(y, eta[j]);
+        return;
+    }
+    const double sgn = y0 ? 1.0 : -1.0;
 #pragma unroll
     for (int h = 0; h < N; h += M) {
-        double a[M], sp[M];
-#pragma unroll
-        for (int j = 0; j < M; j++) a[j] = fmin(fabs(eta[h + j]), 8.0);  // keeps the fast path's domain; out-of-range terms are replaced below
-        apt_softplus_neg_batch<M>(a, sp);
+        double a[M], v[M];
+        double emax = -CUDART_INF;
+        bool odd = false;
 #pragma unroll
         for (int j = 0; j < M; j++) {
-            const double t = sgn * eta[h + j];
-            double v = -(fmax(t, 0.0) + sp[j]);
-            if (!(yok && fabs(eta[h + j]) <= 8.0)) v = bern_logit_literal(y, eta[h + j]);
-            acc[h + j] += v;
+            const double e = eta[h + j];
+            a[j] = fmin(fabs(e), 64.0);
+            emax = fmax(emax, e);
+            odd |= !(fabs(e) <= 709.0);  // NaN, Inf, or exp(|eta|) about to overflow: generic path
         }
+        apt_softplus_neg_batch<M>(a, v);
+#pragma unroll
+        for (int j = 0; j < M; j++) v[j] = -(fmax(sgn * eta[h + j], 0.0) + v[j]);
+        if (y0 && emax > 8.0) {
+#pragma unroll
+            for (int j = 0; j < M; j++)
+                if (eta[h + j] > 8.0) v[j] = bern_logit_literal_q(eta[h + j]);
+        }
+        if (odd) {
+#pragma unroll
+            for (int j = 0; j < M; j++)
+                if (!(fabs(eta[h + j]) <= 709.0)) v[j] = bern_logit_generic(y, eta[h + j]);
+        }
+#pragma unroll
+        for (int j = 0; j < M; j++) acc[h + j] += v[j];
     }
 }
 

@@ -48,6 +48,8 @@ struct GArgs {
     long long next_it;
     int last_of_iter;     // this launch completes the iteration: swap phase, ladder adaptation, output
     long long* dbg;       // optional phase timestamps of the finishing CTA (APTB200_DEBUG_TIMING=1)
+    double* delta;        // [L*K][2*DMAX] block-proposal increments precomputed for the next launch (+ work space)
+    long long* delta_tag; // [L*K][2]  (iteration, timesAdapted) the increments were computed for
 };
 
 #define APT_PEND_DOUBLES 12
@@ -108,7 +110,33 @@ __device__ __forceinline__ void grid_propose_ahead(const GArgs& a, int tid) {
     if (q >= a.k.L * K) return;
     const int l = q / K, kk = q % K;
     Ctx<G> c = grid_ctx<G>(a, l, q, a.next_it, tid);
-    G::propose_stage(a.next_stage, c, a.k.D, kk, a.pend + (size_t)q * APT_PEND_DOUBLES);
+    const double* delta = nullptr;
+    if (a.delta && G::stage_is_block(a.next_stage)) {
+        // valid only if computed for this very iteration and if the rung has not adapted since (APT:859-868)
+        const long long t_it = __ldcg(&a.delta_tag[(size_t)q * 2]), t_ad = __ldcg(&a.delta_tag[(size_t)q * 2 + 1]);
+        const int nad = c.cnt[(kk * G::NU + G::stage_unit0(a.next_stage)) * 3 + 2];
+        if (t_it == a.next_it && t_ad == (long long)nad) delta = a.delta + (size_t)q * 2 * G::DMAX;
+    }
+    G::propose_stage(a.next_stage, c, a.k.D, kk, a.pend + (size_t)q * APT_PEND_DOUBLES, delta);
+}
+
+// the dedicated CTA: increments of the NEXT launch's block proposals, computed while the others stream
+template <class G>
+__device__ __forceinline__ void grid_precompute_delta(const GArgs& a, int tid) {
+    constexpr int K = G::K, W = G::W, TB = G::TB;
+    const int tile = tid / W;
+    if (tile >= TB) return;
+    const int q = a.next_pass * TB + tile;
+    if (q >= a.k.L * K) return;
+    const int l = q / K, kk = q % K;
+    Ctx<G> c = grid_ctx<G>(a, l, q, a.next_it, tid);
+    double* out = a.delta + (size_t)q * 2 * G::DMAX;
+    const int nad = c.cnt[(kk * G::NU + G::stage_unit0(a.next_stage)) * 3 + 2];
+    G::delta_stage(a.next_stage, c, kk, out + G::DMAX, out);
+    if (c.rank == 0) {
+        a.delta_tag[(size_t)q * 2] = a.next_it;
+        a.delta_tag[(size_t)q * 2 + 1] = (long long)nad;
+    }
 }
 
 // first launch of a run: only the proposals of (stage 0, pass 0)
@@ -158,6 +186,12 @@ __global__ void __launch_bounds__(G::GRID_THREADS, G::GRID_MINB) grid_pass_kerne
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nch = a.k.L * K;
     const int q0 = a.pass * TB;
+    // One CTA does not stream: it precomputes the increments of the next launch's block proposals, which depend on
+    // the rungs' sampler state and on slot-addressed normals only.  The control step then just adds them.
+    const bool has_dcta = a.delta != nullptr && a.next_stage >= 0 && G::stage_is_block(a.next_stage) && gridDim.x > 2;
+    const int nstream = (int)gridDim.x - (has_dcta ? 1 : 0);
+    const bool is_dcta = has_dcta && blockIdx.x == gridDim.x - 1;
+    if (is_dcta) grid_precompute_delta<G>(a, tid);
     // ---- 1. proposed states of this pass's chains -> shared memory, param-major / chain-minor
     for (int idx = tid; idx < P * TB; idx += THREADS) {
         const int p = idx / TB, cc = idx % TB;
@@ -179,7 +213,7 @@ __global__ void __launch_bounds__(G::GRID_THREADS, G::GRID_MINB) grid_pass_kerne
         for (int cc = 0; cc < TBT; cc++) acc[g][cc] = 0.0;
     {
         const long n = S::big_n(0);
-        const long ngrp = n / R, step = (long)gridDim.x * RPC;
+        const long ngrp = is_dcta ? 0 : n / R, step = (long)nstream * RPC;
         int ring_pos = 0;
         long grp = (long)blockIdx.x * RPC + tid / CS;
         if (S::RING && grp < ngrp) S::template ring_prime<0>(a.k.D, xbuf, tid, (int)(grp * R));
@@ -191,7 +225,7 @@ __global__ void __launch_bounds__(G::GRID_THREADS, G::GRID_MINB) grid_pass_kerne
     if constexpr (NB == 2) {
         int ring_pos2 = 0;
         const long n = S::big_n(1);
-        const long ngrp = n / R, step = (long)gridDim.x * RPC;
+        const long ngrp = is_dcta ? 0 : n / R, step = (long)nstream * RPC;
         for (long grp = (long)blockIdx.x * RPC + tid / CS; grp < ngrp; grp += step)
             S::template big_eval<1, TBT, R>(a.k.D, thT + coff, (int)(grp * R), grp + step < ngrp ? (int)((grp + step) * R) : -1, acc[NB - 1], xbuf, ring_pos2, tid);
         if (blockIdx.x == 0 && tid / CS < (int)(n - ngrp * R)) S::template big_eval<1, TBT, 1>(a.k.D, thT + coff, (int)(ngrp * R + tid / CS), -1, acc[NB - 1], xbuf, ring_pos2, tid);

@@ -85,7 +85,8 @@ struct Engine {
     DevBuf<int> slot, cnt, accswap;
     DevBuf<double> g_partial, g_pend, g_scratch;  // grid engine
     DevBuf<unsigned int> g_ticket;
-    DevBuf<long long> g_dbg;
+    DevBuf<long long> g_dbg, g_delta_tag;
+    DevBuf<double> g_delta;
     int num_sms = 148, grid_occ = 1;
     DevBuf<double> samples, samples2, samplesT, samples2T, logprobs, temptraj;
     DevBuf<double> tabZ, tabU, tabS;
@@ -171,6 +172,9 @@ struct Engine {
             g_partial.alloc((size_t)num_sms * 8 * 2 * G::TB);
             g_ticket.alloc(1); g_ticket.zero(stream);
             g_dbg.alloc(8); g_dbg.zero(stream);
+            g_delta.alloc(nch * 2 * G::DMAX); g_delta.zero(stream);
+            g_delta_tag.alloc(nch * 2);
+            APT_CUDA(cudaMemsetAsync(g_delta_tag.p, 0xff, nch * 2 * sizeof(long long), stream));
             g_pend.alloc(nch * APT_PEND_DOUBLES); g_pend.zero(stream);
             g_scratch.alloc(nch * 2 * G::DMAX); g_scratch.zero(stream);
         } else {
@@ -359,6 +363,7 @@ struct Engine {
                 g.partial = g_partial.p; g.ticket = g_ticket.p; g.pend = g_pend.p; g.scratch = g_scratch.p;
                 g.npass = npass;
                 g.dbg = getenv("APTB200_DEBUG_TIMING") ? g_dbg.p : nullptr;
+                g.delta = getenv("APTB200_NO_DELTA_CTA") ? nullptr : g_delta.p; g.delta_tag = g_delta_tag.p;
                 APT_CUDA(cudaEventRecord(ev0, stream));
                 g.next_stage = 0; g.next_pass = 0; g.next_it = it0;
                 G::launch_prologue(g, stream);

@@ -1377,7 +1377,7 @@ struct Lowerer {
             while (W < 32 && (long)kp * W < 32) W *= 2;
         }
         if (W < 1 || W > 32 || (W & (W - 1))) throw Error("lanes_per_chain must be a power of two <= 32");
-        int maxthreads = opts.cta_threads > 0 ? opts.cta_threads : 512;
+        int maxthreads = opts.cta_threads > 0 ? opts.cta_threads : 256;  // several CTAs per SM overlap one ladder's swap phase with another's sweep
         tiles = (int)std::min<long>(items, std::max(1, maxthreads / W));
         int team_threads = ((tiles * W + 31) / 32) * 32;
         teams = team_threads == 32 ? 4 : 1;
@@ -1456,11 +1456,21 @@ struct Lowerer {
         for (size_t ui = 0; ui < units.size(); ui++) emit_unit(ui);
         if (engine == 2) {
             // dispatchers used by the grid kernels: propose-ahead for an arbitrary stage, stage launch on the host
-            out << "  template <class C> __device__ static __forceinline__ void propose_stage(int s, C& c, const Data& D, int k, double* pend) {\n    switch (s) {\n";
+            out << "  template <class C> __device__ static __forceinline__ void propose_stage(int s, C& c, const Data& D, int k, double* pend, const double* delta) {\n    switch (s) {\n";
             for (size_t i = 0; i < units.size(); i++)
-                out << "      case " << i << ": { apt::Pend<S" << i << "::NG> p_; apt::rw_propose<Model, S" << i << ">(c, D, k, 0, p_); apt::store_pend<S" << i
-                    << "::NG>(pend, p_, c.rank); break; }\n";
+                out << "      case " << i << ": { apt::Pend<S" << i << "::NG> p_; apt::rw_propose<Model, S" << i << ">(c, D, k, 0, p_, " << (units[i].kind == 1 ? "delta" : "nullptr")
+                    << "); apt::store_pend<S" << i << "::NG>(pend, p_, c.rank); break; }\n";
             out << "    }\n  }\n";
+            out << "  __host__ __device__ static constexpr bool stage_is_block(int s) { return ";
+            for (size_t i = 0; i < units.size(); i++) out << "s == " << i << " ? " << (units[i].kind == 1 ? "true" : "false") << " : ";
+            out << "false; }\n";
+            out << "  __host__ __device__ static constexpr int stage_unit0(int s) { return ";
+            for (size_t i = 0; i < units.size(); i++) out << "s == " << i << " ? " << units[i].unit0 << " : ";
+            out << "0; }\n";
+            out << "  template <class C> __device__ static __forceinline__ void delta_stage(int s, C& c, int k, double* z, double* outp) {\n    switch (s) {\n";
+            for (size_t i = 0; i < units.size(); i++)
+                if (units[i].kind == 1) out << "      case " << i << ": apt::block_increment<Model, S" << i << ">(c, k, 0, z, outp); break;\n";
+            out << "      default: break;\n    }\n  }\n";
             out << "  static void launch_stage(int s, const apt::GArgs& a, int grid, size_t smem, cudaStream_t st) {\n    switch (s) {\n";
             for (size_t i = 0; i < units.size(); i++)
                 out << "      case " << i << ": apt::grid_pass_kernel<Model, S" << i << "><<<grid, GRID_THREADS, smem, st>>>(a); break;\n";
@@ -1477,7 +1487,9 @@ struct Lowerer {
         }
         // sweep: stages
         if (engine != 2) {
-            out << "  template <class C> __device__ static __forceinline__ void propose_stage(int, C&, const Data&, int, double*) {}\n";
+            out << "  template <class C> __device__ static __forceinline__ void propose_stage(int, C&, const Data&, int, double*, const double*) {}\n";
+            out << "  __host__ __device__ static constexpr bool stage_is_block(int) { return false; }\n  __host__ __device__ static constexpr int stage_unit0(int) { return 0; }\n";
+            out << "  template <class C> __device__ static __forceinline__ void delta_stage(int, C&, int, double*, double*) {}\n";
             out << "  static void launch_stage(int, const apt::GArgs&, int, size_t, cudaStream_t) {}\n";
             out << "  static void launch_prologue(const apt::GArgs&, cudaStream_t) {}\n  static int stage_occupancy(int, size_t) { return 1; }\n  static void set_stage_smem(size_t) {}\n";
         }
