@@ -99,7 +99,19 @@ __device__ __forceinline__ double dnorm_log(double x, double mu, double sigma) {
     if (!isfinite(x)) return APT_NEG_INF;
     x = fabs(x);
     if (x >= 2.6815615859885194e154) return APT_NEG_INF;  // 2*sqrt(DBL_MAX)
-    return -(APT_LN_SQRT_2PI + 0.5 * x * x + log(sigma));
+    return -(APT_LN_SQRT_2PI + 0.5 * x * x + apt_log_pos(sigma));
+}
+
+// dnorm with a compile-time constant, positive, finite sd: log(sd) is supplied by the lowering as a literal
+// (the library log() is not constant-folded by nvcc and dominated the small-model kernel, profiles/)
+__device__ __forceinline__ double dnorm_log_csd(double x, double mu, double sigma, double log_sigma) {
+    if (isnan(x) || isnan(mu)) return x + mu;
+    if (!isfinite(x) && mu == x) return CUDART_NAN;
+    x = (x - mu) / sigma;
+    if (!isfinite(x)) return APT_NEG_INF;
+    x = fabs(x);
+    if (x >= 2.6815615859885194e154) return APT_NEG_INF;
+    return -(APT_LN_SQRT_2PI + 0.5 * x * x + log_sigma);
 }
 
 __device__ __forceinline__ double dunif_log(double x, double a, double b) {

@@ -1080,6 +1080,11 @@ struct Lowerer {
             if (try_ceval(d.iargs[1], {}, sz) && sz == 1.0)  // fused: dbinom(prob = ilogit(eta), size = 1)
                 return "apt::bern_logit_log(" + x + ", " + gen_dbl(d.iargs[0]->a[0], env) + ")";
         }
+        if (d.dist == "dnorm") {  // constant sd: pass log(sd) as a literal
+            double sd;
+            if (try_ceval(d.iargs[1], {}, sd) && sd > 0 && std::isfinite(sd))
+                return "apt::dnorm_log_csd(" + x + ", " + gen_dbl(d.iargs[0], env) + ", " + fmt_d(sd) + ", " + fmt_d(std::log(sd)) + ")";
+        }
         std::string fn = d.dist == "dnorm" ? "apt::dnorm_log" : d.dist == "dunif" ? "apt::dunif_log" : d.dist == "dgamma" ? "apt::dgamma_log"
                        : d.dist == "dbeta" ? "apt::dbeta_log" : d.dist == "dbinom" ? "apt::dbinom_log" : d.dist == "dpois" ? "apt::dpois_log"
                        : "apt::dexp_log";
