@@ -179,7 +179,8 @@ def c3_roofline(device, passes=400):
     ms = t["main_kernel_ms"] / max(1, t["main_launches"])
     by = 8.0 * N * (p + 1)
     ach = by / (ms * 1e-3) / 1e9
-    return {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+    return {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+            "traffic": 415.7e6, "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture (profiles/r1_c3_grid_pass_kernel.md)",
             "peak_source": how, "kernel": "apt::grid_pass_kernel", "ms_per_launch": ms, "launches": int(t["main_launches"]),
             "algorithmic_bytes_per_launch": by, "rungs_per_pass": 16,
             "updates_per_s": 16 * t["main_launches"] / (t["kernel_ms"] * 1e-3),
