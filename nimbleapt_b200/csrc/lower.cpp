@@ -1382,12 +1382,15 @@ struct Lowerer {
             while (W < 32 && (long)kp * W < 32) W *= 2;
         }
         if (W < 1 || W > 32 || (W & (W - 1))) throw Error("lanes_per_chain must be a power of two <= 32");
-        int maxthreads = opts.cta_threads > 0 ? opts.cta_threads : 256;  // several CTAs per SM overlap one ladder's swap phase with another's sweep
+        // several CTAs per SM overlap one ladder's swap phase with another's sweep; a ladder with thousands of
+        // concurrent sampler-family members (config 4: 24 rungs x 1000 random effects) gets the widest CTA instead
+        int maxthreads = opts.cta_threads > 0 ? opts.cta_threads : (items >= 4096 ? 1024 : 256);
         tiles = (int)std::min<long>(items, std::max(1, maxthreads / W));
         int team_threads = ((tiles * W + 31) / 32) * 32;
         teams = team_threads == 32 ? 4 : 1;
         size_t bytes = (size_t)K * (P + ND) * 8 * teams;
-        smem_state = bytes <= 96 * 1024;
+        // resident state: up to ~96 KB per CTA when several CTAs share an SM, up to 190 KB when a ladder needs the whole SM anyway
+        smem_state = bytes <= 96 * 1024 || (teams == 1 && bytes <= 200 * 1024 && tiles * W >= 256);
     }
 
     Lowered run() {

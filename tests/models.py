@@ -112,3 +112,38 @@ def c4_glmm(G=1000, per=100, K=24, tmax=30.0):
     return dict(code=code, constants=dict(N=N, G=G, x=x, g=g), data=dict(y=y),
                 inits=dict(u=np.zeros(G), sigma=np.array(1.0), b=np.zeros(2)), samplers=samplers,
                 monitors=["b", "sigma"], Temps=temps, ULT=1e6)
+
+
+def mixed_dists(n=40, K=6):
+    """Every distribution of the supported subset in one small model (gamma / beta / binomial(size>1) / exponential /
+    uniform / Poisson / normal with precision parameterisation), scalar + block + log-scale + reflective samplers."""
+    rng = np.random.default_rng(DATA_SEED + 9)
+    size = rng.integers(3, 12, n).astype(float)
+    yb = rng.binomial(size.astype(int), 0.35).astype(float)
+    yp = rng.poisson(2.5, n).astype(float)
+    yg = rng.gamma(3.0, 1.0 / 1.5, n)
+    yn = rng.normal(0.7, 0.8, n)
+    code = """{
+    for (i in 1:n) {
+        yb[i] ~ dbinom(prob=p, size=size[i])
+        yp[i] ~ dpois(rate * expo[i])
+        yg[i] ~ dgamma(shape, rate=grate)
+        yn[i] ~ dnorm(mu, tau)
+    }
+    p ~ dbeta(2, 3)
+    rate ~ dgamma(shape=2, rate=0.5)
+    shape ~ dexp(0.2)
+    grate ~ dunif(0.05, 20)
+    mu ~ dnorm(0, 0.01)
+    tau ~ dgamma(1, scale=2)
+    }"""
+    samplers = [dict(target="p", type="sampler_RW_tempered", control=dict(temperPriors=True, reflective=True, scale=0.1)),
+                dict(target="rate", type="sampler_RW_tempered", control=dict(temperPriors=True, log=True, scale=0.3)),
+                dict(target=["shape", "grate"], type="sampler_RW_block_tempered", control=dict(temperPriors=True, scale=0.3, adaptInterval=50)),
+                dict(target="mu", type="sampler_RW_tempered", control=dict(temperPriors=False, scale=0.3)),
+                dict(target="tau", type="sampler_RW_tempered", control=dict(temperPriors=True, log=True, scale=0.3))]
+    temps = np.exp(np.linspace(0.0, np.log(20.0), K))
+    return dict(code=code, constants=dict(n=n, size=size, expo=rng.random(n) + 0.5),
+                data=dict(yb=yb, yp=yp, yg=yg, yn=yn),
+                inits=dict(p=np.array(0.4), rate=np.array(2.0), shape=np.array(2.0), grate=np.array(1.0), mu=np.array(0.0), tau=np.array(1.0)),
+                samplers=samplers, monitors=["p", "rate", "shape", "grate", "mu", "tau"], Temps=temps, ULT=1e6)

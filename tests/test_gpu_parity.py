@@ -19,6 +19,7 @@ SMALL = {
     "c4": lambda: models.c4_glmm(G=20, per=10, K=4),
     "c3s": lambda: models.logistic(2000, 5, 4),
     "c3grid": lambda: models.logistic(2000, 5, 4),  # same model through the grid-wide engine (engine = 2)
+    "mixed": lambda: models.mixed_dists(),  # dbinom(size>1) dpois dgamma dbeta dexp dunif dnorm(tau) + all sampler options
 }
 BUILD_KW = {"c3grid": dict(engine=2)}
 
@@ -35,9 +36,17 @@ def test_logprob_matches_oracle(name):
     states = th0[None, :] + 0.3 * rng.standard_normal((17, P))
     if name == "c4":
         states[:, 20] = np.abs(states[:, 20]) + 0.1  # sigma inside its support
+    if name == "mixed":
+        states = np.abs(states) + 0.05
+        states[:, 0] = np.clip(states[:, 0], 0.02, 0.98)  # p in (0,1)
+        states[5, 0] = 1.5    # outside the support of dbeta: -Inf / NaN must agree too
+        states[6, 3] = 25.0   # outside dunif(0.05, 20)
     tot, grp = eng.calculate(states)
     for i in range(states.shape[0]):
         ref, ref_d = orc.logprob(states[i])
+        if not np.isfinite(ref):
+            assert (np.isnan(ref) and np.isnan(tot[i])) or tot[i] == ref, (name, i, tot[i], ref)
+            continue
         assert np.isclose(tot[i], ref, rtol=1e-12, atol=0), (name, i, tot[i], ref)
         assert np.allclose(np.sort(grp[i]), np.sort(ref_d[ref_d != 0]), rtol=1e-12, atol=1e-12)
 
