@@ -449,7 +449,7 @@ struct Engine {
             case APTMOD_INFO_TOTALITERS: return totalIters;
             case APTMOD_INFO_W: return G::W;
             case APTMOD_INFO_CTA: return SH::CTA;
-            case APTMOD_INFO_ENGINE: return 0;
+            case APTMOD_INFO_ENGINE: return G::ENGINE;
             case APTMOD_INFO_BLKSZ: return G::BLKSZ;
         }
         return -1;
