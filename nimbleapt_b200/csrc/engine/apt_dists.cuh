@@ -229,7 +229,7 @@ __device__ __noinline__ double bern_logit_generic(double y, double eta) {
     const double p = 1.0 / (1.0 + exp(-eta));
     return dbinom_raw_log(y, 1.0, p, 1.0 - p);
 }
-__device__ __forceinline__ double bern_logit_literal_q(double eta) {  // y = 0, eta > 8
+__device__ __noinline__ double bern_logit_literal_q(double eta) {  // y = 0, eta > 8; out of line: one copy instead of one per term
     const double e = apt_exp_neg(eta);
     const double p = 1.0 / (1.0 + e);
     const double q = 1.0 - p;
@@ -242,6 +242,15 @@ __device__ __forceinline__ double bern_logit_log(double y, double eta) {
     double r = -(fmax(t, 0.0) + apt_softplus_neg(fmin(fabs(t), 64.0)));
     if (y == 0.0 && eta > 8.0) r = bern_logit_literal_q(eta);
     return r;
+}
+
+// every rule that overrides the fused value, in one out-of-line function (one copy in the kernel, reached rarely
+// for cold rungs and for a fraction of the rows of hot ones)
+__device__ __noinline__ double bern_logit_fix(double y, double eta, double v) {
+    if (!(y == 0.0 || y == 1.0)) return bern_logit_invalid(y, eta);
+    if (!(fabs(eta) <= 709.0)) return bern_logit_generic(y, eta);
+    if (y == 0.0 && eta > 8.0) return bern_logit_literal_q(eta);
+    return v;
 }
 
 // N chains at once (grid engine): acc[c] += log p(y | eta[c]); fused terms in batches of 8 in lock step.  The two
@@ -258,31 +267,77 @@ __device__ __forceinline__ void bern_logit_acc(double y, const double (&eta)[N],
     const double sgn = y0 ? 1.0 : -1.0;
 #pragma unroll
     for (int h = 0; h < N; h += M) {
+        // Bookkeeping on the high words with integer min/max (one issue slot each) instead of FP64 compares and
+        // selects: amax = largest |eta| of the batch, smax = largest eta (as signed integers, which order finite
+        // doubles of equal sign like the doubles themselves; NaN and Inf land above every finite value).
         double a[M], v[M];
-        double emax = -CUDART_INF;
-        bool odd = false;
+        int amax = 0, smax = (int)0x80000000;
 #pragma unroll
         for (int j = 0; j < M; j++) {
-            const double e = eta[h + j];
-            a[j] = fmin(fabs(e), 64.0);
-            emax = fmax(emax, e);
-            odd |= !(fabs(e) <= 709.0);  // NaN, Inf, or exp(|eta|) about to overflow: generic path
+            const int hi = __double2hiint(eta[h + j]);
+            amax = max(amax, hi & 0x7fffffff);
+            smax = max(smax, hi);
+            a[j] = fabs(eta[h + j]);
         }
         apt_softplus_neg_batch<M>(a, v);
+        // -(max(t, 0) + softplus), t = sgn * eta:  t + |t| is exactly 2 max(t, 0), so one rounding as before
 #pragma unroll
-        for (int j = 0; j < M; j++) v[j] = -(fmax(sgn * eta[h + j], 0.0) + v[j]);
-        if (y0 && emax > 8.0) {
-#pragma unroll
-            for (int j = 0; j < M; j++)
-                if (eta[h + j] > 8.0) v[j] = bern_logit_literal_q(eta[h + j]);
-        }
-        if (odd) {
+        for (int j = 0; j < M; j++) v[j] = fma(-0.5, fma(sgn, eta[h + j], a[j]), -v[j]);
+        if ((y0 && smax >= 0x40200000) || amax >= 0x40862800) {  // conservative on the high words; exact tests inside
 #pragma unroll
             for (int j = 0; j < M; j++)
-                if (!(fabs(eta[h + j]) <= 709.0)) v[j] = bern_logit_generic(y, eta[h + j]);
+                if ((y0 && eta[h + j] > 8.0) || !(fabs(eta[h + j]) <= 709.0)) v[j] = bern_logit_fix(y, eta[h + j], v[j]);
         }
 #pragma unroll
         for (int j = 0; j < M; j++) acc[h + j] += v[j];
+    }
+}
+
+// Thread tile of the grid engine: NR rows (each with its own y) x NC chains; rows are taken in groups so that 8
+// terms advance in lock step.  Same arithmetic and fix-ups as bern_logit_acc.
+template <int NR, int NC>
+__device__ __forceinline__ void bern_logit_tile(const double (&y)[NR], const double (&eta)[NR][NC], double (&acc)[NC]) {
+    constexpr int RPB = (NC >= 8) ? 1 : ((8 / NC) < NR ? (8 / NC) : NR);  // rows per batch
+    constexpr int M = RPB * NC;
+    static_assert(NR % RPB == 0, "rows per thread must be a multiple of the batch");
+#pragma unroll
+    for (int r0 = 0; r0 < NR; r0 += RPB) {
+        double a[M], v[M];
+        int amax = 0, smax = (int)0x80000000;  // largest |eta|; largest eta among the y = 0 rows (high words)
+        bool valid = true;
+#pragma unroll
+        for (int rr = 0; rr < RPB; rr++) {
+            const bool y0 = (y[r0 + rr] == 0.0);
+            valid = valid && (y0 || y[r0 + rr] == 1.0);
+#pragma unroll
+            for (int j = 0; j < NC; j++) {
+                const double e = eta[r0 + rr][j];
+                const int hi = __double2hiint(e);
+                amax = max(amax, hi & 0x7fffffff);
+                smax = max(smax, y0 ? hi : (int)0x80000000);
+                a[rr * NC + j] = fabs(e);
+            }
+        }
+        apt_softplus_neg_batch<M>(a, v);
+#pragma unroll
+        for (int rr = 0; rr < RPB; rr++) {
+            const double sgn = 1.0 - 2.0 * y[r0 + rr];
+#pragma unroll
+            for (int j = 0; j < NC; j++) v[rr * NC + j] = fma(-0.5, fma(sgn, eta[r0 + rr][j], a[rr * NC + j]), -v[rr * NC + j]);
+        }
+        if (!valid || smax >= 0x40200000 || amax >= 0x40862800) {  // conservative on the high words; exact tests inside
+#pragma unroll
+            for (int rr = 0; rr < RPB; rr++)
+#pragma unroll
+                for (int j = 0; j < NC; j++) {
+                    const double e = eta[r0 + rr][j];
+                    if (!valid || (y[r0 + rr] == 0.0 && e > 8.0) || !(fabs(e) <= 709.0)) v[rr * NC + j] = bern_logit_fix(y[r0 + rr], e, v[rr * NC + j]);
+                }
+        }
+#pragma unroll
+        for (int rr = 0; rr < RPB; rr++)
+#pragma unroll
+            for (int j = 0; j < NC; j++) acc[j] += v[rr * NC + j];
     }
 }
 

@@ -32,6 +32,11 @@ __device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
     const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gmem) : "memory");
 }
+// 16-byte variant: bypasses L1 (.cg), the data is consumed from shared memory only
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -161,7 +166,8 @@ __device__ __forceinline__ void grid_ladder_step(const GArgs& a, int l, double* 
     rng.seed = a.k.seed;
     rng.ladder = a.k.ladder0 + (uint32_t)l;
     rng.iter = a.k.rng_iter0 + (uint64_t)a.it;
-    ladder_step<G, THREADS, false, true>(a.k, l, a.it, a.k.total_iters0 + a.it + 1, tid, ws, a.k.lpd + (size_t)l * K * ND, rng);
+    ladder_step<G, THREADS, false, true>(a.k, l, a.it, a.k.total_iters0 + a.it + 1, tid, ws, a.k.lpd + (size_t)l * K * ND, rng, a.dbg ? a.dbg + 8 : nullptr);
+    if (a.dbg && tid == 0) a.dbg[15] = clock64();
     if (tid < 32) write_traces<G>(a.k, l, a.it, a.k.theta + (size_t)l * K * P, ws.slot, ws.T, ws.lp, tid);
     __syncthreads();
     for (int j = tid; j < K; j += THREADS) {
@@ -186,12 +192,14 @@ __global__ void __launch_bounds__(G::GRID_THREADS, G::GRID_MINB) grid_pass_kerne
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nch = a.k.L * K;
     const int q0 = a.pass * TB;
+    const long long t_start = a.dbg ? clock64() : 0;
+    if (a.dbg && tid == 0 && blockIdx.x == 0) { unsigned long long g_; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g_)); a.dbg[16 + 2 * ((a.it * a.npass + a.pass) & 31)] = (long long)g_; }
     // One CTA does not stream: it precomputes the increments of the next launch's block proposals, which depend on
     // the rungs' sampler state and on slot-addressed normals only.  The control step then just adds them.
     const bool has_dcta = a.delta != nullptr && a.next_stage >= 0 && G::stage_is_block(a.next_stage) && gridDim.x > 2;
     const int nstream = (int)gridDim.x - (has_dcta ? 1 : 0);
     const bool is_dcta = has_dcta && blockIdx.x == gridDim.x - 1;
-    if (is_dcta) grid_precompute_delta<G>(a, tid);
+    if (is_dcta) { grid_precompute_delta<G>(a, tid); if (a.dbg && tid == 0) a.dbg[7] = clock64() - t_start; }
     // ---- 1. proposed states of this pass's chains -> shared memory, param-major / chain-minor
     for (int idx = tid; idx < P * TB; idx += THREADS) {
         const int p = idx / TB, cc = idx % TB;
@@ -202,16 +210,28 @@ __global__ void __launch_bounds__(G::GRID_THREADS, G::GRID_MINB) grid_pass_kerne
         thT[idx] = a.k.theta[((size_t)l * K + sl) * P + p];
     }
     __syncthreads();
-    // ---- 2. one pass over the data.  CS threads share a row, each owning TBT = TB / CS of the chains (fewer
-    //         accumulators per thread -> more resident warps to cover the FP64 dependent-issue latency)
-    constexpr int CS = G::CSPLIT, TBT = TB / CS, RPC = THREADS / CS;
-    const int half = tid % CS, coff = half * TBT;
+    // ---- 2. one pass over the data.  CS threads share a row (tile mode: a row group), each owning TBT = TB / CS of
+    //         the chains
+    constexpr int CS = S::TILE ? S::CS : G::CSPLIT, TBT = TB / CS, RPC = THREADS / CS;
+    const int half = S::TILE ? (lane % CS) : (tid % CS), coff = half * TBT;
     double acc[NB][TBT];
 #pragma unroll
     for (int g = 0; g < NB; g++)
 #pragma unroll
         for (int cc = 0; cc < TBT; cc++) acc[g][cc] = 0.0;
-    {
+    if constexpr (S::TILE) {
+        // tile mode: warp tiles of TROWS consecutive rows, dealt round-robin over all streaming warps so that the
+        // warps with one tile more than the others are spread evenly over the SMs
+        constexpr int TR = S::TROWS;
+        const long n = S::big_n(0);
+        const long ntile = is_dcta ? 0 : n / TR, wstep = (long)nstream * NWARP;
+        long wt = (long)warp * nstream + blockIdx.x;
+        int ring_pos = 0;
+        if (wt < ntile) S::template ring_prime<0>(a.k.D, xbuf, tid, (int)(wt * TR));
+        for (; wt < ntile; wt += wstep)
+            S::template big_eval<0, TBT, S::RT>(a.k.D, thT + coff, (int)(wt * TR), wt + wstep < ntile ? (int)((wt + wstep) * TR) : -1, acc[0], xbuf, ring_pos, tid);
+        cp_async_wait<0>();
+    } else {
         const long n = S::big_n(0);
         const long ngrp = is_dcta ? 0 : n / R, step = (long)nstream * RPC;
         int ring_pos = 0;
@@ -230,6 +250,7 @@ __global__ void __launch_bounds__(G::GRID_THREADS, G::GRID_MINB) grid_pass_kerne
             S::template big_eval<1, TBT, R>(a.k.D, thT + coff, (int)(grp * R), grp + step < ngrp ? (int)((grp + step) * R) : -1, acc[NB - 1], xbuf, ring_pos2, tid);
         if (blockIdx.x == 0 && tid / CS < (int)(n - ngrp * R)) S::template big_eval<1, TBT, 1>(a.k.D, thT + coff, (int)(ngrp * R + tid / CS), -1, acc[NB - 1], xbuf, ring_pos2, tid);
     }
+    const long long t_streamed = a.dbg ? clock64() : 0;
     // ---- 3. CTA reduction (fixed order: lanes of equal `half` by butterfly, warps ascending)
 #pragma unroll
     for (int g = 0; g < NB; g++)
@@ -241,12 +262,37 @@ __global__ void __launch_bounds__(G::GRID_THREADS, G::GRID_MINB) grid_pass_kerne
             if (lane < CS) red[warp * NB * TB + g * TB + coff + cc] = v;
         }
     __syncthreads();
+    double part = 0.0;
     if (tid < NB * TB) {
-        double s = 0.0;
 #pragma unroll
-        for (int w = 0; w < NWARP; w++) s += red[w * NB * TB + tid];
-        a.partial[(size_t)blockIdx.x * NB * TB + tid] = s;
+        for (int w = 0; w < NWARP; w++) part += red[w * NB * TB + tid];
     }
+    if constexpr (S::TILE) {
+        // rows beyond the last whole tile (fewer than TROWS): one row per thread, all TB chains, CTA 0 only
+        const long n = S::big_n(0);
+        const int rem = (int)(n % S::TROWS);
+        if (rem > 0 && blockIdx.x == 0) {
+            __syncthreads();
+            double ar[TB];
+#pragma unroll
+            for (int cc = 0; cc < TB; cc++) ar[cc] = 0.0;
+            int rp = 0;
+            if (tid < rem) S::template big_eval_rem<0, TB, 1>(a.k.D, thT, (int)(n - rem + tid), -1, ar, xbuf, rp, tid);
+#pragma unroll
+            for (int cc = 0; cc < TB; cc++) {
+                double v = ar[cc];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                if (lane == 0) red[warp * NB * TB + cc] = v;
+            }
+            __syncthreads();
+            if (tid < TB) {
+#pragma unroll
+                for (int w = 0; w < NWARP; w++) part += red[w * NB * TB + tid];
+            }
+        }
+    }
+    if (tid < NB * TB) a.partial[(size_t)blockIdx.x * NB * TB + tid] = part;
     // ---- 4. ticket: the last CTA to arrive finishes the stage
     __threadfence();
     __syncthreads();
@@ -254,7 +300,7 @@ __global__ void __launch_bounds__(G::GRID_THREADS, G::GRID_MINB) grid_pass_kerne
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    if (a.dbg && tid == 0) a.dbg[0] = clock64();
+    if (a.dbg && tid == 0) { a.dbg[0] = clock64(); a.dbg[5] = t_start; a.dbg[6] = t_streamed; }
     {
         // NB*TB values, each summed over the CTAs' partials in a fixed order by a group of 16 lanes
         constexpr int GRP = 16;
@@ -322,10 +368,10 @@ __global__ void __launch_bounds__(G::GRID_THREADS, G::GRID_MINB) grid_pass_kerne
     if (a.last_of_iter) {
         for (int l = 0; l < a.k.L; l++) grid_ladder_step<G>(a, l, s_lad, tid);
     }
-    if (a.dbg && tid == 0 && a.next_stage >= 0) a.dbg[3] = clock64();
+    if (a.dbg && tid == 0) a.dbg[3] = clock64();
     // ---- 6. propose ahead for the next launch
     grid_propose_ahead<G>(a, tid);
-    if (a.dbg) { __syncthreads(); if (tid == 0 && a.next_stage >= 0) a.dbg[4] = clock64(); }
+    if (a.dbg) { __syncthreads(); if (tid == 0) { a.dbg[4] = clock64(); unsigned long long g_; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g_)); a.dbg[17 + 2 * ((a.it * a.npass + a.pass) & 31)] = (long long)g_; } }
     if (tid == 0) *a.ticket = 0u;
 }
 

@@ -171,7 +171,7 @@ struct Engine {
         if constexpr (G::ENGINE == 2) {
             g_partial.alloc((size_t)num_sms * 8 * 2 * G::TB);
             g_ticket.alloc(1); g_ticket.zero(stream);
-            g_dbg.alloc(8); g_dbg.zero(stream);
+            g_dbg.alloc(80); g_dbg.zero(stream);
             g_delta.alloc(nch * 2 * G::DMAX); g_delta.zero(stream);
             g_delta_tag.alloc(nch * 2);
             APT_CUDA(cudaMemsetAsync(g_delta_tag.p, 0xff, nch * 2 * sizeof(long long), stream));
@@ -389,8 +389,10 @@ struct Engine {
                 rngIter += (uint64_t)(it1 - it0);
                 totalIters += (it1 - it0);
                 if (g.dbg) {
-                    auto v = d2h(g_dbg.p, 5);
-                    fprintf(stderr, "[aptb200] finishing CTA cycles: reduce %lld finish %lld ladder %lld propose %lld\n", v[1] - v[0], v[2] - v[1], v[3] - v[2], v[4] - v[3]);
+                    auto v = d2h(g_dbg.p, 80);
+                    fprintf(stderr, "[aptb200] finishing CTA cycles: stream %lld cta-reduce+ticket %lld reduce %lld finish %lld ladder %lld propose %lld total %lld (delta CTA %lld)\n", v[6] - v[5], v[0] - v[6], v[1] - v[0], v[2] - v[1], v[3] - v[2], v[4] - v[3], v[4] - v[5], v[7]);
+                    fprintf(stderr, "   ladder step: load %lld | lp+philox+log %lld | K^2 exp %lld | rowsum %lld | normalise+log %lld | chain %lld | adapt %lld | traces+writeback %lld\n", v[8] - v[2], v[9] - v[8], v[10] - v[9], v[11] - v[10], v[12] - v[11], v[13] - v[12], v[14] - v[13], v[3] - v[15]);
+                    for (int i = 0; i + 1 < 8 && i + 1 < (int)(it1 - it0) * npass; i++) { const int i0_ = (int)((it0 * npass + i) & 31), i1_ = (int)((it0 * npass + i + 1) & 31); fprintf(stderr, "   launch %d: in-kernel %lld ns, gap to next %lld ns\n", i, v[17 + 2 * i0_] - v[16 + 2 * i0_], v[16 + 2 * i1_] - v[17 + 2 * i0_]); }
                 }
             }
         }

@@ -1106,11 +1106,24 @@ struct Lowerer {
     // Grid engine: evaluate R consecutive instances of a big declaration for TB chains at once.  Inner products of
     // a parameter slice with a data row are interchanged so that each data element is loaded once and reused by
     // all chains (the loop over the TB chains is innermost and fully unrolled into registers).
+    // tile mode of the grid engine (see emit_big_eval_fn): lanes of a warp = (row group, chain group)
+    bool tile_want = false, unit_tile = false;
+    int tile_cs = 1, tile_rt = 2, tile_rows = 64;
     void emit_big_eval(Unit& u) {
         std::vector<size_t> bigs;
         for (size_t g = 0; g < u.groups.size(); g++)
             if (u.groups[g].big) bigs.push_back(g);
         out << "    static constexpr int NBIG = " << bigs.size() << ";\n";
+        unit_tile = false;
+        if (!bigs.empty()) {
+            emit_big_eval_fn(u, bigs, "big_eval", true);
+            if (unit_tile) emit_big_eval_fn(u, bigs, "big_eval_rem", false);
+        } else emit_big_eval_fn(u, bigs, "big_eval", true);
+        out << "    static constexpr bool TILE = " << (unit_tile ? "true" : "false") << ";\n";
+        out << "    static constexpr int CS = " << (unit_tile ? tile_cs : 1) << ", RT = " << (unit_tile ? tile_rt : 1) << ", TROWS = " << (unit_tile ? tile_rows : 1) << ";\n";
+    }
+    void emit_big_eval_fn(Unit& u, const std::vector<size_t>& bigs, const std::string& fname, bool allow_ring) {
+        const bool primary = fname == "big_eval";
         if (bigs.empty()) {
             out << "    __device__ static constexpr int big_group(int gi) { return 0; }\n";
             out << "    __host__ __device__ static constexpr long big_n(int gi) { return 0; }\n";
@@ -1119,13 +1132,15 @@ struct Lowerer {
             out << "    static constexpr bool RING = false;\n";
             return;
         }
+        if (primary) {
         out << "    __device__ static constexpr int big_group(int gi) { return ";
         for (size_t i = 0; i + 1 < bigs.size(); i++) out << "gi == " << i << " ? " << bigs[i] << " : ";
         out << bigs.back() << "; }\n";
         out << "    __host__ __device__ static constexpr long big_n(int gi) { return ";
         for (size_t i = 0; i + 1 < bigs.size(); i++) out << "gi == " << i << " ? " << decls[u.groups[bigs[i]].decl].ninst << "L : ";
         out << decls[u.groups[bigs.back()].decl].ninst << "L; }\n";
-        out << "    template <int GI, int TB, int R> __device__ static __forceinline__ void big_eval(const Data& D, const double* __restrict__ thT, int i0, int i_next, double (&acc)[TB], double* xbuf, int& ring_pos, int tid_) {\n";
+        }
+        out << "    template <int GI, int TB, int R> __device__ static __forceinline__ void " << fname << "(const Data& D, const double* __restrict__ thT, int i0, int i_next, double (&acc)[TB], double* xbuf, int& ring_pos, int tid_) {\n";
         out << "      constexpr int TBS = Model::TB;  // chain stride of thT (a thread may own only TB of the TBS chains)\n";
         std::ostringstream prime;  // ring_prime<GI> bodies
         bool any_ring = false;
@@ -1158,7 +1173,59 @@ struct Lowerer {
                     vec = true;
                 std::string nm = "ip" + std::to_string(nh++) + "_";
                 const int BW = 5, RD = 5, RS = 6;
-                const bool ring = vec && !any_ring && bigs.size() == 1 && lp_ % BW == 0 && lp_ / BW >= RD && ring_ok;
+                const bool ring = allow_ring && vec && !any_ring && bigs.size() == 1 && lp_ % BW == 0 && lp_ / BW >= RD && ring_ok;
+                if (allow_ring && vec && !any_ring && bigs.size() == 1 && lp_ % BW == 0 && lp_ / BW >= 3 && ring_ok && tile_want && ips.size() == 1) {
+                    // Tile mode.  A warp owns TR consecutive rows; lane = (row group rg, chain group cg): the thread
+                    // multiplies RT rows (RT/2 adjacent pairs, one LDS.128 each) by TBT chains, so that one broadcast
+                    // load of two parameters feeds 2 RT FMAs and one load of two data values 2 TBT FMAs.  (With one
+                    // row x 16 chains per thread the pass was bound by the shared-memory pipe, not by the FP64 pipe:
+                    // 9 LDS per 16 DFMA; see profiles/.)  The warp streams its rows through a private cp.async ring
+                    // of RS slots of BW columns, 16 bytes per lane and column.
+                    any_ring = true;
+                    unit_tile = true;
+                    const int NBR = lp_ / BW, TR = tile_rows, RG = 32 / tile_cs;
+                    const int TRD = 3, TRS = 4;  // blocks in flight / ring slots (deeper rings cost occupancy)
+                    auto xaddr = [&](const std::string& row, const std::string& col) {
+                        Env e2 = env;
+                        e2[d.loops[0].var] = "(" + std::to_string(d.loops[0].lo) + " + " + row + ")";
+                        int tmp;
+                        return gen_slice_elem(ds, col, e2, tmp);
+                    };
+                    out << "        const int lane_ = tid_ & 31, rg2_ = ((tid_ & 31) / " << tile_cs << ") * 2;\n";
+                    out << "        double* xw_ = xbuf + (tid_ >> 5) * " << TRS * BW * TR << ";\n";
+                    out << "        double " << nm << "[R][TB];\n";
+                    out << "        _Pragma(\"unroll\") for (int r_ = 0; r_ < R; ++r_) { _Pragma(\"unroll\") for (int c_ = 0; c_ < TB; ++c_) " << nm << "[r_][c_] = 0.0; }\n";
+                    out << "        _Pragma(\"unroll " << (NBR % 2 == 0 ? 2 : 1) << "\") for (int b_ = 0; b_ < " << NBR << "; ++b_) {  // not fully unrolled: the loop body must stay inside the instruction cache\n";
+                    out << "          apt::cp_async_wait<" << TRD - 1 << ">();\n          __syncwarp();\n";
+                    out << "          { const int nb_ = b_ + " << TRD << "; int slot_ = ring_pos + " << TRD << "; if (slot_ >= " << TRS << ") slot_ -= " << TRS << ";\n";
+                    out << "            if (nb_ < " << NBR << ") { _Pragma(\"unroll\") for (int e_ = 0; e_ < " << BW << "; ++e_) for (int q_ = lane_; q_ < " << TR / 2
+                        << "; q_ += 32) apt::cp_async16(&xw_[(slot_ * " << BW << " + e_) * " << TR << " + 2 * q_], &" << xaddr("i0 + 2 * q_", "(nb_ * " + std::to_string(BW) + " + e_)") << "); }\n";
+                    out << "            else if (i_next >= 0) { _Pragma(\"unroll\") for (int e_ = 0; e_ < " << BW << "; ++e_) for (int q_ = lane_; q_ < " << TR / 2
+                        << "; q_ += 32) apt::cp_async16(&xw_[(slot_ * " << BW << " + e_) * " << TR << " + 2 * q_], &" << xaddr("i_next + 2 * q_", "((nb_ - " + std::to_string(NBR) + ") * " + std::to_string(BW) + " + e_)") << "); }\n";
+                    out << "            apt::cp_async_commit(); }\n";
+                    {
+                        Env e3 = env;
+                        int tmp;
+                        cv_mode = true;
+                        std::string pe2 = gen_slice_elem(ps, "(b_ * " + std::to_string(BW) + " + e_)", e3, tmp);
+                        out << "          _Pragma(\"unroll\") for (int e_ = 0; e_ < " << BW << "; ++e_) {\n";
+                        out << "            double xr_[R];\n";
+                        out << "            _Pragma(\"unroll\") for (int h_ = 0; h_ < R / 2; ++h_) { const double2 x2_ = *reinterpret_cast<const double2*>(&xw_[(ring_pos * " << BW << " + e_) * " << TR
+                            << " + h_ * " << 2 * RG << " + rg2_]); xr_[2 * h_] = x2_.x; xr_[2 * h_ + 1] = x2_.y; }\n";
+                        out << "            _Pragma(\"unroll\") for (int c_ = 0; c_ < TB; c_ += 2) { const double2 b2_ = *reinterpret_cast<const double2*>(&" << pe2 << ");\n";
+                        out << "              _Pragma(\"unroll\") for (int r_ = 0; r_ < R; ++r_) { " << nm << "[r_][c_] = fma(xr_[r_], b2_.x, " << nm << "[r_][c_]); " << nm << "[r_][c_ + 1] = fma(xr_[r_], b2_.y, " << nm << "[r_][c_ + 1]); } }\n          }\n";
+                    }
+                    out << "          ring_pos = (ring_pos + 1 == " << TRS << ") ? 0 : ring_pos + 1;\n        }\n";
+                    prime << "      if constexpr (GI == " << bi << ") {\n        const int lane_ = tid_ & 31;\n        double* xw_ = xbuf + (tid_ >> 5) * " << TRS * BW * TR << ";\n"
+                          << "        _Pragma(\"unroll\") for (int b_ = 0; b_ < " << TRD << "; ++b_) {\n"
+                          << "          _Pragma(\"unroll\") for (int e_ = 0; e_ < " << BW << "; ++e_) for (int q_ = lane_; q_ < " << TR / 2 << "; q_ += 32) apt::cp_async16(&xw_[(b_ * " << BW << " + e_) * " << TR
+                          << " + 2 * q_], &" << xaddr("i0 + 2 * q_", "(b_ * " + std::to_string(BW) + " + e_)") << ");\n          apt::cp_async_commit();\n        }\n      }\n";
+                    ring_slots = std::max(ring_slots, TRS * BW * TR / 32);
+                    hoisted[ip.get()] = nm + "[r_][c_]";
+                    // rows of this thread: pair h_ = r_ / 2 of row group rg
+                    env[d.loops[0].var] = "(" + std::to_string(d.loops[0].lo) + " + i0 + (r_ >> 1) * " + std::to_string(2 * RG) + " + rg2_ + (r_ & 1))";
+                    continue;
+                }
                 if (ring) {
                     // cp.async ring: every thread streams its own rows through a private shared-memory ring, RD blocks
                     // of BW columns ahead (half a row), so the HBM latency never reaches the FMA chain
@@ -1228,9 +1295,19 @@ struct Lowerer {
                 out << "        }\n";
                 hoisted[ip.get()] = nm + "[r_][c_]";
             }
+            double sz_;
+            if (unit_tile && primary && d.dist == "dbinom" && opts.fuse_links && (is_call(d.iargs[0], "ilogit") || is_call(d.iargs[0], "expit")) && try_ceval(d.iargs[1], {}, sz_) && sz_ == 1.0) {
+                // fused Bernoulli-logit terms of the whole thread tile (pairs of rows in lock step)
+                out << "        double y_[R], eta_[R][TB];\n";
+                out << "        _Pragma(\"unroll\") for (int r_ = 0; r_ < R; ++r_) { y_[r_] = " << gen_dbl(d.lhs, env) << "; _Pragma(\"unroll\") for (int c_ = 0; c_ < TB; ++c_) eta_[r_][c_] = "
+                    << gen_dbl(d.iargs[0]->a[0], env) << "; }\n";
+                out << "        apt::bern_logit_tile<R, TB>(y_, eta_, acc);\n      }\n";
+                cv_mode = false;
+                hoisted.clear();
+                continue;
+            }
             out << "        _Pragma(\"unroll\") for (int r_ = 0; r_ < R; ++r_) {\n";
             out << "          const double x_ = " << gen_dbl(d.lhs, env) << ";\n";
-            double sz_;
             if (d.dist == "dbinom" && opts.fuse_links && (is_call(d.iargs[0], "ilogit") || is_call(d.iargs[0], "expit")) && try_ceval(d.iargs[1], {}, sz_) && sz_ == 1.0) {
                 // fused Bernoulli-logit terms of all chains evaluated in lock step (explicit ILP across chains)
                 out << "          double eta_[TB];\n          _Pragma(\"unroll\") for (int c_ = 0; c_ < TB; ++c_) eta_[c_] = " << gen_dbl(d.iargs[0]->a[0], env) << ";\n";
@@ -1243,8 +1320,10 @@ struct Lowerer {
             hoisted.clear();
         }
         out << "    }\n";
-        out << "    template <int GI> __device__ static __forceinline__ void ring_prime(const Data& D, double* xbuf, int tid_, int i0) {\n" << prime.str() << "    }\n";
-        out << "    static constexpr bool RING = " << (any_ring ? "true" : "false") << ";\n";
+        if (primary) {
+            out << "    template <int GI> __device__ static __forceinline__ void ring_prime(const Data& D, double* xbuf, int tid_, int i0) {\n" << prime.str() << "    }\n";
+            out << "    static constexpr bool RING = " << (any_ring ? "true" : "false") << ";\n";
+        }
     }
     int ring_slots = 0;
     bool ring_ok = true;
@@ -1449,6 +1528,14 @@ struct Lowerer {
                 csplit = (opts.cta_threads == 12 && TB >= 2) ? 2 : 1;  // threads per row, each owning TB / csplit chains (measured slower on B200: off by default)
                 W = std::min(32, 256 / TB);  // control lanes per chain inside the finishing CTA
                 ring_ok = (R == 1) && !getenv("APTB200_NO_RING");
+                // tile mode: TBT chains x RT rows per thread, CS = TB / TBT lanes share a row group
+                tile_want = ring_ok && csplit == 1 && TB >= 2 && !getenv("APTB200_NO_TILE");
+                {
+                    const int tbt = TB >= 16 ? 4 : 2;
+                    tile_cs = std::max(1, TB / tbt);
+                    tile_rt = std::min(8, 2 * tile_cs);
+                    tile_rows = (32 / tile_cs) * tile_rt;
+                }
             }
         }
 

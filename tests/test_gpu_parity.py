@@ -19,9 +19,13 @@ SMALL = {
     "c4": lambda: models.c4_glmm(G=20, per=10, K=4),
     "c3s": lambda: models.logistic(2000, 5, 4),
     "c3grid": lambda: models.logistic(2000, 5, 4),  # same model through the grid-wide engine (engine = 2)
+    # grid engine, tile mode (warp tiles of 64 rows, lanes = row group x chain group): 16 rungs -> 8 rows x 4 chains per
+    # thread, 4 rungs -> 4 rows x 2 chains; N is not a multiple of 64, so the remainder path runs too
+    "c3tile16": lambda: models.logistic(3000, 15, 16, seed_off=5),
+    "c3tile4": lambda: models.logistic(1500, 20, 4, seed_off=6),
     "mixed": lambda: models.mixed_dists(),  # dbinom(size>1) dpois dgamma dbeta dexp dunif dnorm(tau) + all sampler options
 }
-BUILD_KW = {"c3grid": dict(engine=2)}
+BUILD_KW = {"c3grid": dict(engine=2), "c3tile16": dict(engine=2), "c3tile4": dict(engine=2)}
 
 
 @pytest.mark.parametrize("name", list(SMALL))
