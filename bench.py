@@ -303,7 +303,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": args.workload, "ladders_per_gpu": L, "temperatures": K, "samplers_per_rung": NU, "thin": thin,
-                       "engine": "ladder-resident" if eng.info(nb.api.INFO_ENGINE) == 0 else "grid",
+                       "engine": "grid" if eng.info(nb.api.INFO_ENGINE) == 2 else "ladder-resident",
                        "l2": ("inputs (408 MB design matrix) larger than the 126 MB L2: every pass re-streams them from HBM"
                               if args.workload == "c3" else
                               "working set is shared-memory resident; traces stream to HBM (no L2 reuse to flush)")},

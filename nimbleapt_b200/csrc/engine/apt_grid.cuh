@@ -302,13 +302,21 @@ __global__ void __launch_bounds__(G::GRID_THREADS, G::GRID_MINB) grid_pass_kerne
     __threadfence();
     if (a.dbg && tid == 0) { a.dbg[0] = clock64(); a.dbg[5] = t_start; a.dbg[6] = t_streamed; }
     {
-        // NB*TB values, each summed over the CTAs' partials in a fixed order by a group of 16 lanes
-        constexpr int GRP = 16;
+        // NB*TB values, each summed over the CTAs' partials in a fixed order by a group of 16 lanes.  All loads of a
+        // thread are issued before the first add (one L2 round trip instead of one per batch of four).
+        constexpr int GRP = 16, MAXB = 24;  // up to GRP * MAXB = 384 CTAs in registers; beyond that, the loop below
         for (int v = tid / GRP; v < NB * TB; v += THREADS / GRP) {
             const int sub = tid % GRP;
+            double x[MAXB];
+#pragma unroll
+            for (int i = 0; i < MAXB; i++) {
+                const int b = sub + i * GRP;
+                x[i] = (b < (int)gridDim.x) ? __ldcg(&a.partial[(size_t)b * NB * TB + v]) : 0.0;
+            }
             double s = 0.0;
-#pragma unroll 4
-            for (int b = sub; b < (int)gridDim.x; b += GRP) s += __ldcg(&a.partial[(size_t)b * NB * TB + v]);
+#pragma unroll
+            for (int i = 0; i < MAXB; i++) s += x[i];
+            for (int b = sub + MAXB * GRP; b < (int)gridDim.x; b += GRP) s += __ldcg(&a.partial[(size_t)b * NB * TB + v]);
 #pragma unroll
             for (int o = GRP / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
             if (sub == 0) s_new[v] = s;

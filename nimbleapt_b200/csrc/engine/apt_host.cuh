@@ -180,6 +180,14 @@ struct Engine {
         } else {
             if (SH::SM_BYTES > 48 * 1024)
                 APT_CUDA(cudaFuncSetAttribute(ladder_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SH::SM_BYTES));
+            // the resident ladders per SM are bounded by shared memory: ask for the largest carve-out
+            APT_CUDA(cudaFuncSetAttribute(ladder_kernel<G>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+            if (getenv("APTB200_DEBUG_TIMING")) {
+                int occ = 0;
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ladder_kernel<G>, SH::CTA, SH::SM_BYTES);
+                cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, ladder_kernel<G>);
+                fprintf(stderr, "[aptb200] ladder_kernel: %d threads/CTA, %zu B smem/CTA, %d regs, %d CTAs/SM (%d ladders/SM)\n", SH::CTA, (size_t)SH::SM_BYTES, fa.numRegs, occ, occ * SH::TEAMS);
+            }
         }
         APT_CUDA(cudaStreamSynchronize(stream));
     }

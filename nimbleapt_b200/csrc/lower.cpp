@@ -1184,7 +1184,11 @@ struct Lowerer {
                     any_ring = true;
                     unit_tile = true;
                     const int NBR = lp_ / BW, TR = tile_rows, RG = 32 / tile_cs;
-                    const int TRD = 3, TRS = 4;  // blocks in flight / ring slots (deeper rings cost occupancy)
+                    int TRD = 3;  // blocks in flight; ring slots = TRD + 1 (deeper rings cost occupancy)
+                    if (const char* e = getenv("APTB200_TILE_DEPTH")) TRD = std::max(1, std::min(NBR, atoi(e)));
+                    const int TRS = TRD + 1;
+                    int unr = (NBR % 2 == 0 ? 2 : 1);
+                    if (const char* e = getenv("APTB200_TILE_UNROLL")) unr = std::max(1, atoi(e));
                     auto xaddr = [&](const std::string& row, const std::string& col) {
                         Env e2 = env;
                         e2[d.loops[0].var] = "(" + std::to_string(d.loops[0].lo) + " + " + row + ")";
@@ -1195,7 +1199,7 @@ struct Lowerer {
                     out << "        double* xw_ = xbuf + (tid_ >> 5) * " << TRS * BW * TR << ";\n";
                     out << "        double " << nm << "[R][TB];\n";
                     out << "        _Pragma(\"unroll\") for (int r_ = 0; r_ < R; ++r_) { _Pragma(\"unroll\") for (int c_ = 0; c_ < TB; ++c_) " << nm << "[r_][c_] = 0.0; }\n";
-                    out << "        _Pragma(\"unroll " << (NBR % 2 == 0 ? 2 : 1) << "\") for (int b_ = 0; b_ < " << NBR << "; ++b_) {  // not fully unrolled: the loop body must stay inside the instruction cache\n";
+                    out << "        _Pragma(\"unroll " << unr << "\") for (int b_ = 0; b_ < " << NBR << "; ++b_) {  // not fully unrolled: the loop body must stay inside the instruction cache\n";
                     out << "          apt::cp_async_wait<" << TRD - 1 << ">();\n          __syncwarp();\n";
                     out << "          { const int nb_ = b_ + " << TRD << "; int slot_ = ring_pos + " << TRD << "; if (slot_ >= " << TRS << ") slot_ -= " << TRS << ";\n";
                     out << "            if (nb_ < " << NBR << ") { _Pragma(\"unroll\") for (int e_ = 0; e_ < " << BW << "; ++e_) for (int q_ = lane_; q_ < " << TR / 2
@@ -1355,15 +1359,34 @@ struct Lowerer {
                 out << "};\n    return apt::dmnorm_chol_log<" << n << ">(x_, mu_, U_, (" << gen_dbl(d.iargs[0], env) << ") != 0.0);\n";
             } else {
                 out << "    return " << density_expr(d, gen_dbl(d.lhs, env), env) << ";\n";
+                if (is_fused_bern(d)) {
+                    out << "  }\n  __device__ static __forceinline__ double y_d" << di << "(const Data& D, const double* th, int L0, int L1, int L2) {\n    return " << gen_dbl(d.lhs, env) << ";\n";
+                    out << "  }\n  __device__ static __forceinline__ double eta_d" << di << "(const Data& D, const double* th, int L0, int L1, int L2) {\n    return " << gen_dbl(d.iargs[0]->a[0], env) << ";\n";
+                }
             }
             out << "  }\n";
         }
     }
 
+    bool is_fused_bern(const CDecl& d) {
+        double sz;
+        return d.dist == "dbinom" && opts.fuse_links && (is_call(d.iargs[0], "ilogit") || is_call(d.iargs[0], "expit")) && try_ceval(d.iargs[1], {}, sz) && sz == 1.0;
+    }
     void emit_inst_loop(int di, const std::string& acc) {
         const CDecl& d = decls[di];
         if (d.ninst == 1) out << "    if (c.rank == 0) " << acc << " += " << lp_call(di, "0") << ";\n";
-        else
+        else if (is_fused_bern(d) && d.ninst >= 64 && !getenv("APTB200_NO_BATCH")) {
+            // fused Bernoulli-logit terms eight rows at a time (explicit ILP: one term is a chain of ~30 dependent FP64
+            // operations); the terms are added in the same order as the one-by-one loop
+            std::string ycall = lp_call(di, "q + u_ * C::W"), ecall = ycall;
+            ycall.replace(0, 4, "y_d");
+            ecall.replace(0, 4, "eta_d");
+            out << "    { int q = c.rank;\n";
+            out << "      for (; q + 7 * C::W < " << d.ninst << "; q += 8 * C::W) {\n        double y_[8], e_[8][1];\n";
+            out << "        _Pragma(\"unroll\") for (int u_ = 0; u_ < 8; ++u_) { y_[u_] = " << ycall << "; e_[u_][0] = " << ecall << "; }\n";
+            out << "        double a_[1] = {" << acc << "}; apt::bern_logit_tile<8, 1>(y_, e_, a_); " << acc << " = a_[0];\n      }\n";
+            out << "      for (; q < " << d.ninst << "; q += C::W) " << acc << " += " << lp_call(di, "q") << ";\n    }\n";
+        } else
             out << "    for (int q = c.rank; q < " << d.ninst << "; q += C::W) " << acc << " += " << lp_call(di, "q") << ";\n";
     }
 
@@ -1531,9 +1554,11 @@ struct Lowerer {
                 // tile mode: TBT chains x RT rows per thread, CS = TB / TBT lanes share a row group
                 tile_want = ring_ok && csplit == 1 && TB >= 2 && !getenv("APTB200_NO_TILE");
                 {
-                    const int tbt = TB >= 16 ? 4 : 2;
+                    int tbt = TB >= 16 ? 4 : 2;
+                    if (const char* e = getenv("APTB200_TILE_TBT")) tbt = std::max(2, std::min(TB, atoi(e)));  // tuning knobs (scratch/)
                     tile_cs = std::max(1, TB / tbt);
-                    tile_rt = std::min(8, 2 * tile_cs);
+                    tile_rt = std::min(4, 2 * tile_cs);  // 4 rows x 4 chains measured best at 16 rungs (8 x 4 spills at 128 registers)
+                    if (const char* e = getenv("APTB200_TILE_RT")) tile_rt = std::max(2, atoi(e) & ~1);
                     tile_rows = (32 / tile_cs) * tile_rt;
                 }
             }
@@ -1634,6 +1659,18 @@ struct Lowerer {
             << ", NMON = " << mon.size() << ", NMON2 = " << mon2.size() << ", DMAX = " << DMAX << ", W = " << W << ";\n";
         out << "  static constexpr int NARR = " << used_arrays.size() << ", NIARR = " << iarrays.size() << ", BLKSZ = " << BLKSZ << ", EMPSZ = " << EMPSZ << ";\n";
         out << "  static constexpr int TILES_PER_LADDER = " << tiles << ", TEAMS_PER_CTA = " << teams << ";\n";
+        {
+            // resident CTAs per SM the ladder kernel is compiled for (register cap = 64K / (LADDER_MINB * CTA)): as many
+            // as shared memory admits, but never fewer than 64 registers per thread
+            const int team_threads = ((tiles * W + 31) / 32) * 32, cta = team_threads * teams;
+            const bool logtab = team_threads != 32 && K <= 32;
+            const long psize = logtab ? 2L * K * K : ((long)K * (K - 1) / 2 + 1) / 2 * 2;
+            const long team_bytes = ((7L * K + psize + (long)tiles * 2 * DMAX + (smem_state && engine == 1 ? (long)K * (P + ND) : 0)) * 8 + 2L * K * 4 + 15) / 16 * 16;
+            long minb = 232448 / (team_bytes * teams + 1024);
+            minb = std::max(1L, std::min(minb, (long)(1024 / cta)));
+            if (const char* e = getenv("APTB200_LADDER_MINB")) minb = std::max(0, atoi(e));  // 0 = no register cap
+            out << "  static constexpr int LADDER_MINB = " << minb << ";\n";
+        }
         out << "  static constexpr bool STATE_IN_SMEM = " << (smem_state && engine == 1 ? "true" : "false") << ", HAS_FAMILY = " << (has_family ? "true" : "false") << ";\n";
         out << "  static constexpr int ENGINE = " << engine << ", TB = " << TB << ", R = " << R << ", GRID_THREADS = 256, RING_SLOTS = " << ring_slots << ", CSPLIT = " << csplit << ", GRID_MINB = " << (engine == 2 && opts.lanes_per_chain > 0 ? opts.lanes_per_chain : (csplit == 2 ? 3 : 2)) << ", NSTAGE = " << units.size() << ";\n";
         out << "  __device__ static __forceinline__ int mon(int c) { return MON_TAB[c]; }\n";
