@@ -69,6 +69,11 @@ struct DevBuf {
 };
 
 template <class G>
+__global__ void derived_kernel(Data D, int k, long n, double* out) {
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) G::der_fill(D, k, i, out);
+}
+
+template <class G>
 struct Engine {
     using SH = Shape<G>;
     static constexpr int K = G::K, P = G::P;
@@ -135,6 +140,7 @@ struct Engine {
                 APT_CUDA(cudaMemcpyAsync(iarrays[i].p, in->iarrays[i], in->iarray_len[i] * sizeof(int), cudaMemcpyHostToDevice, stream));
             D.ia[i] = iarrays[i].p;
         }
+        refresh_derived();
         const size_t nch = (size_t)L * K;
         theta.alloc(nch * P); lpd.alloc(nch * G::ND); temps.alloc(nch); lp.alloc(nch); slot.alloc(nch);
         scale.alloc(nch * G::NU); cnt.alloc(nch * G::NU * 3);
@@ -209,6 +215,7 @@ struct Engine {
         APT_CUDA(cudaSetDevice(device));
         if (idx < 0 || idx >= G::NARR || (size_t)n != arrays[idx].n) throw ApiError{"set_array: bad index or length"};
         APT_CUDA(cudaMemcpyAsync(arrays[idx].p, v, n * sizeof(double), cudaMemcpyHostToDevice, stream));
+        refresh_derived();
     }
 
     static void grow_trace(DevBuf<double>& b, int L, long long oldcap, long long newcap, long long keep_rows, int cols,
@@ -407,6 +414,25 @@ struct Engine {
         return false;
     }
     int grid_occ_known = 0;
+    // derived arrays live behind the model's own arrays in Data::a[]
+    std::vector<DevBuf<double>> derived;
+    void refresh_derived() {
+        if constexpr (G::NDER > 0) {
+            static_assert(G::NARR + G::NDER <= APT_MAX_ARR, "too many arrays");
+            if (derived.empty()) {
+                derived.resize(G::NDER);
+                for (int k = 0; k < G::NDER; k++) {
+                    derived[k].alloc((size_t)std::max<long>(G::der_inst(k) * G::der_width(k), 1));
+                    D.a[G::NARR + k] = derived[k].p;
+                }
+            }
+            for (int k = 0; k < G::NDER; k++) {
+                const long n = G::der_inst(k);
+                if (n > 0) derived_kernel<G><<<(unsigned)std::min<long>((n + 255) / 256, 4096), 256, 0, stream>>>(D, k, n, derived[k].p);
+            }
+            APT_CUDA(cudaGetLastError());
+        }
+    }
 
     // whole-model logProb of caller-provided states (host pointers): out_lpd [n][ND]
     void logprob(const double* th, int n, double* out_lpd) {

@@ -1012,7 +1012,7 @@ struct Lowerer {
             }
             case Expr::CALL: {
                 static const std::map<std::string, std::string> f1 = {
-                    {"exp", "exp"}, {"log", "log"}, {"abs", "fabs"}, {"sqrt", "sqrt"}, {"ilogit", "apt::ilogit"}, {"expit", "apt::ilogit"},
+                    {"exp", "apt_exp"}, {"log", "log"}, {"abs", "fabs"}, {"sqrt", "sqrt"}, {"ilogit", "apt::ilogit"}, {"expit", "apt::ilogit"},
                     {"logit", "apt::logit"}, {"phi", "apt::iprobit"}, {"iprobit", "apt::iprobit"}, {"icloglog", "apt::icloglog"},
                     {"cloglog", "apt::cloglog"}, {"log1p", "log1p"}, {"step", "apt::stepfn"}, {"lgamma", "lgamma"}, {"loggam", "lgamma"}};
                 auto it = f1.find(e->name);
@@ -1071,10 +1071,43 @@ struct Lowerer {
         return "lp_d" + std::to_string(di) + "(D, th, " + a[0] + ", " + a[1] + ", " + a[2] + ")";
     }
 
+    // 0-based linear instance index of a declaration from the loop values L0, L1, L2 of lp_d
+    std::string lin_of_decl(const CDecl& d) const {
+        if (d.loops.empty()) return "0";
+        std::string r;
+        long mul = 1;
+        for (size_t l = 0; l < d.loops.size() && l < 3; l++) {
+            std::string t = "(L" + std::to_string(l) + " - " + std::to_string(d.loops[l].lo) + ")";
+            if (mul != 1) t += " * " + std::to_string(mul);
+            r += (l ? " + " : "") + t;
+            mul *= d.loops[l].hi - d.loops[l].lo + 1;
+        }
+        return r;
+    }
     bool is_call(const EP& e, const char* name) const { return e->k == Expr::CALL && e->name == name && e->a.size() == 1; }
 
     // C expression of the log-density of a (non-multivariate) stochastic declaration at value expression `x`
-    std::string density_expr(const CDecl& d, const std::string& x, const Env& env) {
+    // derived arrays: per-instance values that depend on data only, filled on the device when data is uploaded
+    struct Derived { int decl; std::string kind; long len; };
+    std::vector<Derived> derived;
+    std::map<int, int> derived_of_decl;
+    bool lhs_is_data(const CDecl& d) const {
+        auto it = vars.find(d.lhs->name);
+        return it != vars.end() && it->second.role == Var::DATA;
+    }
+    std::string density_expr(const CDecl& d, const std::string& x, const Env& env, const std::string& lin = "", int di = -1) {
+        if (d.dist == "dpois" && !lin.empty() && di >= 0 && lhs_is_data(d) && !getenv("APTB200_NO_DERIVED")) {
+            // y ~ dpois(lambda) with y data: -0.5 log(2 pi y) and stirlerr(y) come from a derived array
+            int k;
+            auto f = derived_of_decl.find(di);
+            if (f == derived_of_decl.end()) {
+                k = (int)derived.size();
+                derived.push_back({di, "dpois", 2 * d.ninst});
+                derived_of_decl[di] = k;
+            } else k = f->second;
+            const std::string base = "D.a[NARR + " + std::to_string(k) + "]";
+            return "apt::dpois_log_pre(" + x + ", " + gen_dbl(d.iargs[0], env) + ", " + base + "[2 * (" + lin + ")], " + base + "[2 * (" + lin + ") + 1])";
+        }
         if (d.dist == "dbinom" && opts.fuse_links && (is_call(d.iargs[0], "ilogit") || is_call(d.iargs[0], "expit"))) {
             double sz;
             if (try_ceval(d.iargs[1], {}, sz) && sz == 1.0)  // fused: dbinom(prob = ilogit(eta), size = 1)
@@ -1358,7 +1391,7 @@ struct Lowerer {
                 for (int e = 0; e < n * n; e++) out << (e ? ", " : "") << gen_dbl(d.chol_elems[e], env);
                 out << "};\n    return apt::dmnorm_chol_log<" << n << ">(x_, mu_, U_, (" << gen_dbl(d.iargs[0], env) << ") != 0.0);\n";
             } else {
-                out << "    return " << density_expr(d, gen_dbl(d.lhs, env), env) << ";\n";
+                out << "    return " << density_expr(d, gen_dbl(d.lhs, env), env, lin_of_decl(d), di) << ";\n";
                 if (is_fused_bern(d)) {
                     out << "  }\n  __device__ static __forceinline__ double y_d" << di << "(const Data& D, const double* th, int L0, int L1, int L2) {\n    return " << gen_dbl(d.lhs, env) << ";\n";
                     out << "  }\n  __device__ static __forceinline__ double eta_d" << di << "(const Data& D, const double* th, int L0, int L1, int L2) {\n    return " << gen_dbl(d.iargs[0]->a[0], env) << ";\n";
@@ -1387,7 +1420,7 @@ struct Lowerer {
             out << "        double a_[1] = {" << acc << "}; apt::bern_logit_tile<8, 1>(y_, e_, a_); " << acc << " = a_[0];\n      }\n";
             out << "      for (; q < " << d.ninst << "; q += C::W) " << acc << " += " << lp_call(di, "q") << ";\n    }\n";
         } else
-            out << "    for (int q = c.rank; q < " << d.ninst << "; q += C::W) " << acc << " += " << lp_call(di, "q") << ";\n";
+            out << "    _Pragma(\"unroll 4\") for (int q = c.rank; q < " << d.ninst << "; q += C::W) " << acc << " += " << lp_call(di, "q") << ";\n";
     }
 
     void emit_unit(size_t ui) {
@@ -1673,6 +1706,27 @@ struct Lowerer {
         }
         out << "  static constexpr bool STATE_IN_SMEM = " << (smem_state && engine == 1 ? "true" : "false") << ", HAS_FAMILY = " << (has_family ? "true" : "false") << ";\n";
         out << "  static constexpr int ENGINE = " << engine << ", TB = " << TB << ", R = " << R << ", GRID_THREADS = 256, RING_SLOTS = " << ring_slots << ", CSPLIT = " << csplit << ", GRID_MINB = " << (engine == 2 && opts.lanes_per_chain > 0 ? opts.lanes_per_chain : (csplit == 2 ? 3 : 2)) << ", NSTAGE = " << units.size() << ";\n";
+        // derived arrays (data-only terms, filled by derived_kernel when data is uploaded)
+        out << "  static constexpr int NDER = " << derived.size() << ";\n";
+        out << "  static long der_inst(int k) { return ";
+        for (size_t k = 0; k < derived.size(); k++) out << "k == " << k << " ? " << decls[derived[k].decl].ninst << "L : ";
+        out << "0L; }\n";
+        out << "  static int der_width(int k) { return 2; }\n";
+        out << "  __device__ static __forceinline__ void der_fill(const Data& D, int k, long i, double* out) {\n    switch (k) {\n";
+        for (size_t k = 0; k < derived.size(); k++) {
+            const CDecl& d = decls[derived[k].decl];
+            out << "      case " << k << ": {";
+            long mul = 1;
+            for (size_t l = 0; l < 3; l++) {
+                if (l < d.loops.size()) {
+                    long n = d.loops[l].hi - d.loops[l].lo + 1;
+                    out << " const int L" << l << " = " << d.loops[l].lo << " + (int)((i / " << mul << ") % " << n << ");";
+                    mul *= n;
+                } else out << " const int L" << l << " = 0;";
+            }
+            out << " (void)L0; (void)L1; (void)L2; apt::dpois_pre(" << gen_dbl(d.lhs, decl_env(d)) << ", out + 2 * i); break; }\n";
+        }
+        out << "      default: break;\n    }\n  }\n";
         out << "  __device__ static __forceinline__ int mon(int c) { return MON_TAB[c]; }\n";
         out << "  __device__ static __forceinline__ int mon2(int c) { return MON2_TAB[c]; }\n";
         out << body.str();
