@@ -141,7 +141,9 @@ enum {
     APT_INFO_N_PARAMS = 0, APT_INFO_N_TEMPS, APT_INFO_N_SAMPLER_UNITS, APT_INFO_N_LOGPROB_GROUPS,
     APT_INFO_N_MONITORS, APT_INFO_N_MONITORS2, APT_INFO_MAX_BLOCK_DIM, APT_INFO_ROWS, APT_INFO_ROWS2,
     APT_INFO_TEMPTRAJ_ROWS, APT_INFO_N_LADDERS, APT_INFO_LAUNCHES, APT_INFO_TOTAL_ITERS,
-    APT_INFO_LANES_PER_CHAIN, APT_INFO_CTA_THREADS, APT_INFO_ENGINE_KIND, APT_INFO_BLOCK_STATE_SIZE
+    APT_INFO_LANES_PER_CHAIN, APT_INFO_CTA_THREADS, APT_INFO_ENGINE_KIND, APT_INFO_BLOCK_STATE_SIZE,
+    APT_INFO_FP64_PEAK_GFLOPS /* not a property but a measurement: FP64 FMA throughput of the engine's device (pure DFMA kernel,
+                                 CUDA events), the denominator of the flop roofline of the small-model kernel */
 };
 
 const char* apt_last_error(void);

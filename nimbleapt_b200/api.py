@@ -33,7 +33,7 @@ _BLOCK_KEYS = {"adaptive", "adaptScaleOnly", "adaptInterval", "adaptFactorExpone
 (APT_SAMPLES, APT_SAMPLES2, APT_SAMPLES_TMAX, APT_SAMPLES2_TMAX, APT_LOGPROBS, APT_TEMPTRAJ, APT_TEMPS, APT_ACCSWAP,
  APT_LOGPROBTEMPS, APT_RUNG_STATES, APT_SCALES, APT_BLOCK_STATE, APT_DECISIONS, APT_SWAP_RECORD, APT_MODEL_STATE) = range(15)
 (INFO_N_PARAMS, INFO_N_TEMPS, INFO_N_UNITS, INFO_N_GROUPS, INFO_N_MON, INFO_N_MON2, INFO_DMAX, INFO_ROWS, INFO_ROWS2,
- INFO_TTROWS, INFO_L, INFO_LAUNCHES, INFO_TOTAL_ITERS, INFO_W, INFO_CTA, INFO_ENGINE, INFO_BLKSZ) = range(17)
+ INFO_TTROWS, INFO_L, INFO_LAUNCHES, INFO_TOTAL_ITERS, INFO_W, INFO_CTA, INFO_ENGINE, INFO_BLKSZ, INFO_FP64_GFLOPS) = range(18)
 
 
 def nimbleCode(text):

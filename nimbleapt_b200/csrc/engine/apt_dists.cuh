@@ -362,20 +362,35 @@ __device__ __forceinline__ void bern_logit_tile(const double (&y)[NR], const dou
                 a[rr * NC + j] = fabs(e);
             }
         }
-        apt_softplus_neg_batch<M>(a, v);
+        double w[M];  // 1 + exp(-|eta|)
+        apt_softplus_neg_batch<M>(a, v, w);
 #pragma unroll
         for (int rr = 0; rr < RPB; rr++) {
             const double sgn = 1.0 - 2.0 * y[r0 + rr];
 #pragma unroll
             for (int j = 0; j < NC; j++) v[rr * NC + j] = fma(-0.5, fma(sgn, eta[r0 + rr][j], a[rr * NC + j]), -v[rr * NC + j]);
         }
-        if (!valid || smax >= 0x40200000 || amax >= 0x40862800) {  // conservative on the high words; exact tests inside
+        if (smax >= 0x40200000) {
+            // y = 0 and eta > 8: the reference's own chain p = 1/(1+exp(-eta)), q = 1-p, log(q), whose rounding the
+            // decisions of hot chains depend on (see above) -- for the whole batch in lock step, reusing 1+exp(-eta)
+            double lq[M];
+#pragma unroll
+            for (int j = 0; j < M; j++) lq[j] = 1.0 - 1.0 / w[j];
+#pragma unroll
+            for (int j = 0; j < M; j++) lq[j] = apt_log_pos(lq[j]);  // q == 0 -> -Inf
+#pragma unroll
+            for (int rr = 0; rr < RPB; rr++)
+#pragma unroll
+                for (int j = 0; j < NC; j++)
+                    if (y[r0 + rr] == 0.0 && eta[r0 + rr][j] > 8.0) v[rr * NC + j] = lq[rr * NC + j];
+        }
+        if (!valid || amax >= 0x40862800) {  // invalid response, |eta| >= 709, Inf, NaN: exact tests inside
 #pragma unroll
             for (int rr = 0; rr < RPB; rr++)
 #pragma unroll
                 for (int j = 0; j < NC; j++) {
                     const double e = eta[r0 + rr][j];
-                    if (!valid || (y[r0 + rr] == 0.0 && e > 8.0) || !(fabs(e) <= 709.0)) v[rr * NC + j] = bern_logit_fix(y[r0 + rr], e, v[rr * NC + j]);
+                    if (!valid || !(fabs(e) <= 709.0)) v[rr * NC + j] = bern_logit_fix(y[r0 + rr], e, v[rr * NC + j]);
                 }
         }
 #pragma unroll

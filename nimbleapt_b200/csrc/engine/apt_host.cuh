@@ -68,6 +68,25 @@ struct DevBuf {
     ~DevBuf() { release(); }
 };
 
+// pure FP64 FMA throughput (the flop-roofline denominator): 16 independent accumulators per thread
+__global__ void __launch_bounds__(256, 2) fp64_peak_kernel(double* out, int iters, double a, double b) {
+    double acc[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) acc[i] = threadIdx.x * 1e-3 + i;
+    const double x = a + threadIdx.x * 1e-9;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int u = 0; u < 16; u++) {
+#pragma unroll
+            for (int i = 0; i < 16; i++) acc[i] = fma(acc[i], x, b);
+        }
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) s += acc[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 template <class G>
 __global__ void derived_kernel(Data D, int k, long n, double* out) {
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) G::der_fill(D, k, i, out);
@@ -414,6 +433,27 @@ struct Engine {
         return false;
     }
     int grid_occ_known = 0;
+    long long measure_fp64() const {
+        cudaSetDevice(device);
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+        const int grid = sms * 2, iters = 4000;
+        DevBuf<double> o;
+        o.alloc((size_t)grid * 256);
+        fp64_peak_kernel<<<grid, 256, 0, stream>>>(o.p, iters, 0.999, 1e-3);  // warm-up
+        float best = 1e30f;
+        for (int rep = 0; rep < 3; rep++) {
+            cudaEventRecord(ev0, stream);
+            fp64_peak_kernel<<<grid, 256, 0, stream>>>(o.p, iters, 0.999, 1e-3);
+            cudaEventRecord(ev1, stream);
+            cudaEventSynchronize(ev1);
+            float ms = 0;
+            cudaEventElapsedTime(&ms, ev0, ev1);
+            best = std::min(best, ms);
+        }
+        const double flops = 2.0 * grid * 256.0 * iters * 256.0;
+        return (long long)(flops / (best * 1e-3) / 1e9);
+    }
     // derived arrays live behind the model's own arrays in Data::a[]
     std::vector<DevBuf<double>> derived;
     void refresh_derived() {
@@ -487,6 +527,7 @@ struct Engine {
             case APTMOD_INFO_CTA: return SH::CTA;
             case APTMOD_INFO_ENGINE: return G::ENGINE;
             case APTMOD_INFO_BLKSZ: return G::BLKSZ;
+            case APTMOD_INFO_FP64_GFLOPS: return measure_fp64();
         }
         return -1;
     }

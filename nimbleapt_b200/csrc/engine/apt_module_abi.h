@@ -57,7 +57,8 @@ enum {
     APTMOD_INFO_P = 0, APTMOD_INFO_K, APTMOD_INFO_NU, APTMOD_INFO_ND, APTMOD_INFO_NMON, APTMOD_INFO_NMON2,
     APTMOD_INFO_DMAX, APTMOD_INFO_ROWS, APTMOD_INFO_ROWS2, APTMOD_INFO_TTROWS, APTMOD_INFO_L,
     APTMOD_INFO_LAUNCHES, APTMOD_INFO_TOTALITERS, APTMOD_INFO_W, APTMOD_INFO_CTA, APTMOD_INFO_ENGINE,
-    APTMOD_INFO_BLKSZ
+    APTMOD_INFO_BLKSZ,
+    APTMOD_INFO_FP64_GFLOPS /* measures: a pure DFMA kernel on the engine's device, timed with CUDA events */
 };
 
 /* timing of the last run, measured with CUDA events on the engine's stream */
