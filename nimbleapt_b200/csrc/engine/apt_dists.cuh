@@ -341,7 +341,10 @@ __device__ __forceinline__ void bern_logit_acc(double y, const double (&eta)[N],
 // terms advance in lock step.  Same arithmetic and fix-ups as bern_logit_acc.
 template <int NR, int NC>
 __device__ __forceinline__ void bern_logit_tile(const double (&y)[NR], const double (&eta)[NR][NC], double (&acc)[NC]) {
-    constexpr int RPB = (NC >= 8) ? 1 : ((8 / NC) < NR ? (8 / NC) : NR);  // rows per batch
+#ifndef APT_TILE_BATCH
+#define APT_TILE_BATCH 8
+#endif
+    constexpr int RPB = (NC >= APT_TILE_BATCH) ? 1 : ((APT_TILE_BATCH / NC) < NR ? (APT_TILE_BATCH / NC) : NR);  // rows per batch
     constexpr int M = RPB * NC;
     static_assert(NR % RPB == 0, "rows per thread must be a multiple of the batch");
 #pragma unroll

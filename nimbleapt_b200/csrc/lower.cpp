@@ -1580,8 +1580,10 @@ struct Lowerer {
                 TB = opts.rungs_per_pass > 0 ? opts.rungs_per_pass : 16;
                 while (TB > 1 && TB / 2 >= nchains) TB /= 2;
                 if (TB < 1 || TB > 32 || (TB & (TB - 1))) throw Error("rungs_per_pass must be a power of two <= 32");
-                R = opts.cta_threads == 2 ? 2 : 1;  // rows per thread (cta_threads doubles as the tuning knob of the grid engine)
-                csplit = (opts.cta_threads == 12 && TB >= 2) ? 2 : 1;  // threads per row, each owning TB / csplit chains (measured slower on B200: off by default)
+                // scalar streaming path (used when tile mode does not apply): one row per thread, all TB chains.  Two rows
+                // per thread and chains split over two threads were measured slower and survive only as tuning switches.
+                R = getenv("APTB200_GRID_R2") ? 2 : 1;
+                csplit = (getenv("APTB200_GRID_CSPLIT2") && TB >= 2) ? 2 : 1;
                 W = std::min(32, 256 / TB);  // control lanes per chain inside the finishing CTA
                 ring_ok = (R == 1) && !getenv("APTB200_NO_RING");
                 // tile mode: TBT chains x RT rows per thread, CS = TB / TBT lanes share a row group
@@ -1705,7 +1707,7 @@ struct Lowerer {
             out << "  static constexpr int LADDER_MINB = " << minb << ";\n";
         }
         out << "  static constexpr bool STATE_IN_SMEM = " << (smem_state && engine == 1 ? "true" : "false") << ", HAS_FAMILY = " << (has_family ? "true" : "false") << ";\n";
-        out << "  static constexpr int ENGINE = " << engine << ", TB = " << TB << ", R = " << R << ", GRID_THREADS = 256, RING_SLOTS = " << ring_slots << ", CSPLIT = " << csplit << ", GRID_MINB = " << (engine == 2 && opts.lanes_per_chain > 0 ? opts.lanes_per_chain : (csplit == 2 ? 3 : 2)) << ", NSTAGE = " << units.size() << ";\n";
+        out << "  static constexpr int ENGINE = " << engine << ", TB = " << TB << ", R = " << R << ", GRID_THREADS = 256, RING_SLOTS = " << ring_slots << ", CSPLIT = " << csplit << ", GRID_MINB = " << (getenv("APTB200_GRID_MINB") ? std::max(1, atoi(getenv("APTB200_GRID_MINB"))) : (csplit == 2 ? 3 : 2)) << ", NSTAGE = " << units.size() << ";\n";
         // derived arrays (data-only terms, filled by derived_kernel when data is uploaded)
         out << "  static constexpr int NDER = " << derived.size() << ";\n";
         out << "  static long der_inst(int k) { return ";
