@@ -84,6 +84,8 @@ typedef struct {
     int engine;           /* 0 = auto, 1 = ladder-resident kernel, 2 = grid-wide likelihood passes */
     int rungs_per_pass;   /* grid engine: chains evaluated per pass over the data (0 = auto) */
     int verbose;          /* print the initial ladder like APT:279 and the nvcc command */
+    int cluster_ctas;     /* ladder-resident engine: CTAs (SMs) per ladder, 1 | 2 | 4 | 8; 0 = auto (more than one only with
+                             few ladders and large sampler families: thread-block cluster, state in global memory) */
 } apt_build_opts;
 
 /* arguments of cAPT$run (APT:336-348).  Initialise with apt_run_args_default(). */

@@ -16,7 +16,7 @@ class BuildOpts(C.Structure):
     _fields_ = [("monitorTmax", C.c_int), ("ULT", C.c_double), ("n_ladders", C.c_int), ("ladder0", C.c_uint32),
                 ("seed", C.c_uint32), ("device", C.c_int), ("record_decisions", C.c_int), ("fuse_links", C.c_int),
                 ("lanes_per_chain", C.c_int), ("cta_threads", C.c_int), ("engine", C.c_int),
-                ("rungs_per_pass", C.c_int), ("verbose", C.c_int)]
+                ("rungs_per_pass", C.c_int), ("verbose", C.c_int), ("cluster_ctas", C.c_int)]
 
 
 ABORT_FN = C.CFUNCTYPE(C.c_int, C.c_void_p)

@@ -142,7 +142,7 @@ class APT:
     the nvcc compile and the device allocation all happen here, so `compileNimble` is an identity."""
 
     def __init__(self, conf, Temps, monitorTmax=True, ULT=1e6, thinPrintTemps=1, nLadders=1, seed=11, ladder0=0,
-                 device=0, record=False, fuseLinks=True, lanesPerChain=0, ctaThreads=0, engine=0, rungsPerPass=0,
+                 device=0, record=False, fuseLinks=True, lanesPerChain=0, ctaThreads=0, engine=0, rungsPerPass=0, clusterCtas=0,
                  verbose=False, compileOnly=False, **dots):
         if isinstance(conf, NimbleModel):  # APT:249-250
             conf = configureMCMC(conf, **dots)
@@ -196,6 +196,7 @@ class APT:
         o.monitorTmax, o.ULT, o.n_ladders, o.ladder0, o.seed, o.device = int(bool(monitorTmax)), float(ULT), int(nLadders), int(ladder0), int(seed), int(device)
         o.record_decisions, o.fuse_links, o.lanes_per_chain, o.cta_threads = int(bool(record)), int(bool(fuseLinks)), int(lanesPerChain), int(ctaThreads)
         o.engine, o.rungs_per_pass, o.verbose = int(engine), int(rungsPerPass), int(bool(verbose))
+        o.cluster_ctas = int(clusterCtas)
         self._temps0 = temps
         self.nTemps = len(temps)
         self.nLadders = int(nLadders)

@@ -105,7 +105,7 @@ struct Engine {
     std::vector<DevBuf<double>> arrays;
     std::vector<DevBuf<int>> iarrays;
     Data D{};
-    DevBuf<double> theta, lpd, temps, lp, scale, blk, empir, famdelta, model_theta, scale0, blk0;
+    DevBuf<double> theta, lpd, temps, lp, scale, blk, empir, famdelta, wpart, model_theta, scale0, blk0;
     DevBuf<int> slot, cnt, accswap;
     DevBuf<double> g_partial, g_pend, g_scratch;  // grid engine
     DevBuf<unsigned int> g_ticket;
@@ -166,6 +166,7 @@ struct Engine {
         blk.alloc(std::max<size_t>(nch * G::BLKSZ, 1)); empir.alloc(std::max<size_t>(nch * G::EMPSZ, 1));
         accswap.alloc(nch * K); model_theta.alloc((size_t)L * P);
         famdelta.alloc(G::HAS_FAMILY ? nch * G::NU * APT_FAM_MAXG : 1); famdelta.zero(stream);
+        wpart.alloc((size_t)L * 8 * APT_FAM_MAXG); wpart.zero(stream);
         empir.zero(stream); lp.zero(stream);
         // Temps <- sort(Temps)  (APT:266)
         std::vector<double> t(in->temps, in->temps + K);
@@ -331,7 +332,7 @@ struct Engine {
         a.adapt_temps = ra->adaptTemps; a.tune1 = ra->tuneTemper1; a.tune2 = ra->tuneTemper2; a.ULT = ULT;
         a.thin = thin; a.thin2 = thin2; a.monitor_tmax = monitor_tmax;
         a.off = off; a.off2 = off2; a.cap = cap; a.cap2 = cap2; a.ttcap = ttcap;
-        a.theta = theta.p; a.lpd = lpd.p; a.temps = temps.p; a.lp = lp.p; a.scale = scale.p; a.blk = blk.p; a.empir = empir.p; a.famdelta = famdelta.p;
+        a.theta = theta.p; a.lpd = lpd.p; a.temps = temps.p; a.lp = lp.p; a.scale = scale.p; a.blk = blk.p; a.empir = empir.p; a.famdelta = famdelta.p; a.wpart = wpart.p;
         a.slot = slot.p; a.cnt = cnt.p; a.accswap = accswap.p;
         a.samples = samples.p; a.samples2 = samples2.p; a.samplesT = samplesT.p; a.samples2T = samples2T.p;
         a.logprobs = logprobs.p; a.temptraj = temptraj.p;
@@ -348,6 +349,16 @@ struct Engine {
                 a.it0 = it0; a.it1 = std::min<long long>(ra->niter, it0 + chunk);
                 a.rng_iter0 = rngIter; a.total_iters0 = totalIters;
                 APT_CUDA(cudaEventRecord(ev0, stream));
+                if constexpr (G::CLUSTER > 1) {
+                    cudaLaunchConfig_t cfg{};
+                    cfg.gridDim = dim3((unsigned)(L * G::CLUSTER)); cfg.blockDim = dim3(SH::CTA);
+                    cfg.dynamicSmemBytes = SH::SM_BYTES; cfg.stream = stream;
+                    cudaLaunchAttribute at[1];
+                    at[0].id = cudaLaunchAttributeClusterDimension;
+                    at[0].val.clusterDim.x = G::CLUSTER; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+                    cfg.attrs = at; cfg.numAttrs = 1;
+                    APT_CUDA(cudaLaunchKernelEx(&cfg, ladder_kernel<G>, a));
+                } else
                 ladder_kernel<G><<<grid, SH::CTA, SH::SM_BYTES, stream>>>(a);
                 APT_CUDA(cudaGetLastError());
                 APT_CUDA(cudaEventRecord(ev1, stream));

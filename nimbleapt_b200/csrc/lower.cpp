@@ -1499,6 +1499,17 @@ struct Lowerer {
         out << "  };\n";
     }
 
+    // wide update (apt_engine.cuh::rw_update_wide): only in cluster mode, for single samplers whose dependants include
+    // a FULL declaration with many more instances than one tile could stride through quickly
+    bool unit_is_wide(const Unit& u, int cluster, int tiles, int W) const {
+        if (cluster <= 1 || u.count != 1 || getenv("APTB200_NO_WIDE")) return false;
+        for (auto& g : u.groups) {
+            if (!g.full) return false;  // old values of PARTIAL groups would need a second wide pass
+        }
+        long mx = 0;
+        for (auto& g : u.groups) mx = std::max(mx, decls[g.decl].ninst);
+        return mx >= 32L * W;
+    }
     void choose_shape(int& W, int& tiles, int& teams, bool& smem_state) {
         long ndep = 1, items = K;
         for (auto& u : units) {
@@ -1556,6 +1567,24 @@ struct Lowerer {
         int W, tiles, teams;
         bool smem_state;
         choose_shape(W, tiles, teams, smem_state);
+        // Cluster mode: with few ladders and a CTA-wide team whose work items (sampler-family members x rungs) exceed
+        // one CTA's tiles many times over, a ladder spans a thread-block cluster of up to 8 CTAs (one per SM); chain
+        // state then lives in global memory and the stages are separated by cluster barriers.
+        int cluster = 1;
+        {
+            long items = K;
+            for (auto& u : units) items = std::max<long>(items, (long)K * u.count);
+            const int nl = std::max(1, opts.n_ladders);
+            if (teams == 1 && items >= 8L * tiles && !getenv("APTB200_NO_CLUSTER")) {
+                while (cluster < 8 && (long)nl * cluster * 2 <= 148 && items >= 4L * tiles * cluster * 2) cluster *= 2;
+            }
+            if (opts.cluster_ctas > 0) {
+                if (opts.cluster_ctas > 8 || (opts.cluster_ctas & (opts.cluster_ctas - 1))) throw Error("cluster_ctas must be 1, 2, 4 or 8");
+                if (teams != 1 && opts.cluster_ctas > 1) throw Error("cluster_ctas > 1 needs a CTA-wide team (lanes_per_chain * chains in flight > 32)");
+                cluster = opts.cluster_ctas;
+            }
+            if (cluster > 1) smem_state = false;
+        }
         // ---- engine selection.  Grid engine: few chains, at least one declaration too large for one CTA per
         // chain (config 3: N = 1e6 rows): every tempered update of all chains is served by ONE pass over the data.
         int engine = 1, TB = 1, R = 1, csplit = 1;
@@ -1569,14 +1598,21 @@ struct Lowerer {
             if (engine == 2) {
                 if (has_family) throw Error("grid engine: sampler families are not supported yet (use engine = 1)");
                 const long big_min = opts.engine == 2 ? 256 : 8192;
-                bool any = false;
+                bool any = false, all = true;
                 for (auto& u : units) {
                     int nb = 0;
                     for (auto& g : u.groups)
                         if (g.full && decls[g.decl].ninst >= big_min && decls[g.decl].loops.size() == 1 && decls[g.decl].dist != "dmnorm") { g.big = true; nb++; any = true; }
                     if (nb > 2) throw Error("grid engine: at most 2 large declarations per sampler are supported");
+                    if (nb == 0) all = false;
                 }
+                if (!all && opts.engine != 2) {  // auto: a sampler without a large declaration belongs to the ladder-resident engine
+                    engine = 1;
+                    for (auto& u : units)
+                        for (auto& g : u.groups) g.big = false;
+                } else {
                 if (!any) throw Error("grid engine requested but no declaration is large enough to be evaluated grid-wide");
+                if (!all) throw Error("grid engine: every sampler needs a large declaration among its dependents (use engine = 1)");
                 TB = opts.rungs_per_pass > 0 ? opts.rungs_per_pass : 16;
                 while (TB > 1 && TB / 2 >= nchains) TB /= 2;
                 if (TB < 1 || TB > 32 || (TB & (TB - 1))) throw Error("rungs_per_pass must be a power of two <= 32");
@@ -1595,6 +1631,7 @@ struct Lowerer {
                     tile_rt = std::min(4, 2 * tile_cs);  // 4 rows x 4 chains measured best at 16 rungs (8 x 4 spills at 128 registers)
                     if (const char* e = getenv("APTB200_TILE_RT")) tile_rt = std::max(2, atoi(e) & ~1);
                     tile_rows = (32 / tile_cs) * tile_rt;
+                }
                 }
             }
         }
@@ -1659,9 +1696,14 @@ struct Lowerer {
                     << ">(c, D, it_ / " << units[ui].count << ", it_ % " << units[ui].count << ");\n";
                 out << "    c.team_sync();\n    if (active) apt::family_commit<Model, S" << ui << ">(c);\n";
                 ui++;
+            } else if (unit_is_wide(units[ui], cluster, tiles, W)) {
+                // cluster mode, a sampler whose dependants are a large declaration: the whole cluster evaluates ONE
+                // chain at a time (K x W lanes could not cover the latency of thousands of terms per lane)
+                out << "    for (int k = 0; k < K; k++) apt::rw_update_wide<Model, S" << ui << ">(c, D, k, active);\n";
+                ui++;
             } else {
                 out << "    if (active) for (int k = c.tile_id; k < K; k += c.ntiles) {\n";
-                while (ui < units.size() && units[ui].count == 1) {
+                while (ui < units.size() && units[ui].count == 1 && !unit_is_wide(units[ui], cluster, tiles, W)) {
                     out << "      apt::rw_update<Model, S" << ui << ">(c, D, k, 0);\n";
                     ui++;
                 }
@@ -1693,7 +1735,7 @@ struct Lowerer {
         out << "  static constexpr int P = " << P << ", ND = " << ND << ", NU = " << NU << ", NSAMP = " << units.size() << ", K = " << K
             << ", NMON = " << mon.size() << ", NMON2 = " << mon2.size() << ", DMAX = " << DMAX << ", W = " << W << ";\n";
         out << "  static constexpr int NARR = " << used_arrays.size() << ", NIARR = " << iarrays.size() << ", BLKSZ = " << BLKSZ << ", EMPSZ = " << EMPSZ << ";\n";
-        out << "  static constexpr int TILES_PER_LADDER = " << tiles << ", TEAMS_PER_CTA = " << teams << ";\n";
+        out << "  static constexpr int TILES_PER_LADDER = " << tiles << ", TEAMS_PER_CTA = " << teams << ", CLUSTER = " << (engine == 1 ? cluster : 1) << ";\n";
         {
             // resident CTAs per SM the ladder kernel is compiled for (register cap = 64K / (LADDER_MINB * CTA)): as many
             // as shared memory admits, but never fewer than 64 registers per thread

@@ -127,6 +127,17 @@ def test_c4_family_medium():
     np.testing.assert_allclose(eng.logProbsLadder(0), orc.logProbs(0), rtol=1e-9)
 
 
+def test_c4_cluster_mode_wide_updates():
+    """The same model with the ladder spanning a cluster of 4 CTAs: family members over all CTAs, the block sampler's
+    1200 Poisson terms evaluated cluster-wide one chain at a time (rw_update_wide), state in global memory."""
+    spec = models.c4_glmm(G=60, per=20, K=6)
+    eng, orc = _both(spec, clusterCtas=4, lanesPerChain=32)
+    assert "rw_update_wide" in eng.lowered_source()
+    _run_both(eng, orc, 210, 9)
+    np.testing.assert_allclose(eng.mvSamples.matrix(0), orc.samples(0), rtol=1e-7, atol=1e-9)
+    np.testing.assert_allclose(eng.logProbsLadder(0), orc.logProbs(0), rtol=1e-9)
+
+
 def test_grid_engine_mid_size_against_oracle():
     """Grid engine on a 100k-row logistic model, 16 rungs in one pass: decisions vs the oracle for 30 iterations."""
     spec = models.logistic(100000, 50, 16, seed_off=3)

@@ -23,9 +23,11 @@ SMALL = {
     # thread, 4 rungs -> 4 rows x 2 chains; N is not a multiple of 64, so the remainder path runs too
     "c3tile16": lambda: models.logistic(3000, 15, 16, seed_off=5),
     "c3tile4": lambda: models.logistic(1500, 20, 4, seed_off=6),
+    # ladder spanning a thread-block cluster (state in global memory, cluster barriers between sampler stages)
+    "c4cluster": lambda: models.c4_glmm(G=20, per=10, K=4),
     "mixed": lambda: models.mixed_dists(),  # dbinom(size>1) dpois dgamma dbeta dexp dunif dnorm(tau) + all sampler options
 }
-BUILD_KW = {"c3grid": dict(engine=2), "c3tile16": dict(engine=2), "c3tile4": dict(engine=2)}
+BUILD_KW = {"c4cluster": dict(clusterCtas=4, lanesPerChain=32), "c3grid": dict(engine=2), "c3tile16": dict(engine=2), "c3tile4": dict(engine=2)}
 
 
 @pytest.mark.parametrize("name", list(SMALL))
