@@ -9,8 +9,9 @@
  *   nimbleCode({...}) / nimbleModel(code, constants, data, inits)   apt_model_create + apt_model_set_array
  *     (vignettes/nimbleAPT-vignette.Rmd:56-72)
  *   conf$addSampler(target, type = "sampler_RW_tempered" |          apt_model_add_sampler
- *     "sampler_RW_block_tempered", control = list(...))
- *     (APT:649-660, APT:770-781; vignette:131-132)
+ *     "sampler_RW_block_tempered" | "sampler_slice_tempered",
+ *     control = list(...))
+ *     (APT:649-660, APT:770-781, APT:898-912; vignette:131-132; demo/APT_demo.R:174-177)
  *   configureMCMC(model, monitors =, thin =) monitors/thin           apt_model_set_monitors / apt_model_set_thin
  *     (APT:302-311)
  *   buildAPT(conf, Temps, monitorTmax, ULT, thinPrintTemps)          apt_build        (lowering + nvcc + device state)
@@ -36,6 +37,10 @@
  *     block b < 0x8000   -> two standard normals z[2b], z[2b+1] by Box-Muller on
  *                           u1 = U(w0,w1), u2 = U(w2,w3):  sqrt(-2 ln u1) * (cos, sin)(2 pi u2)
  *     block 0x8000       -> acceptance uniform U(w0,w1) (only consumed when 0 >= logMHR, nimble `decide`)
+ *   sampler_slice_tempered (APT:929-964): uniform number j of the update, in the order the reference draws them
+ *     (j = 0: rexp(1) = -log U; 1: offset of the initial interval; 2: maxStepsL; 3: first x1; 4, 5, ...: shrinkage
+ *     draws), is read from block j / 2 as U(w0,w1) for even j and U(w2,w3) for odd j.  Injected tables are not
+ *     consulted by this sampler.
  *   swap proposal ii (0-based) of the iteration: unit = 0xFFFFFFFF, rung field = ii, block 0:
  *     rcat uniform U(w0,w1), acceptance uniform U(w2,w3)
  *   U(hi,lo) = ((hi >> 6) * 2^26 + (lo >> 6) + 0.5) * 2^-52: 52 random bits, strictly inside (0,1).
@@ -68,6 +73,8 @@ typedef struct {
     int temperPriors;           /* control$temperPriors: -1 = unspecified -> error (APT:660,781) */
     const double* propCov;      /* control$propCov, d x d column-major, NULL = 'identity' (block sampler only) */
     int propCov_dim;            /* d of the matrix passed in propCov (checked against the target, APT:816) */
+    double width;               /* control$width          (slice sampler only, APT:911)  default 1   */
+    int sliceMaxSteps;          /* control$sliceMaxSteps  (slice sampler only, APT:912)  default 100 */
 } apt_sampler_control;
 
 typedef struct {
@@ -131,9 +138,9 @@ enum {
     APT_ACCSWAP = 7,        /* accCountSwap   [nTemps][nTemps] (from, to), last run      APT:482 */
     APT_LOGPROBTEMPS = 8,   /* logProbTemps   [nTemps]                                   APT:447 */
     APT_RUNG_STATES = 9,    /* mvTemps        [nTemps][n_params]                         APT:272 */
-    APT_SCALES = 10,        /* sampler scale  [nTemps][n_sampler_units]                  APT:743,859 */
+    APT_SCALES = 10,        /* sampler scale (slice sampler: width)  [nTemps][n_sampler_units]  APT:743,859,982 */
     APT_BLOCK_STATE = 11,   /* per rung, per block sampler: propCov, chol, scale*chol (d*d each, column-major) */
-    APT_DECISIONS = 12,     /* test hook [niter][nTemps][n_sampler_units] 0/1 */
+    APT_DECISIONS = 12,     /* test hook [niter][nTemps][n_sampler_units] 0/1 (slice sampler: log-probability evaluations of the update mod 256) */
     APT_SWAP_RECORD = 13,   /* test hook [niter][nTemps]  iTo | accepted << 16 */
     APT_MODEL_STATE = 14    /* the model's parameter values after run (rung 1)           APT:548 */
 };
@@ -156,7 +163,8 @@ void apt_build_opts_default(apt_build_opts* o);
 void apt_run_args_default(apt_run_args* a);
 
 /* ---- model + configuration (replaces nimbleCode/nimbleModel/configureMCMC for the supported BUGS subset:
- *      dnorm dunif dgamma dbeta dbinom dbern dpois dexp dmnorm(cholesky=), deterministic links) */
+ *      dnorm dunif dgamma dbeta dbinom dbern dpois dexp dcat dmnorm(cholesky=), deterministic links,
+ *      elements of constant arrays selected by a sampled node, e.g. rfx[k]) */
 int apt_model_create(const char* bugs_code, apt_model** out);
 void apt_model_free(apt_model* m);
 int apt_model_set_array(apt_model* m, const char* name, int role, const double* values, const int64_t* dims, int ndim);

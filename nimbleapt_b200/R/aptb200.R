@@ -14,6 +14,7 @@
 
 sampler_RW_tempered       <- structure(list(name = "sampler_RW_tempered"),       class = "aptb200_sampler_type")
 sampler_RW_block_tempered <- structure(list(name = "sampler_RW_block_tempered"), class = "aptb200_sampler_type")
+sampler_slice_tempered    <- structure(list(name = "sampler_slice_tempered"),    class = "aptb200_sampler_type")
 
 ## Works with a nimble MCMCconf (conf$samplerConfs[[i]]$target / $name / $control, conf$monitors, conf$thin, conf$model)
 ## or with a plain list(model = list(code =, constants =, data =, inits =), samplers = list(...), monitors =, thin =).
@@ -44,7 +45,7 @@ buildAPT <- function(conf, Temps, monitorTmax = TRUE, ULT = 1E6, thinPrintTemps 
     for (nm in names(data))      .Call("aptR_model_set_array", m, nm, 1L, data[[nm]])
     for (nm in names(inits))     .Call("aptR_model_set_array", m, nm, 2L, inits[[nm]])
     for (s in samplers) {
-        if (is.null(s$control$temperPriors))                                             # APT:660, APT:781
+        if (is.null(s$control$temperPriors) && !grepl("slice", s$type))                  # APT:660, APT:781 (not read by the slice sampler, APT:909-912)
             stop(paste0("control$temperPriors unspecified in ", s$type))
         .Call("aptR_model_add_sampler", m, s$target, s$type, s$control)
     }

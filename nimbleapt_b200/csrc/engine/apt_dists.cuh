@@ -252,6 +252,28 @@ __device__ __forceinline__ double dexp_log(double x, double scale) {
     return (-x / scale) - log(scale);
 }
 
+// nimble's dcat(x, prob) [NIMBLE-UNVERIFIED: "prob" need not be normalised; values outside 1..K and non-integers
+// have probability 0]; the reference's demo model uses it for its discrete node (demo/APT_demo.R:84).
+template <int K>
+__device__ __forceinline__ double dcat_log(double x, const double (&prob)[K]) {
+    if (isnan(x)) return x;
+    double sum = 0.0;
+#pragma unroll
+    for (int i = 0; i < K; i++) sum += prob[i];
+    if (isnan(sum)) return sum;
+    if (x < 1.0 || x > (double)K || x != floor(x)) return APT_NEG_INF;
+    double px = prob[0];
+    const int ix = (int)x - 1;
+#pragma unroll
+    for (int i = 1; i < K; i++) px = (i == ix) ? prob[i] : px;  // no dynamic indexing of a register array
+    return log(px / sum);
+}
+// element of a constant array selected by a sampled node (e.g. rfx[k]): clamped into the array, so that a state the
+// prior excludes (its logProb is -Inf) cannot read out of bounds
+__device__ __forceinline__ int dyn_index(double v, int n) {
+    return (int)fmin(fmax(v, 1.0), (double)n);
+}
+
 // Fused form of  y ~ dbinom(prob = ilogit(eta), size = 1)  (lowering peephole, build option fuse_links):
 //   log p(y | eta) = -(max(t, 0) + log(1 + exp(-|t|))),  t = (1 - 2y) eta          (apt_softplus.cuh)
 // instead of the reference's chain  p = 1/(1+exp(-eta)); q = 1-p; dbinom_raw(y, 1, p, q).  Walking through

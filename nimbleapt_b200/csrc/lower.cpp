@@ -71,6 +71,7 @@ struct Group {
 };
 struct Unit {  // one generated sampler struct: a single sampler or a family
     int kind = 0, d = 1, unit0 = 0, count = 1;
+    bool discrete = false;  // slice sampler: model$isDiscrete(target) (APT:926)
     std::vector<int> tgt;  // theta indices of member 0
     const SamplerConf* conf = nullptr;
     std::vector<Group> groups;
@@ -271,6 +272,9 @@ struct Lowerer {
                 } else if (dist == "dexp") {
                     d.dist = dist;
                     d.args = {has_kw(c, "scale") ? kwarg(c, "scale", 99) : mk_bin('/', one, need(kwarg(c, "rate", 0), "rate"))};
+                } else if (dist == "dcat") {  // demo/APT_demo.R:84
+                    d.dist = dist;
+                    d.args = {need(kwarg(c, "prob", 0), "prob")};
                 } else if (dist == "dmnorm") {
                     d.dist = dist;
                     if (!has_kw(c, "cholesky"))
@@ -279,7 +283,7 @@ struct Lowerer {
                               has_kw(c, "prec_param") ? kwarg(c, "prec_param", 99) : one};
                 } else {
                     throw Error("line " + std::to_string(rd.line) + ": unsupported distribution '" + dist +
-                                "' (supported: dnorm dunif dgamma dbeta dbinom dbern dpois dexp dmnorm)");
+                                "' (supported: dnorm dunif dgamma dbeta dbinom dbern dpois dexp dcat dmnorm)");
                 }
             } else {
                 EP rhs = rd.rhs;
@@ -523,6 +527,11 @@ struct Lowerer {
                 for (auto& ix : d.lhs->a)
                     if (ix->k == Expr::RANGE) ln = (int)(std::llround(ceval(ix->a[1], {})) - std::llround(ceval(ix->a[0], {})) + 1);
                 if (ln != d.mvn_n) throw Error("dmnorm: node and mean have different lengths");
+            } else if (d.dist == "dcat") {
+                // the probability vector, element by element (kept in mean_elems so that the dependency analysis sees it)
+                for (auto& el : vector_elements(d.args[0])) d.mean_elems.push_back(inline_det(el));
+                d.mvn_n = (int)d.mean_elems.size();
+                if (d.mvn_n < 1 || d.mvn_n > 64) throw Error("dcat: the probability vector must have between 1 and 64 elements");
             } else {
                 for (auto& a : d.args) d.iargs.push_back(inline_det(a));
             }
@@ -755,6 +764,16 @@ struct Lowerer {
         throw Error("target has no stochastic declaration");
     }
 
+    bool target_is_discrete(int tgt) const {  // model$isDiscrete(target): the target's own distribution
+        for (int di : stoch_decls) {
+            const CDecl& d = decls[di];
+            if (!d.lhs_param) continue;
+            const Var& v = vars.at(d.lhs->name);
+            if (tgt >= v.theta_off && tgt < v.theta_off + v.size) return d.dist == "dcat" || d.dist == "dbinom" || d.dist == "dpois";
+        }
+        throw Error("target has no stochastic declaration");
+    }
+
     void build_units() {
         const auto& S = spec.samplers;
         if (S.empty()) throw Error("no samplers configured: add sampler_RW_tempered / sampler_RW_block_tempered samplers");
@@ -765,11 +784,15 @@ struct Lowerer {
             int kind;
             if (sc.type == "sampler_RW_tempered" || sc.type == "RW_tempered") kind = 0;
             else if (sc.type == "sampler_RW_block_tempered" || sc.type == "RW_block_tempered") kind = 1;
-            else throw Error("unsupported sampler type '" + sc.type + "' (supported: sampler_RW_tempered, sampler_RW_block_tempered)");
-            if (sc.ctl.temperPriors < 0)  // APT:660, APT:781
+            else if (sc.type == "sampler_slice_tempered" || sc.type == "slice_tempered") kind = 2;
+            else throw Error("unsupported sampler type '" + sc.type + "' (supported: sampler_RW_tempered, sampler_RW_block_tempered, sampler_slice_tempered)");
+            if (sc.ctl.temperPriors < 0 && kind != 2)  // APT:660, APT:781 (the slice sampler never reads it, APT:909-912)
                 throw Error("control$temperPriors unspecified in " + std::string(kind == 0 ? "sampler_RW_tempered" : "sampler_RW_block_tempered"));
             std::vector<int> tgt = expand_target(sc.target);
             if (kind == 0 && tgt.size() > 1) throw Error("cannot use RW sampler on more than one target; try RW_block sampler");  // APT:682
+            if (kind == 2 && tgt.size() > 1) throw Error("cannot use slice sampler on more than one target node");  // APT:928
+            if (kind == 2 && !(sc.ctl.width > 0)) throw Error("slice sampler: control$width must be positive");
+            if (kind == 2 && sc.ctl.sliceMaxSteps < 1) throw Error("slice sampler: control$sliceMaxSteps must be >= 1");
             if (kind == 0 && sc.ctl.log && sc.ctl.reflective)
                 throw Error("cannot use reflective RW sampler on a log scale (i.e. with options log=TRUE and reflective=TRUE");  // APT:684
             if (sc.ctl.adaptFactorExponent < 0) throw Error("cannot use RW sampler with adaptFactorExponent control parameter less than 0");  // APT:685
@@ -789,6 +812,10 @@ struct Lowerer {
                 u.blkoff = blkoff; blkoff += 3 * u.d * u.d;
                 u.empoff = empoff;
                 if (sc.ctl.adaptive && !sc.ctl.adaptScaleOnly) empoff += sc.ctl.adaptInterval * u.d;
+            }
+            if (kind == 2) {  // sumJumps (APT:925) lives in the per-rung sampler block state
+                u.blkoff = blkoff; blkoff += 1;
+                u.discrete = target_is_discrete(tgt[0]);
             }
             // family detection: a run of scalar samplers on consecutive theta elements with identical control
             size_t e = s + 1;
@@ -901,11 +928,15 @@ struct Lowerer {
                 if (e->a.empty()) {
                     auto it = env.find(e->name);
                     if (it != env.end()) return it->second;
+                    // a scalar sampled node used as an index (demo/APT_demo.R:42-71, rfx[k]): clamped by gen_offset
+                    auto pv = vars.find(e->name);
+                    if (pv != vars.end() && pv->second.role == Var::PARAM && pv->second.size == 1 && dyn_dim > 0 && !cv_mode)
+                        return "apt::dyn_index(th[" + std::to_string(pv->second.theta_off) + "], " + std::to_string(dyn_dim) + ")";
                     throw Error("unknown index variable '" + e->name + "'");
                 } else {
                     auto it = vars.find(e->name);
                     if (it == vars.end() || (it->second.role != Var::CONST && it->second.role != Var::DATA))
-                        throw Error("index expressions may only use loop variables and constants: " + to_string(e));
+                        throw Error("index expressions may only use loop variables, constants and scalar sampled nodes: " + to_string(e));
                     return "(int)" + gen_load(it->second, e, env);
                 }
             case Expr::BIN:
@@ -937,13 +968,16 @@ struct Lowerer {
         int64_t stride = 1;
         for (size_t k = 0; k < e->a.size(); k++) {
             if (e->a[k]->k == Expr::RANGE) throw Error("vector slice used where a scalar is required: " + to_string(e));
+            dyn_dim = (v.role == Var::CONST || v.role == Var::DATA) ? v.dims[k] : 0;  // only constant arrays may be indexed by a sampled node
             std::string term = "(" + gen_int(e->a[k], env) + " - 1)";
+            dyn_dim = 0;
             if (stride != 1) term += " * " + std::to_string(stride);
             s += (k ? " + " : "") + term;
             stride *= v.dims[k];
         }
         return s;
     }
+    int64_t dyn_dim = 0;  // extent of the array dimension whose index expression is being generated (0: no sampled-node index allowed)
     // chain-vectorised mode (grid engine): parameters of TB chains live in shared memory as thT[param][chain]
     bool cv_mode = false;
     std::map<const Expr*, std::string> hoisted;  // inprod nodes already emitted as per-(row, chain) arrays
@@ -1390,6 +1424,10 @@ struct Lowerer {
                 out << "};\n    const double U_[" << n * n << "] = {";
                 for (int e = 0; e < n * n; e++) out << (e ? ", " : "") << gen_dbl(d.chol_elems[e], env);
                 out << "};\n    return apt::dmnorm_chol_log<" << n << ">(x_, mu_, U_, (" << gen_dbl(d.iargs[0], env) << ") != 0.0);\n";
+            } else if (d.dist == "dcat") {
+                out << "    const double p_[" << d.mvn_n << "] = {";
+                for (int e = 0; e < d.mvn_n; e++) out << (e ? ", " : "") << gen_dbl(d.mean_elems[e], env);
+                out << "};\n    return apt::dcat_log<" << d.mvn_n << ">(" << gen_dbl(d.lhs, env) << ", p_);\n";
             } else {
                 out << "    return " << density_expr(d, gen_dbl(d.lhs, env), env, lin_of_decl(d), di) << ";\n";
                 if (is_fused_bern(d)) {
@@ -1434,7 +1472,9 @@ struct Lowerer {
             << ", COUNT = " << u.count << ", AI = " << ctl.adaptInterval << ", BLKOFF = " << u.blkoff << ", EMPOFF = " << u.empoff << ";\n";
         out << "    static constexpr bool LOG = " << (ctl.log ? "true" : "false") << ", REFL = " << (ctl.reflective ? "true" : "false")
             << ", ADAPT = " << (ctl.adaptive ? "true" : "false") << ", SCALE_ONLY = " << (ctl.adaptScaleOnly ? "true" : "false")
-            << ", TEMPER_PRIORS = " << (ctl.temperPriors ? "true" : "false") << ", HAS_PARTIAL = " << (has_partial ? "true" : "false") << ";\n";
+            << ", TEMPER_PRIORS = " << (ctl.temperPriors ? "true" : "false") << ", HAS_PARTIAL = " << (has_partial ? "true" : "false")
+            << ", DISCRETE = " << (u.discrete ? "true" : "false") << ";\n";
+        out << "    static constexpr int MAXSTEPS = " << ctl.sliceMaxSteps << ";\n";
         out << "    static constexpr double AEXP = " << fmt_d(ctl.adaptFactorExponent) << ";\n";
         auto sw = [&](const char* name, const char* type, std::function<std::string(const Group&)> f) {
             out << "    __device__ static constexpr " << type << " " << name << "(int g) { return ";
@@ -1502,7 +1542,7 @@ struct Lowerer {
     // wide update (apt_engine.cuh::rw_update_wide): only in cluster mode, for single samplers whose dependants include
     // a FULL declaration with many more instances than one tile could stride through quickly
     bool unit_is_wide(const Unit& u, int cluster, int tiles, int W) const {
-        if (cluster <= 1 || u.count != 1 || getenv("APTB200_NO_WIDE")) return false;
+        if (cluster <= 1 || u.count != 1 || u.kind == 2 || getenv("APTB200_NO_WIDE")) return false;
         for (auto& g : u.groups) {
             if (!g.full) return false;  // old values of PARTIAL groups would need a second wide pass
         }
@@ -1595,6 +1635,11 @@ struct Lowerer {
                     if (g.full) maxfull = std::max(maxfull, decls[g.decl].ninst);
             const long nchains = (long)std::max(1, opts.n_ladders) * K;
             if (opts.engine == 2 || (opts.engine == 0 && !has_family && nchains <= 256 && maxfull >= 65536)) engine = 2;
+            for (auto& u : units)
+                if (u.kind == 2) {
+                    if (opts.engine == 2) throw Error("grid engine: sampler_slice_tempered is not supported (use engine = 1)");
+                    engine = 1;
+                }
             if (engine == 2) {
                 if (has_family) throw Error("grid engine: sampler families are not supported yet (use engine = 1)");
                 const long big_min = opts.engine == 2 ? 256 : 8192;
@@ -1602,7 +1647,7 @@ struct Lowerer {
                 for (auto& u : units) {
                     int nb = 0;
                     for (auto& g : u.groups)
-                        if (g.full && decls[g.decl].ninst >= big_min && decls[g.decl].loops.size() == 1 && decls[g.decl].dist != "dmnorm") { g.big = true; nb++; any = true; }
+                        if (g.full && decls[g.decl].ninst >= big_min && decls[g.decl].loops.size() == 1 && decls[g.decl].dist != "dmnorm" && decls[g.decl].dist != "dcat") { g.big = true; nb++; any = true; }
                     if (nb > 2) throw Error("grid engine: at most 2 large declarations per sampler are supported");
                     if (nb == 0) all = false;
                 }
@@ -1704,7 +1749,7 @@ struct Lowerer {
             } else {
                 out << "    if (active) for (int k = c.tile_id; k < K; k += c.ntiles) {\n";
                 while (ui < units.size() && units[ui].count == 1 && !unit_is_wide(units[ui], cluster, tiles, W)) {
-                    out << "      apt::rw_update<Model, S" << ui << ">(c, D, k, 0);\n";
+                    out << "      apt::" << (units[ui].kind == 2 ? "slice_update" : "rw_update") << "<Model, S" << ui << ">(c, D, k, 0);\n";
                     ui++;
                 }
                 out << "    }\n";
@@ -1778,7 +1823,7 @@ struct Lowerer {
         for (size_t i = 0; i < units.size(); i++) {
             const Unit& u = units[i];
             out << "      {" << u.kind << ", " << u.d << ", " << u.unit0 << ", " << u.count << ", " << u.blkoff << ", " << u.empoff << ", "
-                << u.conf->ctl.adaptInterval << ", " << fmt_d(u.conf->ctl.scale) << ", "
+                << u.conf->ctl.adaptInterval << ", " << fmt_d(u.kind == 2 ? u.conf->ctl.width : u.conf->ctl.scale) << ", "
                 << ((u.kind == 1 && !u.conf->propCov.empty()) ? "PROPCOV" + std::to_string(i) : std::string("nullptr")) << "},\n";
         }
         out << "    };\n    return info[s];\n  }\n};\n}  // namespace aptgen\n}  // namespace\nAPT_DEFINE_MODULE(aptgen::Model)\n";

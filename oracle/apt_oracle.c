@@ -8,6 +8,7 @@
  *   pSwapCalc                    APT_functions.R:556-576
  *   sampler_RW_tempered          APT_functions.R:649-761
  *   sampler_RW_block_tempered    APT_functions.R:770-889
+ *   sampler_slice_tempered       APT_functions.R:898-995
  *   sampler indexing             APT_functions.R:281-287
  * plus the nimble behaviours those lines call into (calculateDiff, getLogProb, decide, decideAndJump,
  * setAndCalculateDiff, calcAdaptationFactor, rmnorm_chol, rcat, nimCopy, initializeModel), restated from
@@ -43,7 +44,7 @@
 enum { OP_END = 0, OP_CONST, OP_LOOP, OP_LOAD0, OP_LOAD1, OP_LOAD2, OP_ADD, OP_SUB, OP_MUL, OP_DIV, OP_POW, OP_NEG,
        OP_EXP, OP_LOG, OP_ABS, OP_SQRT, OP_ILOGIT, OP_LOGIT, OP_PHI, OP_ICLOGLOG, OP_CLOGLOG, OP_LOG1P, OP_STEP,
        OP_MIN, OP_MAX, OP_INPROD, OP_SUM, OP_LGAMMA };
-enum { D_NORM = 0, D_UNIF, D_GAMMA, D_BETA, D_BINOM, D_POIS, D_MNORM_CHOL, D_EXP };
+enum { D_NORM = 0, D_UNIF, D_GAMMA, D_BETA, D_BINOM, D_POIS, D_MNORM_CHOL, D_EXP, D_CAT };
 
 /* declaration record layout (ints) */
 enum { R_KIND = 0, R_DIST, R_NLOOP, R_LO0, R_LO1, R_LO2, R_HI0, R_HI1, R_HI2, R_VAR, R_LNDIM, R_LIDX0, R_LIDX1,
@@ -74,12 +75,14 @@ typedef struct {
     double adapt_exp, scale0;
     double* propcov0;
     int lower_code, upper_code;
+    int max_steps, discrete; /* sampler_slice_tempered: control$sliceMaxSteps (APT:912), model$isDiscrete(target) (APT:926) */
     int ncopyv, ncopylp;
     int *copyv, *copylp;
 } orc_sspec;
 
 typedef struct {
-    double scale, gamma1;
+    double scale, gamma1; /* slice sampler: scale = width */
+    double sumJumps;      /* slice sampler (APT:925) */
     int timesRan, timesAccepted, timesAdapted;
     double *propCov, *chol, *cholScaled, *empir;
 } orc_sstate;
@@ -262,6 +265,14 @@ static double calc_node(orc_ctx* c, int d, int inst) {
             for (int i = 0; i < n; i++) ch[i + j * n] = *vref(c, off + (ac[2] - 1 + i) + (ac[4] - 1 + j) * nrow);
         int prec = (int)eval(c, a[2 * ARGREC + 1]);
         lp = apt_dmnorm_chol_log(x, mu, ch, n, prec, wk);
+    } else if (r[R_DIST] == D_CAT) {
+        double x = *vref(c, lhs_index(c, r, 0));
+        const int* ap = &a[0];
+        double other = ap[6] >= 0 ? eval(c, ap[6]) : 0;
+        int n = ap[5] - ap[4] + 1;
+        double pr[64];
+        for (int e = 0; e < n && e < 64; e++) pr[e] = slice_get(c, ap, other, e);
+        lp = apt_dcat_log(x, pr, n);
     } else {
         double x = *vref(c, lhs_index(c, r, 0));
         double p0 = r[R_NARGS] > 0 ? eval(c, a[1]) : 0;
@@ -299,7 +310,8 @@ static double calculate_diff(orc_ctx* c, const int* nd, const int* ni, int n) {
 }
 static double get_logprob_nodes(orc_ctx* c, const int* nd, const int* ni, int n) {
     double s = 0;
-    for (int k = 0; k < n; k++) s += c->lp[c->m->lp_off[nd[k]] + ni[k]];
+    for (int k = 0; k < n; k++)
+        if (c->m->decl[nd[k] * DREC + R_KIND] == 1) s += c->lp[c->m->lp_off[nd[k]] + ni[k]]; /* deterministic nodes carry no logProb */
     return s;
 }
 static double get_logprob_all(orc_ctx* c) {
@@ -388,6 +400,7 @@ int orc_spec_set(const orc_model* m, orc_sspec* specs, int s, int kind, int d, c
     if (propcov0) memcpy(p->propcov0, propcov0, sizeof(double) * d * d);
     else for (int i = 0; i < d * d; i++) p->propcov0[i] = (i % (d + 1) == 0) ? 1.0 : 0.0;
     p->lower_code = lower_code; p->upper_code = upper_code;
+    p->max_steps = 100; p->discrete = 0;
     /* copy lists for nimCopy(nodes = calcNodes, logProb = TRUE)  (APT:722-724, decideAndJump) */
     orc_ctx c; c.m = m; c.mut = NULL; c.lp = NULL;
     int nv = 0, nl = 0;
@@ -415,8 +428,14 @@ int orc_spec_set(const orc_model* m, orc_sspec* specs, int s, int kind, int d, c
     return 0;
 }
 
+/* extra control of sampler_slice_tempered (kind 2); scale0 of orc_spec_set carries control$width */
+int orc_spec_set_slice(orc_sspec* specs, int s, int max_steps, int discrete) {
+    specs[s].max_steps = max_steps; specs[s].discrete = discrete;
+    return 0;
+}
+
 static void sstate_reset(const orc_sspec* p, orc_sstate* s) {
-    s->scale = p->scale0; s->gamma1 = 0; s->timesRan = s->timesAccepted = s->timesAdapted = 0;
+    s->scale = p->scale0; s->gamma1 = 0; s->sumJumps = 0; s->timesRan = s->timesAccepted = s->timesAdapted = 0;
     if (p->kind == 1) {
         int d = p->d;
         memcpy(s->propCov, p->propcov0, sizeof(double) * d * d);
@@ -660,6 +679,74 @@ static int run_block(orc_ladder* L, int s, int tt, orc_buf* model, orc_buf* save
     return jump;
 }
 
+/* sampler_slice_tempered$run (APT:929-964), setAndCalculateTarget (APT:969-975), adaptiveProcedure (APT:976-987).
+   Uniform number j of the update (in the order the reference draws them: rexp, L offset, maxStepsL, x1, shrinkage
+   draws ...) is read from slot block j / 2, words (0,1) for even j and (2,3) for odd j; rexp(1) = -log(U).
+   Returns the number of setAndCalculateTarget calls (recorded modulo 256 as the unit's "decision"). */
+typedef struct { orc_ladder* L; int s, tt; uint32_t j; uint32_t w[4]; } slice_rng;
+static double slice_unif(slice_rng* r) {
+    if ((r->j & 1u) == 0) apt_slot_words(r->L->seed, r->L->ladder, r->L->rngIter, (uint32_t)r->s, (uint32_t)r->tt, r->j >> 1, r->w);
+    double u = (r->j & 1u) ? apt_u53(r->w[2], r->w[3]) : apt_u53(r->w[0], r->w[1]);
+    r->j++;
+    return u;
+}
+static double slice_set_and_calc(orc_ctx* c, const orc_sspec* p, orc_buf* model, double value, int* ncalls) {
+    if (p->discrete) value = floor(value);
+    model->mut[p->tgt[0]] = value;
+    double lp = 0;
+    for (int k = 0; k < p->ncalc; k++) lp += calc_node(c, p->calc_decl[k], p->calc_inst[k]); /* calculate(model, calcNodes) */
+    (*ncalls)++;
+    return lp;
+}
+static int run_slice(orc_ladder* L, int s, int tt, orc_buf* model, orc_buf* saved, double temperature) {
+    const orc_sspec* p = &L->specs[s];
+    orc_sstate* st = &L->ss[s + tt * L->NS];
+    orc_ctx c; c.m = L->m; c.mut = model->mut; c.lp = model->lp;
+    slice_rng rg; rg.L = L; rg.s = s; rg.tt = tt; rg.j = 0;
+    int ncalls = 0;
+    double width = st->scale;
+    double u = get_logprob_nodes(&c, p->calc_decl, p->calc_inst, p->ncalc) / temperature - (-log(slice_unif(&rg)));
+    double x0 = model->mut[p->tgt[0]];
+    double Lb = x0 - slice_unif(&rg) * width;
+    double Rb = Lb + width;
+    int maxStepsL = (int)floor(slice_unif(&rg) * p->max_steps);
+    int maxStepsR = p->max_steps - 1 - maxStepsL;
+    double lp = slice_set_and_calc(&c, p, model, Lb, &ncalls) / temperature;
+    while (maxStepsL > 0 && !isnan(lp) && lp >= u) {
+        Lb = Lb - width;
+        lp = slice_set_and_calc(&c, p, model, Lb, &ncalls) / temperature;
+        maxStepsL--;
+    }
+    lp = slice_set_and_calc(&c, p, model, Rb, &ncalls) / temperature;
+    while (maxStepsR > 0 && !isnan(lp) && lp >= u) {
+        Rb = Rb + width;
+        lp = slice_set_and_calc(&c, p, model, Rb, &ncalls) / temperature;
+        maxStepsR--;
+    }
+    double x1 = Lb + slice_unif(&rg) * (Rb - Lb);
+    lp = slice_set_and_calc(&c, p, model, x1, &ncalls) / temperature;
+    while (isnan(lp) || lp < u) {
+        if (x1 < x0) Lb = x1; else Rb = x1;
+        x1 = Lb + slice_unif(&rg) * (Rb - Lb);
+        lp = slice_set_and_calc(&c, p, model, x1, &ncalls) / temperature;
+    }
+    copy_nodes(p, model, saved);
+    double jumpDist = fabs(x1 - x0);
+    if (p->adaptive) {
+        st->timesRan++;
+        st->sumJumps += jumpDist;
+        if (st->timesRan % p->adapt_interval == 0) {
+            double adaptFactor = pow(3.0 / 4.0, st->timesAdapted);
+            double meanJump = st->sumJumps / st->timesRan;
+            st->scale = st->scale + (2 * meanJump - st->scale) * adaptFactor;
+            st->timesAdapted++;
+            st->timesRan = 0;
+            st->sumJumps = 0;
+        }
+    }
+    return ncalls & 0xFF;
+}
+
 /* ------------------------------------------------------------------ swap machinery */
 /* pSwapCalc  (APT:556-576) */
 static void pswap_calc(orc_ladder* L) {
@@ -748,7 +835,8 @@ int orc_ladder_run(orc_ladder* L, long niter, int reset, int resetMV, int resetT
             orc_buf* saved = &L->saved[tt];
             for (int s = 0; s < NS; s++) {
                 int jump = L->specs[s].kind == 0 ? run_scalar(L, s, tt, model, saved, L->Temps[tt])
-                                                 : run_block(L, s, tt, model, saved, L->Temps[tt]);
+                         : L->specs[s].kind == 1 ? run_block(L, s, tt, model, saved, L->Temps[tt])
+                                                 : run_slice(L, s, tt, model, saved, L->Temps[tt]);
                 if (L->recDec) L->recDec[((size_t)L->itRun * K + tt) * NS + s] = (unsigned char)jump;
             }
             orc_ctx c; c.m = m; c.mut = model->mut; c.lp = model->lp;

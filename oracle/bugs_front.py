@@ -21,7 +21,8 @@ import numpy as np
 OPS = dict(END=0, CONST=1, LOOP=2, LOAD0=3, LOAD1=4, LOAD2=5, ADD=6, SUB=7, MUL=8, DIV=9, POW=10, NEG=11,
            EXP=12, LOG=13, ABS=14, SQRT=15, ILOGIT=16, LOGIT=17, PHI=18, ICLOGLOG=19, CLOGLOG=20, LOG1P=21,
            STEP=22, MIN=23, MAX=24, INPROD=25, SUM=26, LGAMMA=27)
-DISTS = dict(dnorm=0, dunif=1, dgamma=2, dbeta=3, dbinom=4, dpois=5, dmnorm=6, dexp=7)
+DISTS = dict(dnorm=0, dunif=1, dgamma=2, dbeta=3, dbinom=4, dpois=5, dmnorm=6, dexp=7, dcat=8)
+DISCRETE_DISTS = ("dcat", "dbinom", "dpois")  # model$isDiscrete(target), APT_functions.R:926
 DREC, MAXARGS, ARGREC = 80, 6, 8
 R_KIND, R_DIST, R_NLOOP, R_LO0, R_HI0, R_VAR, R_LNDIM, R_LIDX0, R_LRDIM, R_LRLO, R_LRHI, R_NARGS, R_ARGS = \
     0, 1, 2, 3, 6, 9, 10, 11, 13, 14, 15, 16, 17
@@ -263,6 +264,8 @@ class OracleModel:
                     cargs = [kw.get("lambda", args[0] if args else None)]
                 elif dist == "dexp":
                     cargs = [kw["scale"]] if "scale" in kw else [("bin", "/", one, kw.get("rate", args[0] if args else None))]
+                elif dist == "dcat":  # nimbleAPT/demo/APT_demo.R:84
+                    cargs = [kw.get("prob", args[0] if args else None)]
                 elif dist == "dmnorm":
                     mean = kw.get("mean", args[0] if args else None)
                     assert "cholesky" in kw, "oracle front end supports dmnorm(mean, cholesky=, prec_param=) only"
@@ -438,8 +441,13 @@ class OracleModel:
             elif name in self.vars:
                 v = self.vars[name]
                 assert all(i[0] != "range" for i in t[2]), "vector slice used where a scalar is required: " + name
-                for i in t[2]:
+                for dim, i in enumerate(t[2]):
                     self._compile_expr(i, loopnames, subst)
+                    if any(self.vars[r[1]].role in ("param", "det") for r in self._reads(i, [])):
+                        # index computed from a sampled node (demo: rfx_theta[k]): clamped into the array so that a
+                        # state the prior excludes (k outside 1..K has logProb -Inf) cannot read out of bounds
+                        self._emit("CONST", self._const(float(v.dims[dim]))); self._emit("MIN")
+                        self._emit("CONST", self._const(1.0)); self._emit("MAX")
                 if len(t[2]) == 0:
                     assert v.size == 1, "whole-array use of %s where a scalar is required" % name
                 self._emit("LOAD%d" % len(t[2]), self.varid[name])
@@ -502,7 +510,7 @@ class OracleModel:
             r[R_NARGS] = len(d["args"])
             for a, t in enumerate(d["args"]):
                 base = R_ARGS + a * ARGREC
-                if d["stoch"] and d["dist"] == "dmnorm" and a == 0:
+                if d["stoch"] and (d["dist"] == "dmnorm" or d["dist"] == "dcat") and a == 0:
                     rec, other = self._slice_rec(t, loopnames, None)
                     if other is not None:
                         rec[6] = self.compile_scalar(other, loopnames)
@@ -560,7 +568,12 @@ class OracleModel:
                 base = base + (lo - 1) * stride
                 cnt, stride_r = hi - lo + 1, stride
             else:
-                val = np.asarray(self.const_eval(i, env))
+                try:
+                    val = np.asarray(self.const_eval(i, env))
+                except (KeyError, ValueError):
+                    # index computed from a sampled node: only constant arrays may be indexed this way, and those
+                    # are never looked up here (the sampled node inside the index is itself one of the reads)
+                    raise ValueError("element of a non-constant array selected by a sampled node: %r" % (t,))
                 base = base + (np.broadcast_to(val, (n,)).astype(np.int64) - 1) * stride
             stride *= v.dims[k]
         return base, cnt, stride_r
@@ -641,6 +654,19 @@ class OracleModel:
                     if d["dist"] == "dbeta":
                         return ("num", 0.0), ("num", 1.0), subst
                     return ("num", -inf), ("num", inf), subst
+        raise KeyError("target has no stochastic declaration")
+
+    def is_discrete(self, target_idx):
+        """model$isDiscrete(target) for a scalar target (APT_functions.R:926)."""
+        for d in self.cdecls:
+            v = self.vars[d["lhs"][1]]
+            if not (d["stoch"] and v.role == "param"):
+                continue
+            env, n = self._inst_env(d)
+            base, cnt, stride = self.lhs_elements(d, env, n)
+            for e in range(cnt):
+                if np.any(v.off + base + e * stride == target_idx):
+                    return d["dist"] in DISCRETE_DISTS
         raise KeyError("target has no stochastic declaration")
 
     def monitor_indices(self, names):

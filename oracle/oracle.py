@@ -37,6 +37,7 @@ def lib():
         L.orc_spec_set.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, ip, C.c_int, ip, ip, C.c_int, ip,
                                    ip, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double,
                                    dp, C.c_int, C.c_int]
+        L.orc_spec_set_slice.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
         L.orc_ladder_new.restype = C.c_void_p
         L.orc_ladder_new.argtypes = [C.c_void_p, C.c_void_p, C.c_int, dp, C.c_int, C.c_uint32, C.c_uint32, C.c_double,
                                      C.c_int, C.c_int, ip, C.c_int, ip]
@@ -82,7 +83,8 @@ def _da(a):
     return a, a.ctypes.data_as(C.POINTER(C.c_double))
 
 
-SAMPLER_KINDS = {"sampler_RW_tempered": 0, "RW_tempered": 0, "sampler_RW_block_tempered": 1, "RW_block_tempered": 1}
+SAMPLER_KINDS = {"sampler_RW_tempered": 0, "RW_tempered": 0, "sampler_RW_block_tempered": 1, "RW_block_tempered": 1,
+                 "sampler_slice_tempered": 2, "slice_tempered": 2}
 
 
 class OracleAPT:
@@ -98,9 +100,13 @@ class OracleAPT:
         for s in samplers:
             ctl = dict(s.get("control", {}))
             kind = SAMPLER_KINDS[s["type"]]
+            if kind == 2:  # sampler_slice_tempered never reads temperPriors (APT_functions.R:909-912)
+                ctl.setdefault("temperPriors", True)
             if "temperPriors" not in ctl:  # APT_functions.R:660,781
                 raise ValueError("control$temperPriors unspecified in %s" % s["type"])
             tgt = om.expand_target(s["target"])
+            if kind == 2 and len(tgt) > 1:  # APT_functions.R:928
+                raise ValueError("cannot use slice sampler on more than one target node")
             if kind == 0 and len(tgt) > 1:  # APT_functions.R:682
                 raise ValueError("cannot use RW sampler on more than one target; try RW_block sampler")
             cd, ci, td, ti = om.dependencies(tgt)
@@ -140,7 +146,7 @@ class OracleAPT:
                 if not np.allclose(pcm, pcm.T):  # APT_functions.R:817
                     raise ValueError("propCov matrix must be symmetric")
                 pca, pcp = _da(pcm.reshape(-1, order="F"))
-            scale = float(ctl.get("scale", 1.0))
+            scale = float(ctl.get("scale", 1.0)) if sp["kind"] != 2 else float(ctl.get("width", 1.0))  # APT_functions.R:911
             afe = float(ctl.get("adaptFactorExponent", 0.8))
             if ctl.get("log", False) and ctl.get("reflective", False):  # APT_functions.R:684
                 raise ValueError("cannot use reflective RW sampler on a log scale")
@@ -151,6 +157,8 @@ class OracleAPT:
                            int(bool(ctl.get("adaptive", True))), int(bool(ctl.get("adaptScaleOnly", False))),
                            int(ctl.get("adaptInterval", 200)), int(bool(ctl["temperPriors"])), afe, scale, pcp,
                            sp["lower"], sp["upper"])
+            if sp["kind"] == 2:
+                L.orc_spec_set_slice(self.specs, i, int(ctl.get("sliceMaxSteps", 100)), int(om.is_discrete(sp["tgt"][0])))
         self.mon, self.mon_labels = om.monitor_indices(list(monitors))
         self.mon2, self.mon2_labels = om.monitor_indices(list(monitors2))
         m1, m1p = _ia(self.mon if self.mon else [0]); m2, m2p = _ia(self.mon2 if self.mon2 else [0])

@@ -212,6 +212,22 @@ double apt_dexp_log(double x, double scale) {
 }
 
 /*
+ * nimble's dcat(x, prob, K, give_log) [NIMBLE-UNVERIFIED, restated from its documented behaviour: "prob" need not
+ * be normalised; values outside 1..K and non-integers have probability 0]: log(prob[x] / sum(prob)).
+ * Used by the demo model of the reference (nimbleAPT/demo/APT_demo.R:84, `k ~ dcat(pk[1:K])`).
+ */
+double apt_dcat_log(double x, const double* prob, int K) {
+    if (isnan(x)) return x;
+    double sum = 0.0;
+    for (int i = 0; i < K; i++) {
+        if (isnan(prob[i])) return prob[i];
+        sum += prob[i];
+    }
+    if (x < 1.0 || x > (double)K || x != floor(x)) return NEG_INF;
+    return log(prob[(int)x - 1] / sum);
+}
+
+/*
  * nimble's dmnorm_chol(x, mean, chol, n, prec_param, give_log) [NIMBLE-UNVERIFIED, restated from its
  * documented behaviour]: chol is the UPPER Cholesky factor U (U'U = cov or precision), column-major.
  *   dens = -n*log(sqrt(2pi)) + (prec_param ? +1 : -1) * sum_i log U_ii

@@ -147,3 +147,50 @@ def mixed_dists(n=40, K=6):
                 data=dict(yb=yb, yp=yp, yg=yg, yn=yn),
                 inits=dict(p=np.array(0.4), rate=np.array(2.0), shape=np.array(2.0), grate=np.array(1.0), mu=np.array(0.0), tau=np.array(1.0)),
                 samplers=samplers, monitors=["p", "rate", "shape", "grate", "mu", "tau"], Temps=temps, ULT=1e6)
+
+
+def demo_wrong(N=50, K=10, nTemps=7):
+    """The 'wrong' model of nimbleAPT/demo/APT_demo.R:83-92 with its four tempered samplers (demo:173-177) and
+    Temps = 1:7 (demo:196).  The demo's user functions k2theta / k2sigma (demo:42-71: theta0 + rfx_theta[k] and
+    abs(sigma0 + rfx_sigma[k])) are written as index expressions on the sampled node k, which the BUGS subset
+    supports; `pk`, `rfx_theta`, `rfx_sigma` are passed as constants (the demo passes them as inits of
+    right-hand-side-only nodes, demo:108)."""
+    rng = np.random.default_rng(DATA_SEED + 7)
+    y = rng.standard_normal(N)  # right$simulate('y'): theta = 0, sigma0 = 1 (demo:99-101,125)
+    rfx_theta, rfx_sigma = rng.standard_normal(K), rng.standard_normal(K)
+    code = """{
+    k      ~ dcat(pk[1:K])
+    theta0 ~ dnorm(0, sd=1E6)
+    theta  <- theta0 + rfx_theta[k]
+    sigma0 ~ dexp(1)
+    sigma  <- abs(abs(sigma0 + rfx_sigma[k]))
+    for (i in 1:N) {
+        y[i] ~ dnorm(mean=theta, sd=sigma)
+    }
+    }"""
+    tp = dict(temperPriors=True)
+    return dict(code=code, constants=dict(N=N, K=K, pk=np.full(K, 1.0 / K), rfx_theta=rfx_theta, rfx_sigma=rfx_sigma),
+                data=dict(y=y), inits=dict(k=np.array(1.0), theta0=np.array(0.0), sigma0=np.array(1.0)),
+                samplers=[dict(target="theta0", type="sampler_RW_tempered", control=tp),
+                          dict(target="sigma0", type="sampler_RW_tempered", control=tp),
+                          dict(target="k", type="sampler_slice_tempered", control=tp),
+                          dict(target=["theta0", "sigma0"], type="sampler_RW_block_tempered", control=tp)],
+                monitors=["k", "theta0", "sigma0"], Temps=np.arange(1, nTemps + 1, dtype=float), ULT=1e6)
+
+
+def demo_wrong_k_posterior(spec):
+    """Exact marginal posterior of k in demo_wrong(): theta0 has an (effectively) flat prior and integrates out
+    analytically, sigma0 ~ dexp(1) is integrated on a grid."""
+    y = spec["data"]["y"]
+    N, rs = len(y), spec["constants"]["rfx_sigma"]
+    s2 = float(np.sum((y - y.mean()) ** 2))
+    g = np.linspace(1e-6, 30.0, 3000001)
+    lw = []
+    for kk in range(len(rs)):
+        sg = np.abs(g + rs[kk])
+        with np.errstate(divide="ignore", invalid="ignore"):
+            lf = -g - (N - 1) * np.log(sg) - s2 / (2 * sg ** 2)
+        lw.append(np.where(np.isfinite(lf), lf, -np.inf))
+    lw = np.array(lw)
+    pk = np.trapezoid(np.exp(lw - lw.max()), g, axis=1)
+    return pk / pk.sum()

@@ -70,6 +70,21 @@ def test_control_validation_mirrors_reference():
     with pytest.raises(nb.AptError, match="propCov matrix must be symmetric"):  # APT:817
         nb.buildAPT(conf, Temps=[1, 2, 3])
     with pytest.raises(ValueError, match="unsupported sampler type"):
-        conf.addSampler("theta[1]", type="sampler_slice_tempered", control=dict(temperPriors=True))
+        conf.addSampler("theta[1]", type="sampler_RW_multinomial_tempered", control=dict(temperPriors=True))
+    conf.removeSamplers()
+    conf.addSampler("theta[1:2]", type="sampler_slice_tempered", control={})
+    with pytest.raises(nb.AptError, match="cannot use slice sampler on more than one target node"):  # APT:928
+        nb.buildAPT(conf, Temps=[1, 2, 3])
     with pytest.raises(TypeError, match="conf must either be a nimbleModel or a MCMCconf"):  # APT:252
         nb.buildAPT("not a conf", Temps=[1, 2])
+
+
+def test_demo_model_lowers_with_slice_sampler():
+    """demo/APT_demo.R:83-92,173-177: dcat, a constant array indexed by the sampled node, sampler_slice_tempered."""
+    apt = build_engine(models.demo_wrong(), compileOnly=True)
+    src = apt.lowered_source()
+    assert "apt::slice_update<Model, S2>" in src and "DISCRETE = true" in src
+    assert "apt::dcat_log<10>" in src and "apt::dyn_index(th[0], 10)" in src
+    assert os.path.exists(apt.modulePath)
+    with pytest.raises(nb.AptError, match="grid engine: sampler_slice_tempered is not supported"):
+        build_engine(models.demo_wrong(), compileOnly=True, engine=2)

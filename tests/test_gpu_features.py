@@ -50,9 +50,23 @@ def test_continuation_and_thinning():
     np.testing.assert_allclose(eng.modelState(0), orc.rung_state(0, 0), rtol=1e-8)  # APT:548
 
 
-@pytest.mark.parametrize("variant", ["temperPriorsFalse", "logScale", "reflective", "scaleOnly", "nonAdaptive", "identityPropCov"])
+@pytest.mark.parametrize("variant", ["temperPriorsFalse", "logScale", "reflective", "scaleOnly", "nonAdaptive", "identityPropCov",
+                                     "sliceContinuous", "slicePartial"])
 def test_control_options(variant):
-    if variant in ("temperPriorsFalse", "logScale", "reflective"):
+    if variant == "sliceContinuous":
+        # sampler_slice_tempered on a continuous node (APT:898-995): stepping out, shrinkage, width adaptation
+        spec = dict(models.c2_mixture(n=20, K=4, tmax=30.0))
+        spec["samplers"] = [dict(target="theta[1]", type="sampler_slice_tempered", control=dict(width=0.5, sliceMaxSteps=10, adaptInterval=50)),
+                            dict(target="theta[2]", type="sampler_RW_tempered", control=dict(temperPriors=True))]
+    elif variant == "slicePartial":
+        # slice updates whose dependants are a subset of a declaration (one random-effect group) + a non-adaptive one
+        spec = models.c4_glmm(G=6, per=8, K=4)
+        samplers = [dict(target="u[%d]" % (k + 1), type="sampler_slice_tempered", control=dict(adaptive=k != 1, adaptInterval=40)) for k in range(3)]
+        samplers += [dict(target="u[%d]" % (k + 1), type="sampler_RW_tempered", control=dict(temperPriors=True)) for k in range(3, 6)]
+        samplers.append(dict(target="b[1:2]", type="sampler_RW_block_tempered", control=dict(temperPriors=True)))
+        samplers.append(dict(target="sigma", type="sampler_RW_tempered", control=dict(temperPriors=True, log=True)))
+        spec = dict(spec, samplers=samplers)
+    elif variant in ("temperPriorsFalse", "logScale", "reflective"):
         spec = models.c4_glmm(G=6, per=8, K=4)
         samplers = [dict(target="u[%d]" % (k + 1), type="sampler_RW_tempered", control=dict(temperPriors=variant != "temperPriorsFalse")) for k in range(6)]
         samplers.append(dict(target="b[1:2]", type="sampler_RW_block_tempered", control=dict(temperPriors=variant != "temperPriorsFalse")))
@@ -116,6 +130,25 @@ def test_posterior_matches_oracle_within_4_mcse_c1():
         eg, eo = f(g), f(o)
         se = np.sqrt(eg.var(ddof=1) / Lg + eo.var(ddof=1) / Lo)
         assert abs(eg.mean() - eo.mean()) < 4 * se, (eg.mean(), eo.mean(), se)
+
+
+def test_posterior_demo_model_slice_sampler_within_4_mcse():
+    """The reference's demo model (demo/APT_demo.R): the discrete node k is sampled by sampler_slice_tempered; its
+    exact marginal posterior is known (tests/models.py).  64 independent ladders give the Monte-Carlo error."""
+    spec = models.demo_wrong()
+    exact = models.demo_wrong_k_posterior(spec)
+    L, niter, burn = 64, 6000, 1000
+    eng = build_engine(spec, nLadders=L)
+    eng.run(niter)
+    freq = np.zeros((L, len(exact)))
+    for l in range(L):
+        k = eng.mvSamples.matrix(l)[burn:, 0]
+        assert np.all(k == np.floor(k)) and k.min() >= 1 and k.max() <= len(exact)
+        freq[l] = np.bincount(k.astype(int) - 1, minlength=len(exact)) / len(k)
+    mean, mcse = freq.mean(axis=0), freq.std(axis=0, ddof=1) / np.sqrt(L)
+    assert np.all(np.abs(mean - exact) <= 4 * mcse + 2e-3), (mean, exact, mcse)
+    w = eng.scales(0)[:, 2]  # adapted slice widths (APT:982)
+    assert np.all(w > 0) and not np.allclose(w, 1.0)
 
 
 def test_c4_family_medium():

@@ -25,6 +25,9 @@ SMALL = {
     "c3tile4": lambda: models.logistic(1500, 20, 4, seed_off=6),
     # ladder spanning a thread-block cluster (state in global memory, cluster barriers between sampler stages)
     "c4cluster": lambda: models.c4_glmm(G=20, per=10, K=4),
+    # the reference's demo model (demo/APT_demo.R:83-92,173-177): dcat + dexp, a discrete node sampled by
+    # sampler_slice_tempered, elements of constant arrays selected by that node, scalar + block RW samplers
+    "demo": lambda: models.demo_wrong(),
     "mixed": lambda: models.mixed_dists(),  # dbinom(size>1) dpois dgamma dbeta dexp dunif dnorm(tau) + all sampler options
 }
 BUILD_KW = {"c4cluster": dict(clusterCtas=4, lanesPerChain=32), "c3grid": dict(engine=2), "c3tile16": dict(engine=2), "c3tile4": dict(engine=2)}
@@ -42,6 +45,10 @@ def test_logprob_matches_oracle(name):
     states = th0[None, :] + 0.3 * rng.standard_normal((17, P))
     if name == "c4":
         states[:, 20] = np.abs(states[:, 20]) + 0.1  # sigma inside its support
+    if name == "demo":
+        states[:, 0] = rng.integers(1, 11, size=states.shape[0])  # k inside its support ...
+        states[:3, 0] = [0.0, 11.0, 2.5]                           # ... and outside (dcat: -Inf on both sides)
+        states[:, 2] = np.abs(states[:, 2]) + 0.05                 # sigma0 > 0
     if name == "mixed":
         states = np.abs(states) + 0.05
         states[:, 0] = np.clip(states[:, 0], 0.02, 0.98)  # p in (0,1)

@@ -106,3 +106,20 @@ def test_dexp_stirlerr_bd0_lbeta():
         assert close(L.apt_bd0(x, np_), float(X * mp.log(X / M) + M - X), rtol=1e-13, atol=1e-18)
     for a, b in ((0.5, 0.7), (3.0, 12.0), (20.0, 30.0), (1e-3, 400.0)):
         assert close(L.apt_lbeta(a, b), special.betaln(a, b), rtol=1e-12, atol=1e-12)
+
+
+def test_dcat_unnormalised_and_edges():
+    """nimble's dcat (demo/APT_demo.R:84): log(prob[x] / sum(prob)); -Inf outside 1..K and for non-integers."""
+    import ctypes as C
+    L = lib()
+    L.apt_dcat_log.restype = C.c_double
+    L.apt_dcat_log.argtypes = [C.c_double, C.POINTER(C.c_double), C.c_int]
+    p = np.array([0.2, 1.5, 0.0, 3.3, 0.7])
+    pp = p.ctypes.data_as(C.POINTER(C.c_double))
+    for x in range(1, 6):
+        ref = np.log(p[x - 1] / p.sum()) if p[x - 1] > 0 else -np.inf
+        got = L.apt_dcat_log(float(x), pp, 5)
+        assert got == ref or close(got, ref, rtol=1e-15)
+    for x in (0.0, 6.0, -1.0, 2.5):
+        assert L.apt_dcat_log(x, pp, 5) == -np.inf
+    assert np.isnan(L.apt_dcat_log(float("nan"), pp, 5))

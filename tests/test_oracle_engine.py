@@ -77,6 +77,29 @@ def test_c2_analytic_posterior():
     assert abs(frac_pos.mean() - 0.5) < 4 * frac_pos.std(ddof=1) / np.sqrt(L) + 0.02  # both modes visited equally
 
 
+def test_demo_model_slice_sampler_exact_posterior():
+    """sampler_slice_tempered (APT:898-995) on the discrete node of the reference's demo model (demo/APT_demo.R:83-92):
+    the marginal posterior of k is known exactly (models.demo_wrong_k_posterior)."""
+    spec = models.demo_wrong()
+    exact = models.demo_wrong_k_posterior(spec)
+    L, niter, burn = 32, 10000, 1000
+    o = build_oracle(spec, nLadders=L)
+    o.run(niter, nthreads=8)
+    freq = np.zeros((L, len(exact)))
+    for l in range(L):
+        k = o.samples(l)[burn:, 0]
+        assert np.all(k == np.floor(k)) and k.min() >= 1 and k.max() <= len(exact)  # floor() of the slice draw, inside 1..K
+        freq[l] = np.bincount(k.astype(int) - 1, minlength=len(exact)) / len(k)
+    mean, mcse = freq.mean(axis=0), freq.std(axis=0, ddof=1) / np.sqrt(L)
+    assert np.all(np.abs(mean - exact) <= 4 * mcse + 2e-3), (mean, exact, mcse)
+    widths = np.array([o.scale(0, t, 2) for t in range(o.K)])
+    assert np.all(widths > 0) and not np.allclose(widths, 1.0)  # adaptiveProcedure ran (APT:976-987)
+    bad = dict(spec)
+    bad["samplers"] = [dict(target=["theta0", "sigma0"], type="sampler_slice_tempered", control={})]
+    with pytest.raises(ValueError, match="more than one target"):  # APT:928
+        build_oracle(bad)
+
+
 def test_sampler_validation_errors():
     spec = models.c2_mixture(K=4)
     bad = dict(spec)
