@@ -303,7 +303,7 @@ def main():
         sm = eng.mvSamples.matrix(-1)            # D2H: thinned traces of every local ladder
         return sm, sm
 
-    e2e_once(max(thin, (args.warmup // thin) * thin))  # untimed warm-up of the same call sequence (first NCCL collective sets up its channels)
+    e2e_once(args.steps)  # untimed warm-up of the same call sequence at the same size (first NCCL collective sets up its channels, trace and gather buffers reach their final size)
     barrier()
     t0 = time.perf_counter()
     samples, samples_all = e2e_once(args.steps)

@@ -41,6 +41,8 @@ struct apt_engine {
     void* nccl_dl = nullptr;
     void* comm = nullptr;
     int world = 1, rank = 0;
+    void* gather_buf = nullptr;  // device destination of the trace all-gather, kept between calls (grow only)
+    size_t gather_cap = 0;
 };
 
 #define API_BEGIN try {
@@ -390,6 +392,7 @@ struct RtFns {
     int (*Malloc)(void**, size_t);
     int (*Free)(void*);
     int (*Memcpy)(void*, const void*, size_t, int);
+    int (*MemcpyAsync)(void*, const void*, size_t, int, void*);
     int (*DeviceSynchronize)(void);
     int (*StreamSynchronize)(void*);
 };
@@ -429,6 +432,7 @@ static void load_nccl() {
     g_rt.Malloc = (decltype(g_rt.Malloc))r("cudaMalloc");
     g_rt.Free = (decltype(g_rt.Free))r("cudaFree");
     g_rt.Memcpy = (decltype(g_rt.Memcpy))r("cudaMemcpy");
+    g_rt.MemcpyAsync = (decltype(g_rt.MemcpyAsync))r("cudaMemcpyAsync");
     g_rt.DeviceSynchronize = (decltype(g_rt.DeviceSynchronize))r("cudaDeviceSynchronize");
     g_rt.StreamSynchronize = (decltype(g_rt.StreamSynchronize))r("cudaStreamSynchronize");
 }
@@ -475,17 +479,18 @@ int apt_comm_allgather_samples(apt_engine* e, int what, double* out, int64_t cap
     if (e->fn.device_ptr(e->mod, what, &dptr, &n_local, &stream)) throw Error("trace not available on the device");
     const int64_t total = n_local * e->world;
     if (total > capacity) throw Error("output buffer too small");
-    void* dall = nullptr;
-    RT_OK(g_rt.Malloc(&dall, (size_t)total * 8));
-    try {
-        NCCL_OK(g_nccl.AllGather(dptr, dall, (size_t)n_local, 8 /* ncclFloat64 */, e->comm, stream));
-        RT_OK(g_rt.StreamSynchronize(stream));
-        RT_OK(g_rt.Memcpy(out, dall, (size_t)total * 8, 2 /* D2H */));
-    } catch (...) {
-        g_rt.Free(dall);
-        throw;
+    // the gathered traces land in a device buffer the engine keeps (a cudaMalloc / cudaFree pair per call costs
+    // milliseconds and makes NCCL register a new buffer every time); the copy to the caller's host buffer is queued
+    // on the same stream right behind the collective
+    if ((size_t)total * 8 > e->gather_cap) {
+        if (e->gather_buf) g_rt.Free(e->gather_buf);
+        e->gather_buf = nullptr; e->gather_cap = 0;
+        RT_OK(g_rt.Malloc(&e->gather_buf, (size_t)total * 8));
+        e->gather_cap = (size_t)total * 8;
     }
-    g_rt.Free(dall);
+    NCCL_OK(g_nccl.AllGather(dptr, e->gather_buf, (size_t)n_local, 8 /* ncclFloat64 */, e->comm, stream));
+    RT_OK(g_rt.MemcpyAsync(out, e->gather_buf, (size_t)total * 8, 2 /* D2H */, stream));
+    RT_OK(g_rt.StreamSynchronize(stream));
     if (n_written) *n_written = total;
     API_END
 }
@@ -511,6 +516,11 @@ int apt_comm_allreduce_sum(apt_engine* e, double* inout, int64_t n) {
 
 int apt_comm_finalize(apt_engine* e) {
     API_BEGIN
+    if (e && e->gather_buf) {
+        g_rt.SetDevice(e->device);
+        g_rt.Free(e->gather_buf);
+        e->gather_buf = nullptr; e->gather_cap = 0;
+    }
     if (e && e->comm) {
         g_nccl.CommDestroy(e->comm);
         e->comm = nullptr;
