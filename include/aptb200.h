@@ -23,6 +23,7 @@
  *     $mvSamples2Tmax, $logProbs, $tempTraj, $accCountSwap, $Temps
  *     (APT:310-317, 386-393, 514-539, 277, 482)
  *   model$calculate()                                                apt_logprob
+ *   cAPT$calculateWAIC(nburnin)   (APT:593-635)                      apt_waic
  *
  * Conventions: every entry point returns 0 on success and a non-zero status otherwise; the message is
  * available from apt_last_error() (thread-local).  No C++ exception, longjmp or device pointer crosses this
@@ -93,6 +94,8 @@ typedef struct {
     int verbose;          /* print the initial ladder like APT:279 and the nvcc command */
     int cluster_ctas;     /* ladder-resident engine: CTAs (SMs) per ladder, 1 | 2 | 4 | 8; 0 = auto (more than one only with
                              few ladders and large sampler families: thread-block cluster, state in global memory) */
+    int enable_waic;      /* buildAPT(enableWAIC = TRUE) / configureMCMC(enableWAIC = TRUE)  APT:259,329-333: checks that the
+                             model has data nodes and that the monitors are valid for WAIC (mcmc_checkWAICmonitors, APT:1313) */
 } apt_build_opts;
 
 /* arguments of cAPT$run (APT:336-348).  Initialise with apt_run_args_default(). */
@@ -195,6 +198,12 @@ int apt_get_timing(apt_engine* e, apt_timing* t);
 /* whole-model log probability of caller-provided parameter vectors: theta [n][n_params] ->
  * out_total [n] and (optional) out_groups [n][n_logprob_groups] */
 int apt_logprob(apt_engine* e, const double* theta, int n, double* out_total, double* out_groups);
+/* cAPT$calculateWAIC(nburnin)  (APT:593-635) from the rung-1 samples in mvSamples: nburnin is in iterations before
+ * thinning (the rows skipped are ceiling(nburnin / thin of the last run), APT:605).  ladder >= 0: that ladder's samples
+ * (the reference has one ladder); -1: the samples of all local ladders pooled.  out[0] = WAIC = -2 (lppd - pWAIC),
+ * out[1] = lppd (logAvgProb), out[2] = pWAIC.  Fewer than 2 post-burn-in samples: out[0] = -Inf (APT:607-610).
+ * Fails unless the engine was built with enable_waic (the reference prints an error and returns NaN, APT:596-599). */
+int apt_waic(apt_engine* e, int64_t nburnin, int ladder, double out[3]);
 /* overwrite the model's current parameter values (inits) of one ladder (-1: all) before the next reset run */
 int apt_set_inits(apt_engine* e, const double* theta, int ladder);
 /* re-upload a constant/data array (same shape) — e.g. new observations for the same model */

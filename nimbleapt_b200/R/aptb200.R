@@ -7,6 +7,7 @@
 ##   cAPT$run(niter, reset, resetMV, resetTempering, simulateAll, time, adaptTemps, printTemps, tuneTemper1,
 ##            tuneTemper2, progressBar, thin, thin2)                                      APT_functions.R:336-348
 ##   as.matrix(cAPT$mvSamples), cAPT$logProbs, cAPT$tempTraj, cAPT$accCountSwap, cAPT$Temps
+##   cAPT$calculateWAIC(nburnin)                                                         APT_functions.R:593-635
 ##   runAPT(cAPT, niter, thin, ...)   (named by the north star; not present in the reference, SURVEY.md F5)
 ## The two sampler names are *recording* samplers: they capture target + control and never run in R.
 
@@ -52,7 +53,9 @@ buildAPT <- function(conf, Temps, monitorTmax = TRUE, ULT = 1E6, thinPrintTemps 
     .Call("aptR_model_set_monitors", m, 1L, as.character(monitors),  as.integer(thin), as.integer(thin2))
     .Call("aptR_model_set_monitors", m, 2L, as.character(monitors2), as.integer(thin), as.integer(thin2))
     Temps <- as.numeric(sort(Temps))                                                     # APT:266
-    h <- .Call("aptR_build", m, Temps, monitorTmax, ULT, as.integer(nLadders), as.integer(seed), as.integer(device))
+    dots <- list(...)
+    enableWAIC <- isTRUE(dots$enableWAIC) || isTRUE(conf$enableWAIC)                      # APT:259,329
+    h <- .Call("aptR_build", m, Temps, monitorTmax, ULT, as.integer(nLadders), as.integer(seed), as.integer(device), enableWAIC)
     self <- new.env()
     self$handle <- h; self$model <- m; self$nTemps <- length(Temps); self$thinPrintTemps <- thinPrintTemps
     self$monitorNames  <- strsplit(.Call("aptR_model_names", m, 1L), "\n")[[1]]
@@ -65,6 +68,16 @@ buildAPT <- function(conf, Temps, monitorTmax = TRUE, ULT = 1E6, thinPrintTemps 
         .Call("aptR_run", h, niter, c(reset, resetMV, resetTempering, simulateAll, time, adaptTemps, as.logical(printTemps)),
               c(tuneTemper1, tuneTemper2), as.integer(c(thin, thin2)))
         invisible(NULL)
+    }
+    self$calculateWAIC <- function(nburnin = 0, ladder = 0L) {                            # APT:593-635
+        if (!enableWAIC) {
+            print("Error: must set enableWAIC = TRUE in buildAPT to use the method calcualteWAIC. See help(buildAPT) and help(buildMCMC) for additional information.")
+            return(NaN)
+        }
+        w <- .Call("aptR_waic", h, nburnin, as.integer(ladder))
+        if (w[1] == -Inf) print("Error: need more than one post burn-in MCMC samples")
+        else if (is.nan(w[1])) print("WAIC was calculated as NaN.  You may need to add monitors to model latent states, in order for a valid WAIC calculation.")
+        w[1]
     }
     mk <- function(what, names, rowsInfo) structure(list(fetch = function(ladder = 0L) {
         x <- get(what, info(rowsInfo), length(names), ladder); colnames(x) <- names; x }), class = "aptb200_samples")

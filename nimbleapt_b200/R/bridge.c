@@ -91,11 +91,12 @@ SEXP aptR_model_names(SEXP p, SEXP which) {
     return Rf_mkString(buf); /* '\n'-separated; split on the R side */
 }
 
-SEXP aptR_build(SEXP p, SEXP temps, SEXP monitorTmax, SEXP ULT, SEXP nLadders, SEXP seed, SEXP device) {
+SEXP aptR_build(SEXP p, SEXP temps, SEXP monitorTmax, SEXP ULT, SEXP nLadders, SEXP seed, SEXP device, SEXP enableWAIC) {
     apt_build_opts o;
     apt_build_opts_default(&o);
     o.monitorTmax = Rf_asLogical(monitorTmax); o.ULT = Rf_asReal(ULT); o.n_ladders = Rf_asInteger(nLadders);
     o.seed = (uint32_t)Rf_asInteger(seed); o.device = Rf_asInteger(device); o.verbose = 1;
+    o.enable_waic = Rf_asLogical(enableWAIC);
     apt_engine* e = NULL;
     SEXP t = PROTECT(Rf_coerceVector(temps, REALSXP));
     int rc = apt_build(R_ExternalPtrAddr(p), REAL(t), LENGTH(t), &o, &e);
@@ -140,3 +141,12 @@ SEXP aptR_get(SEXP h, SEXP what, SEXP ladder, SEXP rows, SEXP cols) {
 }
 
 SEXP aptR_info(SEXP h, SEXP what) { return Rf_ScalarReal((double)apt_info(R_ExternalPtrAddr(h), Rf_asInteger(what))); }
+
+/* cAPT$calculateWAIC(nburnin)  (APT:593-635): numeric(3) = WAIC, lppd, pWAIC */
+SEXP aptR_waic(SEXP h, SEXP nburnin, SEXP ladder) {
+    SEXP out = PROTECT(Rf_allocVector(REALSXP, 3));
+    int rc = apt_waic(R_ExternalPtrAddr(h), (int64_t)Rf_asReal(nburnin), Rf_asInteger(ladder), REAL(out));
+    UNPROTECT(1);
+    chk(rc);
+    return out;
+}

@@ -17,7 +17,7 @@ class BuildOpts(C.Structure):
     _fields_ = [("monitorTmax", C.c_int), ("ULT", C.c_double), ("n_ladders", C.c_int), ("ladder0", C.c_uint32),
                 ("seed", C.c_uint32), ("device", C.c_int), ("record_decisions", C.c_int), ("fuse_links", C.c_int),
                 ("lanes_per_chain", C.c_int), ("cta_threads", C.c_int), ("engine", C.c_int),
-                ("rungs_per_pass", C.c_int), ("verbose", C.c_int), ("cluster_ctas", C.c_int)]
+                ("rungs_per_pass", C.c_int), ("verbose", C.c_int), ("cluster_ctas", C.c_int), ("enable_waic", C.c_int)]
 
 
 ABORT_FN = C.CFUNCTYPE(C.c_int, C.c_void_p)
@@ -42,7 +42,7 @@ EXPORTS = ["apt_last_error", "apt_version", "apt_sampler_control_default", "apt_
            "apt_run_args_default", "apt_model_create", "apt_model_free", "apt_model_set_array",
            "apt_model_add_sampler", "apt_model_remove_samplers", "apt_model_set_monitors", "apt_model_set_thin",
            "apt_model_names", "apt_model_lower", "apt_model_compile", "apt_build", "apt_free", "apt_run", "apt_info", "apt_get",
-           "apt_get_timing", "apt_logprob", "apt_set_inits", "apt_set_array", "apt_comm_unique_id", "apt_comm_init",
+           "apt_get_timing", "apt_logprob", "apt_waic", "apt_set_inits", "apt_set_array", "apt_comm_unique_id", "apt_comm_init",
            "apt_comm_allgather_samples", "apt_comm_allreduce_sum", "apt_comm_finalize"]
 
 _lib = None
@@ -80,6 +80,7 @@ def lib():
     L.apt_get.argtypes = [vp, C.c_int, C.c_int, dp, C.c_int64, C.POINTER(C.c_int64)]
     L.apt_get_timing.argtypes = [vp, C.POINTER(Timing)]
     L.apt_logprob.argtypes = [vp, dp, C.c_int, dp, dp]
+    L.apt_waic.argtypes = [vp, C.c_int64, C.c_int, dp]
     L.apt_set_inits.argtypes = [vp, dp, C.c_int]
     L.apt_set_array.argtypes = [vp, C.c_char_p, dp, C.c_int64]
     L.apt_comm_unique_id.argtypes = [C.POINTER(C.c_ubyte)]

@@ -21,6 +21,7 @@ Only device memory, kernels and NCCL live below this file, all inside libaptb200
 numpy is used for host arrays; torch is not used.
 """
 import ctypes as C
+import os
 import numpy as np
 
 from . import _lib
@@ -69,13 +70,14 @@ def nimbleModel(code, constants=None, data=None, inits=None, **_ignored):
 class MCMCconf:
     """configureMCMC(model, ...): holds samplerConfs, monitors, thin (APT_functions.R:249-250, 302-311)."""
 
-    def __init__(self, model, nodes=None, monitors=None, monitors2=None, thin=1, thin2=1, **_ignored):
+    def __init__(self, model, nodes=None, monitors=None, monitors2=None, thin=1, thin2=1, enableWAIC=False, **_ignored):
         if not isinstance(model, NimbleModel):
             raise TypeError("configureMCMC needs a nimbleModel")
         self.model = model
         self.monitors = [monitors] if isinstance(monitors, str) else list(monitors or [])
         self.monitors2 = [monitors2] if isinstance(monitors2, str) else list(monitors2 or [])
         self.thin, self.thin2 = int(thin), int(thin2)
+        self.enableWAIC = bool(enableWAIC)  # APT:231,329
         # nimble would assign default (non-tempered) samplers here; buildAPT can only use tempered samplers, so
         # like the vignette (:130) users call removeSamplers() and add tempered ones.
         self.samplerConfs = []
@@ -151,7 +153,7 @@ class APT:
 
     def __init__(self, conf, Temps, monitorTmax=True, ULT=1e6, thinPrintTemps=1, nLadders=1, seed=11, ladder0=0,
                  device=0, record=False, fuseLinks=True, lanesPerChain=0, ctaThreads=0, engine=0, rungsPerPass=0, clusterCtas=0,
-                 verbose=False, compileOnly=False, **dots):
+                 verbose=False, compileOnly=False, enableWAIC=False, **dots):
         if isinstance(conf, NimbleModel):  # APT:249-250
             conf = configureMCMC(conf, **dots)
         elif not isinstance(conf, MCMCconf):  # APT:251-253
@@ -205,6 +207,8 @@ class APT:
         o.record_decisions, o.fuse_links, o.lanes_per_chain, o.cta_threads = int(bool(record)), int(bool(fuseLinks)), int(lanesPerChain), int(ctaThreads)
         o.engine, o.rungs_per_pass, o.verbose = int(engine), int(rungsPerPass), int(bool(verbose))
         o.cluster_ctas = int(clusterCtas)
+        self.enableWAIC = bool(enableWAIC) or conf.enableWAIC  # APT:259,329
+        o.enable_waic = int(self.enableWAIC)
         self._temps0 = temps
         self.nTemps = len(temps)
         self.nLadders = int(nLadders)
@@ -218,6 +222,10 @@ class APT:
             check(L.apt_model_compile(self._m, len(temps), C.byref(o), buf, len(buf)))
             self.modulePath = buf.value.decode()
             return
+        if os.environ.get("APTB200_PREBUILD"):  # build tool (tools/prebuild_test_modules.sh): fill the module cache, never run
+            buf = C.create_string_buffer(4096)
+            check(L.apt_model_compile(self._m, len(temps), C.byref(o), buf, len(buf)))
+            raise AptError("APTB200_PREBUILD is set: the module was compiled into the cache and is not run")
         check(L.apt_build(self._m, _dp(temps), len(temps), C.byref(o), C.byref(self._h)))
         self.mvSamples = _Samples(self, APT_SAMPLES, self.monitorNames)
         self.mvSamples2 = _Samples(self, APT_SAMPLES2, self.monitorNames2)
@@ -354,6 +362,22 @@ class APT:
         tot, grp = np.empty(n), np.empty((n, nd))
         check(lib().apt_logprob(self._h, _dp(th), n, _dp(tot), _dp(grp)))
         return tot, grp
+
+    def calculateWAIC(self, nburnin=0, ladder=0, details=False):
+        """cAPT$calculateWAIC(nburnin) (APT_functions.R:593-635), evaluated on the device from mvSamples.
+        ladder = -1 pools the samples of all local ladders.  details=True returns (WAIC, lppd, pWAIC)."""
+        if not self.enableWAIC:  # APT:596-599: prints and returns NaN
+            print("Error: must set enableWAIC = TRUE in buildAPT to use the method calcualteWAIC. See help(buildAPT) and "
+                  "help(buildMCMC) for additional information.")
+            return float("nan")
+        out = np.empty(3)
+        check(lib().apt_waic(self._h, int(nburnin), int(ladder), _dp(out)))
+        if out[0] == -np.inf:  # APT:607-610
+            print("Error: need more than one post burn-in MCMC samples")
+        elif np.isnan(out[0]):  # APT:632
+            print("WAIC was calculated as NaN.  You may need to add monitors to model latent states, in order for a valid "
+                  "WAIC calculation.")
+        return tuple(out) if details else float(out[0])
 
     def setInits(self, theta, ladder=-1):
         th = np.ascontiguousarray(theta, dtype=np.float64)

@@ -29,6 +29,7 @@ struct ModFns {
     int (*set_array)(void*, int, const double*, int64_t, char*, int);
     void (*timing_get)(void*, aptmod_timing*);
     int (*device_ptr)(void*, int, void**, int64_t*, void**);
+    int (*waic)(void*, long long, int, double*, char*, int);
 };
 
 struct apt_engine {
@@ -36,7 +37,7 @@ struct apt_engine {
     void* mod = nullptr;
     ModFns fn{};
     Lowered low;
-    int n_ladders = 1, device = 0;
+    int n_ladders = 1, device = 0, enable_waic = 0;
     // NCCL (lazy)
     void* nccl_dl = nullptr;
     void* comm = nullptr;
@@ -253,6 +254,7 @@ int apt_build(apt_model* m, const double* temps, int n_temps, const apt_build_op
         e->fn.set_array = (decltype(e->fn.set_array))sym("aptmod_set_array");
         e->fn.timing_get = (decltype(e->fn.timing_get))sym("aptmod_timing_get");
         e->fn.device_ptr = (decltype(e->fn.device_ptr))dlsym(e->dl, "aptmod_device_ptr");
+        e->fn.waic = (decltype(e->fn.waic))sym("aptmod_waic");
         aptmod_init in{};
         in.n_ladders = o.n_ladders; in.ladder0 = o.ladder0; in.seed = o.seed; in.device = o.device;
         in.temps = temps; in.n_temps = n_temps; in.ULT = o.ULT; in.monitor_tmax = o.monitorTmax;
@@ -269,7 +271,7 @@ int apt_build(apt_model* m, const double* temps, int n_temps, const apt_build_op
         in.thin_conf = m->spec.thin; in.thin2_conf = m->spec.thin2;
         char err[2048] = {0};
         if (e->fn.create(&in, &e->mod, err, sizeof err)) throw Error(err);
-        e->n_ladders = o.n_ladders; e->device = o.device;
+        e->n_ladders = o.n_ladders; e->device = o.device; e->enable_waic = o.enable_waic;
         // arrays were copied to the device: drop the borrowed pointers
         e->low.arrays.clear();
     } catch (...) {
@@ -351,6 +353,17 @@ int apt_logprob(apt_engine* e, const double* theta, int n, double* out_total, do
         out_total[i] = s;
     }
     if (out_groups) memcpy(out_groups, g.data(), g.size() * sizeof(double));
+    API_END
+}
+
+int apt_waic(apt_engine* e, int64_t nburnin, int ladder, double out[3]) {
+    API_BEGIN
+    if (!e || !out) throw Error("null argument");
+    out[0] = out[1] = out[2] = NAN;
+    if (!e->enable_waic)  // APT:596-599 (the reference prints this and returns NaN)
+        throw Error("must set enableWAIC = TRUE in buildAPT to use the method calcualteWAIC. See help(buildAPT) and help(buildMCMC) for additional information.");
+    char err[2048] = {0};
+    if (e->fn.waic(e->mod, (long long)nburnin, ladder, out, err, sizeof err)) throw Error(err);
     API_END
 }
 

@@ -13,6 +13,7 @@
 #include "apt_engine.cuh"
 #include "apt_grid.cuh"
 #include "apt_module_abi.h"
+#include "apt_waic.cuh"
 
 namespace apt {
 
@@ -118,6 +119,7 @@ struct Engine {
     DevBuf<int> recswap;
     long long cap = 0, cap2 = 0, ttcap = 0, rows = 0, rows2 = 0, ttrows = 0, rec_iters = 0;
     long long totalIters = 1;
+    int last_thin = 1;  // thinToUseVec[1] of the last run (APT:351,605)
     uint64_t rngIter = 0;
     bool resetAnyway = true;
     aptmod_timing timing{};
@@ -282,6 +284,7 @@ struct Engine {
         int thin = ra->thin != -1 ? ra->thin : thin_conf;               // APT:351-353
         int thin2 = ra->thin2 != -1 ? ra->thin2 : thin2_conf;
         if (thin < 1 || thin2 < 1) throw ApiError{"thin and thin2 must be >= 1"};
+        last_thin = thin;
         bool reset = ra->reset != 0, resetTempering = ra->resetTempering != 0;
         if (resetAnyway) {  // APT:358-363
             reset = true; resetTempering = true; resetAnyway = false; totalIters = 1;
@@ -496,6 +499,38 @@ struct Engine {
         APT_CUDA(cudaStreamSynchronize(stream));
     }
 
+    // calculateWAIC (APT:593-635): out3 = {WAIC, logAvgProb, pWAIC}
+    void waic(long long nburnin, int ladder, double* out3) {
+        APT_CUDA(cudaSetDevice(device));
+        if (ladder >= L) throw ApiError{"ladder index out of range"};
+        if constexpr (G::NDATA == 0) throw ApiError{"WAIC cannot be calculated, as no data nodes were detected in the model."};  // APT:331
+        else if constexpr ((size_t)WaicShape<G>::S * P * 8 > 48 * 1024) throw ApiError{"calculateWAIC: too many parameters for the shared-memory staging of the device kernel"};
+        else {
+            if (nburnin < 0) nburnin = 0;
+            const long long nb = (nburnin + last_thin - 1) / last_thin;  // nburninPostThinning, APT:605
+            const long long n = rows - nb;                              // numMCMCSamples, APT:606
+            out3[1] = out3[2] = std::nan("");
+            if (n < 2) { out3[0] = -INFINITY; return; }               // APT:607-610
+            DevBuf<double> res;
+            res.alloc((size_t)2 * G::NDATA);
+            const unsigned grid = (unsigned)((G::NDATA + WAIC_THREADS - 1) / WAIC_THREADS);
+            APT_CUDA(cudaEventRecord(ev0, stream));
+            waic_kernel<G><<<grid, WAIC_THREADS, 0, stream>>>(D, samples.p, cap, nb, n, ladder < 0 ? 0 : ladder, ladder < 0 ? L : 1,
+                                                            model_theta.p, res.p);
+            APT_CUDA(cudaGetLastError());
+            APT_CUDA(cudaEventRecord(ev1, stream));
+            auto v = d2h(res.p, (size_t)2 * G::NDATA);
+            float ms = 0;
+            APT_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
+            waic_ms = ms;
+            launches_total++;
+            double lavg = 0, pw = 0;  // APT:623-629: summed in data-node order
+            for (long j = 0; j < G::NDATA; j++) { lavg += v[(size_t)j]; pw += v[(size_t)G::NDATA + j]; }
+            out3[0] = -2 * (lavg - pw); out3[1] = lavg; out3[2] = pw;   // APT:630
+        }
+    }
+    double waic_ms = 0;
+
     // device-resident, compact [L][rows][cols] view of a trace for collectives (NCCL all-gather); no host staging
     DevBuf<double> compact;
     void device_ptr(int what, void** ptr, int64_t* n, void** strm) {
@@ -706,6 +741,10 @@ inline void set_err(char* err, int errlen, const std::string& m) {
     APT_EXPORT int aptmod_set_array(void* h, int idx, const double* v, int64_t n, char* err, int errlen) {                     \
         APT_GUARD(static_cast<apt::Engine<G>*>(h)->set_array(idx, v, n))                                            \
     }                                                                                                               \
+    APT_EXPORT int aptmod_waic(void* h, long long nburnin, int ladder, double* out3, char* err, int errlen) {                  \
+        APT_GUARD(static_cast<apt::Engine<G>*>(h)->waic(nburnin, ladder, out3))                                     \
+    }                                                                                                               \
+    APT_EXPORT double aptmod_waic_ms(void* h) { return static_cast<apt::Engine<G>*>(h)->waic_ms; }                             \
     APT_EXPORT void aptmod_timing_get(void* h, aptmod_timing* t) { *t = static_cast<apt::Engine<G>*>(h)->timing; }             \
     APT_EXPORT int aptmod_device_ptr(void* h, int what, void** ptr, int64_t* n, void** strm) {                                 \
         try { static_cast<apt::Engine<G>*>(h)->device_ptr(what, ptr, n, strm); return 0; } catch (...) { return 1; }            \

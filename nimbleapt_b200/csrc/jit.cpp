@@ -55,7 +55,7 @@ std::string jit_compile(const std::string& source, bool verbose) {
     const std::string extra = getenv("APTB200_EXTRA_NVCC_FLAGS") ? std::string(" ") + getenv("APTB200_EXTRA_NVCC_FLAGS") : std::string();
     const std::string flags = extra + " -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xcompiler -fvisibility=hidden -Xcompiler -fno-gnu-unique -diag-suppress 177 -shared";
     uint64_t h = fnv1a(source);
-    for (const char* hdr : {"apt_engine.cuh", "apt_host.cuh", "apt_dists.cuh", "apt_module_abi.h", "apt_sferr_table.cuh", "apt_grid.cuh", "apt_softplus.cuh", "apt_softplus_tables.h"}) {
+    for (const char* hdr : {"apt_engine.cuh", "apt_host.cuh", "apt_dists.cuh", "apt_module_abi.h", "apt_sferr_table.cuh", "apt_grid.cuh", "apt_softplus.cuh", "apt_softplus_tables.h", "apt_waic.cuh"}) {
         std::string txt = slurp(inc + "/" + hdr);
         h = fnv1a(txt, h);
     }

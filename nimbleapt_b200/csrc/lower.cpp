@@ -1579,6 +1579,70 @@ struct Lowerer {
         smem_state = bytes <= 96 * 1024 || (teams == 1 && bytes <= 200 * 1024 && tiles * W >= 256);
     }
 
+    // buildAPT with enableWAIC (APT:322-333): there must be data nodes, and every parameter of a data node must be monitored
+    // or be downstream of monitored nodes (mcmc_checkWAICmonitors, APT:1313-1341; variable-level like the reference).
+    // Deterministic nodes are inlined here, so "stochastic dependents of a variable" are the declarations that read it.
+    void check_waic_monitors(const std::vector<int>& mon) {
+        bool any_data = false;
+        for (int di : stoch_decls) any_data |= vars.at(decls[di].lhs->name).role == Var::DATA;
+        if (!any_data) throw Error("WAIC cannot be calculated, as no data nodes were detected in the model.");  // APT:331
+        std::set<std::string> monv, top, visited;
+        for (int c : mon)
+            if (c >= 0)
+                for (auto& n : param_order) {
+                    const Var& v = vars.at(n);
+                    if (c >= v.theta_off && c < v.theta_off + v.size) monv.insert(n);
+                }
+        // parents of each stochastic declaration: PARAM variables it reads (patterns that are not its own left-hand side)
+        auto parents = [&](int di) {
+            std::set<std::string> ps;
+            for (auto& p : patterns[di])
+                if (!p.own) ps.insert(p.v->name);
+            return ps;
+        };
+        for (auto& n : param_order) top.insert(n);
+        for (int di : stoch_decls)
+            if (decls[di].lhs_param && !parents(di).empty()) top.erase(decls[di].lhs->name);
+        std::set<std::string> cur;
+        for (auto& n : top)
+            if (!monv.count(n)) cur.insert(n);
+        while (!cur.empty()) {
+            visited.insert(cur.begin(), cur.end());
+            std::set<std::string> next, bad;
+            for (int di : stoch_decls) {
+                bool dep = false;
+                for (auto& pn : parents(di)) dep |= cur.count(pn) != 0;
+                if (!dep) continue;
+                const Var& lv = vars.at(decls[di].lhs->name);
+                if (lv.role == Var::DATA) bad.insert(lv.name);
+                else if (!monv.count(lv.name) && !visited.count(lv.name)) next.insert(lv.name);
+            }
+            if (!bad.empty()) {
+                std::string l;
+                for (auto& b : bad) l += (l.empty() ? "" : ", ") + b;
+                throw Error("In order for a valid WAIC calculation, all parameters of data nodes in the model must be monitored, or be"
+                            " downstream from monitored nodes. See help(buildMCMC) for more information on valid sets of monitored nodes"
+                            " for WAIC calculations.\n Currently, the following data nodes have un-monitored upstream parameters:\n " + l);
+            }
+            cur = next;
+        }
+        // model$simulate(paramDeps) (APT:327,618) would draw every unmonitored stochastic node downstream of a monitored one
+        // from its conditional prior; the device engine does not simulate, so such a configuration is refused
+        std::set<std::string> down;
+        for (bool grew = true; grew;) {
+            grew = false;
+            for (int di : stoch_decls) {
+                const std::string& ln = decls[di].lhs->name;
+                if (!decls[di].lhs_param || monv.count(ln) || down.count(ln)) continue;
+                for (auto& pn : parents(di))
+                    if (monv.count(pn) || down.count(pn)) { down.insert(ln); grew = true; break; }
+            }
+        }
+        if (!down.empty())
+            throw Error("calculateWAIC: the unmonitored node '" + *down.begin() + "' is downstream of monitored nodes; the reference would"
+                        " simulate it from its prior for every sample (APT:618), which the device engine does not do. Monitor it.");
+    }
+
     Lowered run() {
         canonicalise();
         build_vars();
@@ -1589,14 +1653,52 @@ struct Lowerer {
         std::vector<int> mon, mon2;
         auto names = theta_names();
         std::vector<std::string> mon_names, mon2_names;
+        // node ids of the logProb monitors: stochastic declarations in model order, instances in loop order
+        std::vector<long> lp_node_off;
+        long n_lp_nodes = 0;
+        for (int di : stoch_decls) { lp_node_off.push_back(n_lp_nodes); n_lp_nodes += decls[di].ninst; }
+        auto expand_logprob = [&](const std::string& m, std::vector<int>& dst, std::vector<std::string>& dn) {
+            // "logProb_y", "logProb_y[3]", "logProb_y[2:5]" (nimble's logProb_<var> model variables)
+            EP e = parse_expr_text(m.substr(8));
+            if (e->k != Expr::VAR) throw Error("cannot parse monitor '" + m + "'");
+            auto it = vars.find(e->name);
+            if (it == vars.end() || (it->second.role != Var::PARAM && it->second.role != Var::DATA))
+                throw Error("logProb monitor of '" + e->name + "', which is not a stochastic node");
+            const Var& v = it->second;
+            std::vector<int64_t> want, els;
+            ref_elements(v, e, {}, want);
+            std::set<int64_t> ws(want.begin(), want.end());
+            std::map<std::string, double> env;
+            int found = 0;
+            for (size_t q = 0; q < stoch_decls.size(); q++) {
+                const CDecl& d = decls[stoch_decls[q]];
+                if (d.lhs->name != e->name) continue;
+                for (long inst = 0; inst < d.ninst; inst++) {
+                    inst_env(d, inst, env);
+                    ref_elements(v, d.lhs, env, els);
+                    if (els.empty() || !ws.count(els[0])) continue;  // a multivariate node is named by its first element
+                    dst.push_back(-1 - (int)(lp_node_off[q] + inst));
+                    std::string nm = "logProb_" + v.name;
+                    if (!v.dims.empty()) {
+                        nm += "[" + std::to_string(els[0] % v.dims[0] + 1);
+                        if (v.dims.size() > 1) nm += ", " + std::to_string(els[0] / v.dims[0] + 1);
+                        nm += "]";
+                    }
+                    dn.push_back(nm);
+                    found++;
+                }
+            }
+            if (!found) throw Error("monitor '" + m + "' matches no stochastic node");
+        };
         auto expand_mon = [&](const std::vector<std::string>& src, std::vector<int>& dst, std::vector<std::string>& dn) {
             for (auto& m : src) {
-                if (m.find("logProb") != std::string::npos) throw Error("logProb monitors are not supported by the device engine: " + m);
+                if (m.rfind("logProb_", 0) == 0) { expand_logprob(m, dst, dn); continue; }
                 for (int t : expand_target(m)) { dst.push_back(t); dn.push_back(names[(size_t)t]); }
             }
         };
         expand_mon(spec.monitors, mon, mon_names);
         expand_mon(spec.monitors2, mon2, mon2_names);
+        if (opts.enable_waic) check_waic_monitors(mon);
         int DMAX = 1;
         bool has_family = false;
         for (auto& u : units) {
@@ -1684,6 +1786,28 @@ struct Lowerer {
         std::ostringstream body;
         std::swap(out, body);  // emit model body first to learn which arrays are used
         emit_lp_functions();
+        // log-probability of one stochastic node by id (logProb monitors; evaluated only when a row is written)
+        out << "  __device__ static double lp_node(const Data& D, const double* th, int id) {\n";
+        {
+            long off = 0;
+            for (int di : stoch_decls) {
+                out << "    if (id < " << off + decls[di].ninst << ") return " << lp_call(di, "(id - " + std::to_string(off) + ")") << ";\n";
+                off += decls[di].ninst;
+            }
+        }
+        out << "    return CUDART_NAN;\n  }\n";
+        // data nodes (model$getNodeNames(dataOnly = TRUE), APT:323) for calculateWAIC: node j of the walk -> its log-density
+        {
+            long ndata = 0;
+            std::ostringstream fn;
+            for (int di : stoch_decls) {
+                if (vars.at(decls[di].lhs->name).role != Var::DATA) continue;
+                fn << "    if (j < " << ndata + decls[di].ninst << "L) return " << lp_call(di, "(int)(j - " + std::to_string(ndata) + "L)") << ";\n";
+                ndata += decls[di].ninst;
+            }
+            out << "  static constexpr long NDATA = " << ndata << ";\n";
+            out << "  __device__ static __forceinline__ double lp_data(const Data& D, const double* th, long j) {\n" << fn.str() << "    return CUDART_NAN;\n  }\n";
+        }
         out << "  template <class C> __device__ static __forceinline__ void logprob_all(const Data& D, const double* th, const C& c, double* acc) {\n";
         for (int di : stoch_decls) {
             out << "  ";
@@ -1779,6 +1903,12 @@ struct Lowerer {
         out << "struct Model {\n";
         out << "  static constexpr int P = " << P << ", ND = " << ND << ", NU = " << NU << ", NSAMP = " << units.size() << ", K = " << K
             << ", NMON = " << mon.size() << ", NMON2 = " << mon2.size() << ", DMAX = " << DMAX << ", W = " << W << ";\n";
+        {
+            bool lpmon = false;
+            for (int c : mon) lpmon |= c < 0;
+            for (int c : mon2) lpmon |= c < 0;
+            out << "  static constexpr bool HAS_LP_MON = " << (lpmon ? "true" : "false") << ";\n";
+        }
         out << "  static constexpr int NARR = " << used_arrays.size() << ", NIARR = " << iarrays.size() << ", BLKSZ = " << BLKSZ << ", EMPSZ = " << EMPSZ << ";\n";
         out << "  static constexpr int TILES_PER_LADDER = " << tiles << ", TEAMS_PER_CTA = " << teams << ", CLUSTER = " << (engine == 1 ? cluster : 1) << ";\n";
         {

@@ -944,6 +944,48 @@ int orc_ladders_run(orc_ladder** Ls, int n, int nthreads, long niter, int reset,
     return job.rc;
 }
 
+/* calculateWAIC  (APT:593-635).  data_lp[ndata]: logProb-arena indices of the data nodes (dataNodes, APT:323);
+   nburnin_post = ceiling(nburnin / thin) is formed by the caller (APT:605).  Returns WAIC; out3 = {WAIC, logAvgProb,
+   pWAIC}.  Fewer than 2 post-burn-in samples: -Inf (APT:607-610). */
+double orc_ladder_waic(const orc_ladder* L, long nburnin_post, int ndata, const int* data_lp, double* out3) {
+    const orc_model* m = L->m;
+    const long n = L->nrows - nburnin_post; /* numMCMCSamples, APT:606 */
+    if (n < 2) return -INFINITY;
+    double* lpp = (double*)malloc(sizeof(double) * (size_t)n * ndata); /* logPredProbs, APT:611 */
+    orc_ctx c;
+    c.m = m;
+    c.mut = (double*)malloc(sizeof(double) * (m->nmut + 1));
+    c.lp = (double*)calloc(m->nlp + 1, sizeof(double));
+    for (long i = 0; i < n; i++) {
+        /* copy(mvSamples, model, nodesTo = sampledNodes, row = i + nburninPostThinning): unmonitored nodes keep the
+           model's current values (APT:614,617); simulate(paramDeps) + calculate(dataNodes) (APT:618-619) */
+        memcpy(c.mut, L->model.mut, sizeof(double) * m->nmut);
+        const double* row = &L->samples[(size_t)(i + nburnin_post) * L->nmon];
+        for (int q = 0; q < L->nmon; q++)
+            if (L->mon[q] >= 0) c.mut[L->mon[q]] = row[q];
+        calculate_all(&c);
+        for (int j = 0; j < ndata; j++) lpp[(size_t)i * ndata + j] = c.lp[data_lp[j]];
+    }
+    double logAvgProb = 0, pWAIC = 0;
+    for (int j = 0; j < ndata; j++) { /* APT:623-629 */
+        double mx = -INFINITY;
+        for (long i = 0; i < n; i++) { double v = lpp[(size_t)i * ndata + j]; if (v > mx || v != v) mx = v; }
+        long double se = 0, sm = 0;
+        for (long i = 0; i < n; i++) { se += exp(lpp[(size_t)i * ndata + j] - mx); sm += lpp[(size_t)i * ndata + j]; }
+        logAvgProb += mx + log((double)(se / n));
+        long double mean = sm / n, r = 0; /* R's mean(): a second pass refines the first */
+        for (long i = 0; i < n; i++) r += lpp[(size_t)i * ndata + j] - mean;
+        mean += r / n;
+        long double sv = 0;
+        for (long i = 0; i < n; i++) { long double d = lpp[(size_t)i * ndata + j] - mean; sv += d * d; }
+        pWAIC += (double)(sv / (n - 1)); /* var() */
+    }
+    free(lpp); free(c.mut); free(c.lp);
+    const double WAIC = -2 * (logAvgProb - pWAIC); /* APT:630 */
+    if (out3) { out3[0] = WAIC; out3[1] = logAvgProb; out3[2] = pWAIC; }
+    return WAIC;
+}
+
 /* ------------------------------------------------------------------ accessors */
 long orc_ladder_nrows(const orc_ladder* L, int which) { return which == 2 ? L->nrows2 : which == 3 ? L->ttrows : L->nrows; }
 const double* orc_ladder_ptr(const orc_ladder* L, int what) {

@@ -669,9 +669,101 @@ class OracleModel:
                     return d["dist"] in DISCRETE_DISTS
         raise KeyError("target has no stochastic declaration")
 
+    def data_node_lp_indices(self):
+        """dataNodes <- model$getNodeNames(dataOnly = TRUE) (APT_functions.R:323) as indices into the C oracle's
+        logProb arena (stochastic declarations in topological order, instances in loop order)."""
+        out, off = [], 0
+        for d in self.cdecls:
+            if not d["stoch"]:
+                continue
+            env, n = self._inst_env(d)
+            if self.vars[d["lhs"][1]].role == "data":
+                out += list(range(off, off + n))
+            off += n
+        return out
+
+    def check_waic_monitors(self, monitors):
+        """mcmc_checkWAICmonitors (APT_functions.R:1313-1341): every parameter of a data node must be monitored or
+        be downstream of monitored nodes.  Variable-level, like the reference."""
+        mon = {_parse_expr(m)[1] for m in monitors if not m.startswith("logProb_")}
+        stoch = [d for d in self.cdecls if d["stoch"]]
+
+        def parents(d):  # stochastic parent variables of a declaration, through deterministic nodes
+            seen, todo, out = set(), [d], set()
+            while todo:
+                q = todo.pop()
+                for a in q["args"]:
+                    for r in self._reads(a, []):
+                        rv = self.vars[r[1]]
+                        if rv.role == "param":
+                            out.add(rv.name)
+                        elif rv.role == "det" and rv.name not in seen:
+                            seen.add(rv.name)
+                            todo += [x for x in self.cdecls if not x["stoch"] and x["lhs"][1] == rv.name]
+            return out
+
+        par = [(d, parents(d)) for d in stoch]
+        top = {d["lhs"][1] for d, p in par if not p and self.vars[d["lhs"][1]].role == "param"}
+        this = {v for v in top if v not in mon}
+        visited = set()
+        while this:
+            visited |= this
+            nxt = [d for d, p in par if p & this]
+            bad = sorted({d["lhs"][1] for d in nxt if self.vars[d["lhs"][1]].role == "data"})
+            if bad:
+                raise ValueError("In order for a valid WAIC calculation, all parameters of data nodes in the model must be "
+                                 "monitored, or be downstream from monitored nodes. Currently, the following data nodes have "
+                                 "un-monitored upstream parameters: " + ", ".join(bad))
+            this = {d["lhs"][1] for d in nxt} - mon - visited
+        # model$simulate(paramDeps) (APT_functions.R:327,618) would draw unmonitored stochastic nodes downstream of
+        # monitored ones from their prior: not restated (the engine refuses the configuration as well)
+        down, grew = set(), True
+        while grew:
+            grew = False
+            for d, p in par:
+                ln = d["lhs"][1]
+                if self.vars[ln].role != "param" or ln in mon or ln in down:
+                    continue
+                if p & (mon | down):
+                    down.add(ln); grew = True
+        if down:
+            raise NotImplementedError("unmonitored node %s is downstream of monitored nodes" % sorted(down)[0])
+
+    def _logprob_monitor(self, nm):
+        """'logProb_y' | 'logProb_y[3]' | 'logProb_y[2:5]' -> codes -(lp index)-1 in the C oracle's logProb arena
+        (stochastic declarations in topological order, instances in loop order) and column labels."""
+        t = _parse_expr(nm[len("logProb_"):])
+        v = self.vars[t[1]]
+        base, cnt, stride = self._elem_index(t, {}, 1)
+        want = set(range(v.size)) if not t[2] else {int(base[0]) + e * stride for e in range(cnt)}
+        out, labels, off = [], [], 0
+        for d in self.cdecls:
+            if not d["stoch"]:
+                continue
+            env, n = self._inst_env(d)
+            if d["lhs"][1] == t[1]:
+                b, c, s = self.lhs_elements(d, env, n)
+                for inst in range(n):
+                    e0 = int(b[inst])  # a multivariate node is named by its first element
+                    if e0 in want:
+                        out.append(-(off + inst) - 1)
+                        if not v.dims:
+                            labels.append("logProb_" + v.name)
+                        elif len(v.dims) == 1:
+                            labels.append("logProb_%s[%d]" % (v.name, e0 + 1))
+                        else:
+                            labels.append("logProb_%s[%d, %d]" % (v.name, e0 % v.dims[0] + 1, e0 // v.dims[0] + 1))
+            off += n
+        assert out, "monitor %s matches no stochastic node" % nm
+        return out, labels
+
     def monitor_indices(self, names):
         out, labels = [], []
         for nm in names:
+            if nm.startswith("logProb_"):  # nimble's logProb_<var> model variables (demo/APT_demo.R:180-181)
+                o, l = self._logprob_monitor(nm)
+                out += o; labels += l
+                continue
             t = _parse_expr(nm)
             v = self.vars[t[1]]
             idxs = self.expand_target(nm)

@@ -5,6 +5,7 @@ __graft_entry__.smoke() and bench.py's cpu_baseline / `--impl reference` legs â€
 package `nimbleapt_b200`.
 """
 import ctypes as C
+import math
 import os
 import subprocess
 import numpy as np
@@ -61,6 +62,8 @@ def lib():
         L.orc_ladder_propcov.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.orc_ladder_total_iters.restype = C.c_long
         L.orc_ladder_total_iters.argtypes = [C.c_void_p]
+        L.orc_ladder_waic.restype = C.c_double
+        L.orc_ladder_waic.argtypes = [C.c_void_p, C.c_long, C.c_int, ip, dp]
         for f in ("apt_dnorm_log", "apt_dunif_log", "apt_dgamma_log", "apt_dbeta_log", "apt_dbinom_log"):
             getattr(L, f).restype = C.c_double
             getattr(L, f).argtypes = [C.c_double] * 3
@@ -159,6 +162,7 @@ class OracleAPT:
                            sp["lower"], sp["upper"])
             if sp["kind"] == 2:
                 L.orc_spec_set_slice(self.specs, i, int(ctl.get("sliceMaxSteps", 100)), int(om.is_discrete(sp["tgt"][0])))
+        self.monitors = list(monitors)
         self.mon, self.mon_labels = om.monitor_indices(list(monitors))
         self.mon2, self.mon2_labels = om.monitor_indices(list(monitors2))
         m1, m1p = _ia(self.mon if self.mon else [0]); m2, m2p = _ia(self.mon2 if self.mon2 else [0])
@@ -262,6 +266,19 @@ class OracleAPT:
     def propCov(self, ladder, tt, s, d):
         p = lib().orc_ladder_propcov(self.ladders[ladder], tt, s)
         return np.ctypeslib.as_array(p, shape=(d * d,)).copy().reshape(d, d, order="F")
+
+    def calculateWAIC(self, nburnin=0, ladder=0, thin=1):
+        """calculateWAIC (APT_functions.R:593-635) on the rung-1 samples of one ladder; `thin` is the thinning
+        interval of the run that produced them (thinToUseVec[1], APT_functions.R:605).  Returns (WAIC, lppd, pWAIC)."""
+        idx = self.om.data_node_lp_indices()
+        if not idx:  # APT_functions.R:331
+            raise ValueError("WAIC cannot be calculated, as no data nodes were detected in the model.")
+        self.om.check_waic_monitors(self.monitors)
+        a, ap = _ia(idx)
+        out = np.zeros(3)
+        w = lib().orc_ladder_waic(self.ladders[ladder], int(math.ceil(nburnin / thin)), len(idx), ap,
+                                  out.ctypes.data_as(C.POINTER(C.c_double)))
+        return (w, out[1], out[2]) if np.isfinite(w) or w != w else (w, float("nan"), float("nan"))
 
     def logprob(self, theta):
         """Whole-model log probability at PARAM vector theta; returns (total, per-declaration sums)."""

@@ -175,7 +175,9 @@ def demo_wrong(N=50, K=10, nTemps=7):
                           dict(target="sigma0", type="sampler_RW_tempered", control=tp),
                           dict(target="k", type="sampler_slice_tempered", control=tp),
                           dict(target=["theta0", "sigma0"], type="sampler_RW_block_tempered", control=tp)],
-                monitors=["k", "theta0", "sigma0"], Temps=np.arange(1, nTemps + 1, dtype=float), ULT=1e6)
+                monitors=["k", "theta0", "sigma0"],
+                monitors2=["logProb_k", "logProb_theta0", "logProb_sigma0", "logProb_y"],  # addMonitors2(allLogProbs), demo:180-181
+                Temps=np.arange(1, nTemps + 1, dtype=float), ULT=1e6)
 
 
 def demo_wrong_k_posterior(spec):

@@ -89,6 +89,9 @@ def test_decisions_bit_identical(name, inject):
         np.testing.assert_allclose(eng.TempsLadder(l), orc.Temps(l), rtol=1e-9)
         np.testing.assert_allclose(eng.mvSamples.matrix(l), orc.samples(l), rtol=1e-8, atol=1e-10)
         np.testing.assert_allclose(eng.mvSamplesTmax.matrix(l), orc.samplesTmax(l), rtol=1e-8, atol=1e-10)
+        if spec.get("monitors2"):  # logProb_* monitors of the demo model: per-node log-probabilities of the saved state
+            assert eng.monitorNames2 == orc.mon2_labels
+            np.testing.assert_allclose(eng.mvSamples2.matrix(l), orc.samples2(l), rtol=1e-9, atol=1e-9)
         np.testing.assert_allclose(eng.logProbsLadder(l), orc.logProbs(l), rtol=1e-10)
         np.testing.assert_allclose(eng.tempTrajLadder(l), orc.tempTraj(l), rtol=1e-9)
         np.testing.assert_array_equal(eng.accCountSwapLadder(l), orc.accCountSwap(l))
