@@ -9,9 +9,9 @@
  *   nimbleCode({...}) / nimbleModel(code, constants, data, inits)   apt_model_create + apt_model_set_array
  *     (vignettes/nimbleAPT-vignette.Rmd:56-72)
  *   conf$addSampler(target, type = "sampler_RW_tempered" |          apt_model_add_sampler
- *     "sampler_RW_block_tempered" | "sampler_slice_tempered",
- *     control = list(...))
- *     (APT:649-660, APT:770-781, APT:898-912; vignette:131-132; demo/APT_demo.R:174-177)
+ *     "sampler_RW_block_tempered" | "sampler_slice_tempered" |
+ *     "sampler_RW_multinomial_tempered", control = list(...))
+ *     (APT:649-660, APT:770-781, APT:898-912, APT:1005-1019; vignette:131-132; demo/APT_demo.R:174-177)
  *   configureMCMC(model, monitors =, thin =) monitors/thin           apt_model_set_monitors / apt_model_set_thin
  *     (APT:302-311)
  *   buildAPT(conf, Temps, monitorTmax, ULT, thinPrintTemps)          apt_build        (lowering + nvcc + device state)
@@ -42,6 +42,12 @@
  *     (j = 0: rexp(1) = -log U; 1: offset of the initial interval; 2: maxStepsL; 3: first x1; 4, 5, ...: shrinkage
  *     draws), is read from block j / 2 as U(w0,w1) for even j and U(w2,w3) for odd j.  Injected tables are not
  *     consulted by this sampler.
+ *   sampler_RW_multinomial_tempered (APT:1054-1098): sub-proposal q (0-based, in the order of the two loops APT:1055-1056)
+ *     reads block q: U(w0,w1) is inverted by rbinom (the smallest k with U <= P(X <= k), pmf walked from 0 by its
+ *     recurrence; for prob > 0.5 the walk runs on size - X ~ Binom(size, 1 - prob) and size minus its quantile is
+ *     returned; size <= 1000; R's rbinom consumes a data-dependent number of sequential draws),
+ *     U(w2,w3) is the acceptance uniform.  The recycled u (APT:1040) is pi * U(w0,w1) of block 0x7FFF, drawn at the
+ *     sampler's first update.  Injected tables are not consulted by this sampler.
  *   swap proposal ii (0-based) of the iteration: unit = 0xFFFFFFFF, rung field = ii, block 0:
  *     rcat uniform U(w0,w1), acceptance uniform U(w2,w3)
  *   U(hi,lo) = ((hi >> 6) * 2^26 + (lo >> 6) + 0.5) * 2^-52: 52 random bits, strictly inside (0,1).
@@ -76,6 +82,7 @@ typedef struct {
     int propCov_dim;            /* d of the matrix passed in propCov (checked against the target, APT:816) */
     double width;               /* control$width          (slice sampler only, APT:911)  default 1   */
     int sliceMaxSteps;          /* control$sliceMaxSteps  (slice sampler only, APT:912)  default 100 */
+    int useTempering;           /* control$useTempering   (multinomial sampler only): -1 = unspecified -> error (APT:1015) */
 } apt_sampler_control;
 
 typedef struct {
@@ -142,8 +149,11 @@ enum {
     APT_LOGPROBTEMPS = 8,   /* logProbTemps   [nTemps]                                   APT:447 */
     APT_RUNG_STATES = 9,    /* mvTemps        [nTemps][n_params]                         APT:272 */
     APT_SCALES = 10,        /* sampler scale (slice sampler: width)  [nTemps][n_sampler_units]  APT:743,859,982 */
-    APT_BLOCK_STATE = 11,   /* per rung, per block sampler: propCov, chol, scale*chol (d*d each, column-major) */
-    APT_DECISIONS = 12,     /* test hook [niter][nTemps][n_sampler_units] 0/1 (slice sampler: log-probability evaluations of the update mod 256) */
+    APT_BLOCK_STATE = 11,   /* per rung, per block sampler: propCov, chol, scale*chol (d*d each, column-major); slice sampler: sumJumps;
+                               multinomial sampler: u, then timesRan, AcceptRates, ScaleShifts, totalAdapted, timesAccepted,
+                               ENSwapMatrix, ENSwapDeltaMatrix, RescaleThreshold (d*d each, column-major [iFrom, iTo]) */
+    APT_DECISIONS = 12,     /* test hook [niter][nTemps][n_sampler_units] 0/1 (slice sampler: log-probability evaluations of the update mod 256;
+                               multinomial sampler: accepted sub-proposals of the update) */
     APT_SWAP_RECORD = 13,   /* test hook [niter][nTemps]  iTo | accepted << 16 */
     APT_MODEL_STATE = 14    /* the model's parameter values after run (rung 1)           APT:548 */
 };
@@ -166,7 +176,7 @@ void apt_build_opts_default(apt_build_opts* o);
 void apt_run_args_default(apt_run_args* a);
 
 /* ---- model + configuration (replaces nimbleCode/nimbleModel/configureMCMC for the supported BUGS subset:
- *      dnorm dunif dgamma dbeta dbinom dbern dpois dexp dcat dmnorm(cholesky=), deterministic links,
+ *      dnorm dunif dgamma dbeta dbinom dbern dpois dexp dcat dmulti dmnorm(cholesky=), deterministic links,
  *      elements of constant arrays selected by a sampled node, e.g. rfx[k]) */
 int apt_model_create(const char* bugs_code, apt_model** out);
 void apt_model_free(apt_model* m);

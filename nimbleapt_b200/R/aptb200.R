@@ -2,20 +2,22 @@
 ##
 ## NOT exercised in this image (no R, no nimble: SURVEY.md F7).  It mirrors, name for name, what a user of the
 ## reference touches (nimbleAPT/NAMESPACE:3-9; vignette :127-141):
-##   conf$addSampler(target, type = "sampler_RW_tempered" | "sampler_RW_block_tempered", control = list(...))
+##   conf$addSampler(target, type = "sampler_RW_tempered" | "sampler_RW_block_tempered" | "sampler_slice_tempered" |
+##                   "sampler_RW_multinomial_tempered", control = list(...))
 ##   buildAPT(conf, Temps, monitorTmax = TRUE, ULT = 1E6, thinPrintTemps = 1, ...)      APT_functions.R:242-248
 ##   cAPT$run(niter, reset, resetMV, resetTempering, simulateAll, time, adaptTemps, printTemps, tuneTemper1,
 ##            tuneTemper2, progressBar, thin, thin2)                                      APT_functions.R:336-348
 ##   as.matrix(cAPT$mvSamples), cAPT$logProbs, cAPT$tempTraj, cAPT$accCountSwap, cAPT$Temps
 ##   cAPT$calculateWAIC(nburnin)                                                         APT_functions.R:593-635
 ##   runAPT(cAPT, niter, thin, ...)   (named by the north star; not present in the reference, SURVEY.md F5)
-## The two sampler names are *recording* samplers: they capture target + control and never run in R.
+## The sampler names are *recording* samplers: they capture target + control and never run in R.
 
 .aptb200 <- new.env()
 
 sampler_RW_tempered       <- structure(list(name = "sampler_RW_tempered"),       class = "aptb200_sampler_type")
 sampler_RW_block_tempered <- structure(list(name = "sampler_RW_block_tempered"), class = "aptb200_sampler_type")
 sampler_slice_tempered    <- structure(list(name = "sampler_slice_tempered"),    class = "aptb200_sampler_type")
+sampler_RW_multinomial_tempered <- structure(list(name = "sampler_RW_multinomial_tempered"), class = "aptb200_sampler_type")
 
 ## Works with a nimble MCMCconf (conf$samplerConfs[[i]]$target / $name / $control, conf$monitors, conf$thin, conf$model)
 ## or with a plain list(model = list(code =, constants =, data =, inits =), samplers = list(...), monitors =, thin =).
@@ -46,7 +48,9 @@ buildAPT <- function(conf, Temps, monitorTmax = TRUE, ULT = 1E6, thinPrintTemps 
     for (nm in names(data))      .Call("aptR_model_set_array", m, nm, 1L, data[[nm]])
     for (nm in names(inits))     .Call("aptR_model_set_array", m, nm, 2L, inits[[nm]])
     for (s in samplers) {
-        if (is.null(s$control$temperPriors) && !grepl("slice", s$type))                  # APT:660, APT:781 (not read by the slice sampler, APT:909-912)
+        if (grepl("multinomial", s$type)) {
+            if (is.null(s$control$useTempering)) stop("control$useTempering unspecified in sampler_RW_multinomial_tempered")  # APT:1015
+        } else if (is.null(s$control$temperPriors) && !grepl("slice", s$type))           # APT:660, APT:781 (not read by the slice sampler, APT:909-912)
             stop(paste0("control$temperPriors unspecified in ", s$type))
         .Call("aptR_model_add_sampler", m, s$target, s$type, s$control)
     }

@@ -61,6 +61,7 @@ SEXP aptR_model_add_sampler(SEXP p, SEXP target, SEXP type, SEXP control) {
     if ((v = list_get(control, "temperPriors")) != R_NilValue) c.temperPriors = Rf_asLogical(v);
     if ((v = list_get(control, "width")) != R_NilValue) c.width = Rf_asReal(v);                    /* APT:911 */
     if ((v = list_get(control, "sliceMaxSteps")) != R_NilValue) c.sliceMaxSteps = Rf_asInteger(v);  /* APT:912 */
+    if ((v = list_get(control, "useTempering")) != R_NilValue) c.useTempering = Rf_asLogical(v);    /* APT:1015 */
     SEXP pc = list_get(control, "propCov");
     int prot = 0;
     if (pc != R_NilValue && Rf_isNumeric(pc)) {

@@ -10,7 +10,7 @@ class SamplerControl(C.Structure):
     _fields_ = [("log", C.c_int), ("reflective", C.c_int), ("adaptive", C.c_int), ("adaptScaleOnly", C.c_int),
                 ("adaptInterval", C.c_int), ("adaptFactorExponent", C.c_double), ("scale", C.c_double),
                 ("temperPriors", C.c_int), ("propCov", C.POINTER(C.c_double)), ("propCov_dim", C.c_int),
-                ("width", C.c_double), ("sliceMaxSteps", C.c_int)]
+                ("width", C.c_double), ("sliceMaxSteps", C.c_int), ("useTempering", C.c_int)]
 
 
 class BuildOpts(C.Structure):

@@ -28,11 +28,13 @@ from . import _lib
 from ._lib import AptError, BuildOpts, RunArgs, SamplerControl, Timing, check, lib
 
 _SAMPLER_TYPES = ("sampler_RW_tempered", "RW_tempered", "sampler_RW_block_tempered", "RW_block_tempered",
-                  "sampler_slice_tempered", "slice_tempered")
+                  "sampler_slice_tempered", "slice_tempered",
+                  "sampler_RW_multinomial_tempered", "RW_multinomial_tempered")
 _SCALAR_KEYS = {"log", "reflective", "adaptive", "adaptInterval", "adaptFactorExponent", "scale", "temperPriors"}
 _BLOCK_KEYS = {"adaptive", "adaptScaleOnly", "adaptInterval", "adaptFactorExponent", "scale", "propCov", "temperPriors"}
 # APT:909-912 (the slice sampler never reads temperPriors; the reference's demo passes it anyway, demo/APT_demo.R:176)
 _SLICE_KEYS = {"adaptive", "adaptInterval", "width", "sliceMaxSteps", "temperPriors"}
+_MULTI_KEYS = {"adaptive", "adaptInterval", "useTempering"}  # APT:1013-1015
 
 (APT_SAMPLES, APT_SAMPLES2, APT_SAMPLES_TMAX, APT_SAMPLES2_TMAX, APT_LOGPROBS, APT_TEMPTRAJ, APT_TEMPS, APT_ACCSWAP,
  APT_LOGPROBTEMPS, APT_RUNG_STATES, APT_SCALES, APT_BLOCK_STATE, APT_DECISIONS, APT_SWAP_RECORD, APT_MODEL_STATE) = range(15)
@@ -90,9 +92,9 @@ class MCMCconf:
         name = getattr(type, "__name__", type)
         if name not in _SAMPLER_TYPES:
             raise ValueError("unsupported sampler type %r (supported: sampler_RW_tempered, sampler_RW_block_tempered, "
-                             "sampler_slice_tempered)" % (name,))
+                             "sampler_slice_tempered, sampler_RW_multinomial_tempered)" % (name,))
         block = "block" in name
-        unknown = set(control) - (_SLICE_KEYS if "slice" in name else _BLOCK_KEYS if block else _SCALAR_KEYS)
+        unknown = set(control) - (_MULTI_KEYS if "multinomial" in name else _SLICE_KEYS if "slice" in name else _BLOCK_KEYS if block else _SCALAR_KEYS)
         if unknown:
             raise ValueError("unknown control option(s) for %s: %s" % (name, ", ".join(sorted(unknown))))
         if isinstance(target, (list, tuple)):
@@ -121,6 +123,10 @@ def sampler_RW_tempered():  # pragma: no cover - marker object
 
 def sampler_RW_block_tempered():  # pragma: no cover - marker object
     raise AptError("sampler_RW_block_tempered is selected by name in conf.addSampler(type=...)")
+
+
+def sampler_RW_multinomial_tempered():  # pragma: no cover - marker object
+    raise AptError("sampler_RW_multinomial_tempered is selected by name in conf.addSampler(type=...)")
 
 
 def sampler_slice_tempered():  # pragma: no cover - marker object
@@ -175,7 +181,7 @@ class APT:
             ctl = SamplerControl()
             L.apt_sampler_control_default(C.byref(ctl))
             c = s["control"]
-            for k in ("log", "reflective", "adaptive", "adaptScaleOnly", "adaptInterval", "temperPriors", "sliceMaxSteps"):
+            for k in ("log", "reflective", "adaptive", "adaptScaleOnly", "adaptInterval", "temperPriors", "sliceMaxSteps", "useTempering"):
                 if k in c and c[k] is not None:
                     setattr(ctl, k, int(c[k]))
             for k in ("adaptFactorExponent", "scale", "width"):

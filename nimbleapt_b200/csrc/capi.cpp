@@ -67,7 +67,7 @@ const char* apt_version(void) { return "aptb200 0.1 (sm_100a)"; }
 void apt_sampler_control_default(apt_sampler_control* c) {
     c->log = 0; c->reflective = 0; c->adaptive = 1; c->adaptScaleOnly = 0; c->adaptInterval = 200;
     c->adaptFactorExponent = 0.8; c->scale = 1.0; c->temperPriors = -1; c->propCov = nullptr; c->propCov_dim = 0;
-    c->width = 1.0; c->sliceMaxSteps = 100;
+    c->width = 1.0; c->sliceMaxSteps = 100; c->useTempering = -1;
 }
 void apt_build_opts_default(apt_build_opts* o) {
     memset(o, 0, sizeof *o);

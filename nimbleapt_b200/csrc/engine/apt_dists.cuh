@@ -268,6 +268,47 @@ __device__ __forceinline__ double dcat_log(double x, const double (&prob)[K]) {
     for (int i = 1; i < K; i++) px = (i == ix) ? prob[i] : px;  // no dynamic indexing of a register array
     return log(px / sum);
 }
+// nimble's dmulti(x, size, prob) [NIMBLE-UNVERIFIED: "prob" is normalised internally; sum(x) must equal size]; the
+// target distribution of sampler_RW_multinomial_tempered (APT_functions.R:1046).
+template <int K>
+__device__ __forceinline__ double dmulti_log(const double (&x)[K], const double (&prob)[K], double size) {
+    double sumProb = 0.0, sumX = 0.0;
+    if (isnan(size)) return size;
+#pragma unroll
+    for (int i = 0; i < K; i++) {
+        if (isnan(prob[i])) return prob[i];
+        if (isnan(x[i])) return x[i];
+        sumProb += prob[i];
+        sumX += x[i];
+    }
+#pragma unroll
+    for (int i = 0; i < K; i++)
+        if (x[i] < 0 || x[i] != floor(x[i])) return APT_NEG_INF;
+    if (sumX > size + 10 * 2.220446049250313e-16 || sumX < size - 10 * 2.220446049250313e-16) return APT_NEG_INF;
+    double lp = lgamma(size + 1.0);
+#pragma unroll
+    for (int i = 0; i < K; i++)
+        if (!(x[i] == 0.0 && prob[i] == 0.0)) lp += x[i] * log(prob[i] / sumProb) - lgamma(x[i] + 1.0);
+    return lp;
+}
+
+// rbinom(1, size, prob) by inversion of ONE slot-addressed uniform (include/aptb200.h): the smallest k with
+// u <= P(X <= k), the pmf walked from k = 0 by its recurrence on the smaller of prob / 1 - prob.  size <= 1000.
+__device__ __noinline__ double rbinom_inv(double n, double p, double u) {
+    if (n <= 0 || p <= 0) return 0.0;
+    if (p >= 1) return n;
+    const bool flip = p > 0.5;
+    const double pp = flip ? 1.0 - p : p;
+    const double r = pp / (1.0 - pp);
+    double f = exp(n * log1p(-pp));
+    double k = 0.0;
+    while (u > f && k < n) {
+        u -= f;
+        k += 1.0;
+        f *= r * ((n - k + 1.0) / k);
+    }
+    return flip ? n - k : k;
+}
 // element of a constant array selected by a sampled node (e.g. rfx[k]): clamped into the array, so that a state the
 // prior excludes (its logProb is -Inf) cannot read out of bounds
 __device__ __forceinline__ int dyn_index(double v, int n) {

@@ -107,6 +107,7 @@ struct Engine {
     std::vector<DevBuf<int>> iarrays;
     Data D{};
     DevBuf<double> theta, lpd, temps, lp, scale, blk, empir, famdelta, wpart, model_theta, scale0, blk0;
+    bool blk_initialised = false;  // sampler$reset() leaves some entries alone (Model::blk_keep) once they exist
     DevBuf<int> slot, cnt, accswap;
     DevBuf<double> g_partial, g_pend, g_scratch;  // grid engine
     DevBuf<unsigned int> g_ticket;
@@ -190,6 +191,12 @@ struct Engine {
                 for (int i = 0; i < d * d; i++) pc[i] = hi.propcov0 ? hi.propcov0[i] : ((i % (d + 1)) == 0 ? 1.0 : 0.0);
                 if (host_chol_upper(pc, pc + d * d, d)) throw ApiError{"propCov is not positive definite"};
                 for (int i = 0; i < d * d; i++) pc[2 * d * d + i] = pc[d * d + i] * hi.scale0;
+            }
+            if (hi.kind == 3) {  // APT:1029-1040: u not drawn yet; five zero matrices, ENSwapMatrix, ENSwapDeltaMatrix, RescaleThreshold
+                const int dd = hi.d * hi.d;
+                double* b = &b0[hi.blkoff];
+                b[0] = -1.0;
+                for (int i = 0; i < dd; i++) { b[1 + 5 * dd + i] = 1.0; b[1 + 6 * dd + i] = 1.0; b[1 + 7 * dd + i] = 0.2; }
             }
         }
         scale0.alloc(G::NU); blk0.alloc(b0.size());
@@ -295,7 +302,8 @@ struct Engine {
         long long off, off2;
         if (reset) {                         // APT:369-377
             reset_kernel<G><<<std::min<size_t>((size_t)L * K, 65535), 64, 0, stream>>>(L, model_theta.p, theta.p, slot.p, scale.p,
-                                                                                     cnt.p, blk.p, scale0.p, blk0.p);
+                                                                                     cnt.p, blk.p, scale0.p, blk0.p, !blk_initialised);
+            blk_initialised = true;
             APT_CUDA(cudaGetLastError());
             timing.launches++;
             off = 0; off2 = 0;

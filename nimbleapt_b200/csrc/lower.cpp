@@ -72,6 +72,7 @@ struct Group {
 struct Unit {  // one generated sampler struct: a single sampler or a family
     int kind = 0, d = 1, unit0 = 0, count = 1;
     bool discrete = false;  // slice sampler: model$isDiscrete(target) (APT:926)
+    double ntotal = 0;      // multinomial sampler: Ntotal (APT:1024)
     std::vector<int> tgt;  // theta indices of member 0
     const SamplerConf* conf = nullptr;
     std::vector<Group> groups;
@@ -275,6 +276,9 @@ struct Lowerer {
                 } else if (dist == "dcat") {  // demo/APT_demo.R:84
                     d.dist = dist;
                     d.args = {need(kwarg(c, "prob", 0), "prob")};
+                } else if (dist == "dmulti") {  // target distribution of sampler_RW_multinomial_tempered (APT:1046)
+                    d.dist = dist;
+                    d.args = {need(kwarg(c, "prob", 0), "prob"), need(kwarg(c, "size", 1), "size")};
                 } else if (dist == "dmnorm") {
                     d.dist = dist;
                     if (!has_kw(c, "cholesky"))
@@ -283,7 +287,7 @@ struct Lowerer {
                               has_kw(c, "prec_param") ? kwarg(c, "prec_param", 99) : one};
                 } else {
                     throw Error("line " + std::to_string(rd.line) + ": unsupported distribution '" + dist +
-                                "' (supported: dnorm dunif dgamma dbeta dbinom dbern dpois dexp dcat dmnorm)");
+                                "' (supported: dnorm dunif dgamma dbeta dbinom dbern dpois dexp dcat dmulti dmnorm)");
                 }
             } else {
                 EP rhs = rd.rhs;
@@ -527,6 +531,15 @@ struct Lowerer {
                 for (auto& ix : d.lhs->a)
                     if (ix->k == Expr::RANGE) ln = (int)(std::llround(ceval(ix->a[1], {})) - std::llround(ceval(ix->a[0], {})) + 1);
                 if (ln != d.mvn_n) throw Error("dmnorm: node and mean have different lengths");
+            } else if (d.dist == "dmulti") {
+                for (auto& el : vector_elements(d.args[0])) d.mean_elems.push_back(inline_det(el));
+                d.mvn_n = (int)d.mean_elems.size();
+                if (d.mvn_n < 2 || d.mvn_n > 16) throw Error("dmulti: the probability vector must have between 2 and 16 elements");
+                d.iargs = {inline_det(d.args[1])};
+                int ln = 0;
+                for (auto& ix : d.lhs->a)
+                    if (ix->k == Expr::RANGE) ln = (int)(std::llround(ceval(ix->a[1], {})) - std::llround(ceval(ix->a[0], {})) + 1);
+                if (ln != d.mvn_n) throw Error("dmulti: node and prob have different lengths");
             } else if (d.dist == "dcat") {
                 // the probability vector, element by element (kept in mean_elems so that the dependency analysis sees it)
                 for (auto& el : vector_elements(d.args[0])) d.mean_elems.push_back(inline_det(el));
@@ -769,7 +782,7 @@ struct Lowerer {
             const CDecl& d = decls[di];
             if (!d.lhs_param) continue;
             const Var& v = vars.at(d.lhs->name);
-            if (tgt >= v.theta_off && tgt < v.theta_off + v.size) return d.dist == "dcat" || d.dist == "dbinom" || d.dist == "dpois";
+            if (tgt >= v.theta_off && tgt < v.theta_off + v.size) return d.dist == "dcat" || d.dist == "dbinom" || d.dist == "dpois" || d.dist == "dmulti";
         }
         throw Error("target has no stochastic declaration");
     }
@@ -785,8 +798,10 @@ struct Lowerer {
             if (sc.type == "sampler_RW_tempered" || sc.type == "RW_tempered") kind = 0;
             else if (sc.type == "sampler_RW_block_tempered" || sc.type == "RW_block_tempered") kind = 1;
             else if (sc.type == "sampler_slice_tempered" || sc.type == "slice_tempered") kind = 2;
-            else throw Error("unsupported sampler type '" + sc.type + "' (supported: sampler_RW_tempered, sampler_RW_block_tempered, sampler_slice_tempered)");
-            if (sc.ctl.temperPriors < 0 && kind != 2)  // APT:660, APT:781 (the slice sampler never reads it, APT:909-912)
+            else if (sc.type == "sampler_RW_multinomial_tempered" || sc.type == "RW_multinomial_tempered") kind = 3;
+            else throw Error("unsupported sampler type '" + sc.type + "' (supported: sampler_RW_tempered, sampler_RW_block_tempered, sampler_slice_tempered, sampler_RW_multinomial_tempered)");
+            if (kind == 3 && sc.ctl.useTempering < 0) throw Error("control$useTempering unspecified in sampler_RW_multinomial_tempered");  // APT:1015
+            if (sc.ctl.temperPriors < 0 && kind != 2 && kind != 3)  // APT:660, APT:781 (the slice sampler never reads it, APT:909-912)
                 throw Error("control$temperPriors unspecified in " + std::string(kind == 0 ? "sampler_RW_tempered" : "sampler_RW_block_tempered"));
             std::vector<int> tgt = expand_target(sc.target);
             if (kind == 0 && tgt.size() > 1) throw Error("cannot use RW sampler on more than one target; try RW_block sampler");  // APT:682
@@ -812,6 +827,42 @@ struct Lowerer {
                 u.blkoff = blkoff; blkoff += 3 * u.d * u.d;
                 u.empoff = empoff;
                 if (sc.ctl.adaptive && !sc.ctl.adaptScaleOnly) empoff += sc.ctl.adaptInterval * u.d;
+            }
+            if (kind == 3) {
+                // checks of the setup code (APT:1046-1048); state: u + 8 matrices d x d (APT:1029-1040) in the per-rung block state
+                int owner = -1;
+                long owner_inst = -1;
+                std::map<std::string, double> env;
+                std::vector<int64_t> els;
+                for (int t : tgt)
+                    for (int di : stoch_decls) {
+                        const CDecl& dd = decls[di];
+                        if (!dd.lhs_param) continue;
+                        const Var& v = vars.at(dd.lhs->name);
+                        if (t < v.theta_off || t >= v.theta_off + v.size) continue;
+                        for (long inst = 0; inst < dd.ninst; inst++) {
+                            inst_env(dd, inst, env);
+                            ref_elements(v, dd.lhs, env, els);
+                            for (auto e : els)
+                                if (v.theta_off + e == t) {
+                                    if (dd.dist != "dmulti") throw Error("can only use RW_multinomial sampler for multinomial distributions");  // APT:1046
+                                    if (owner >= 0 && (owner != di || owner_inst != inst)) throw Error("cannot use RW_multinomial sampler on more than one target");  // APT:1047
+                                    owner = di; owner_inst = inst;
+                                }
+                        }
+                    }
+                if (owner < 0) throw Error("target has no stochastic declaration");
+                if ((int)tgt.size() != decls[owner].mvn_n) throw Error("RW_multinomial sampler: the target must be the whole multinomial node");
+                if (sc.ctl.adaptive && sc.ctl.adaptInterval < 100) throw Error("adaptInterval < 100 is not recommended for RW_multinomial sampler");  // APT:1048
+                u.blkoff = blkoff; blkoff += 1 + 8 * u.d * u.d;
+                u.discrete = true;
+                u.ntotal = 0;  // Ntotal <- sum(values(model, target)) at setup (APT:1024)
+                for (int t : tgt)
+                    for (auto& n : param_order) {
+                        const Var& v = vars.at(n);
+                        if (t >= v.theta_off && t < v.theta_off + v.size) u.ntotal += v.arr->v[(size_t)(t - v.theta_off)];
+                    }
+                if (!(u.ntotal >= 0 && u.ntotal <= 1000)) throw Error("RW_multinomial sampler: sum of the target must be between 0 and 1000 (rbinom by inversion)");
             }
             if (kind == 2) {  // sumJumps (APT:925) lives in the per-rung sampler block state
                 u.blkoff = blkoff; blkoff += 1;
@@ -1424,6 +1475,21 @@ struct Lowerer {
                 out << "};\n    const double U_[" << n * n << "] = {";
                 for (int e = 0; e < n * n; e++) out << (e ? ", " : "") << gen_dbl(d.chol_elems[e], env);
                 out << "};\n    return apt::dmnorm_chol_log<" << n << ">(x_, mu_, U_, (" << gen_dbl(d.iargs[0], env) << ") != 0.0);\n";
+            } else if (d.dist == "dmulti") {
+                const int n = d.mvn_n;
+                int rdim = -1;
+                for (size_t k = 0; k < d.lhs->a.size(); k++)
+                    if (d.lhs->a[k]->k == Expr::RANGE) rdim = (int)k;
+                long lo = (long)std::llround(ceval(d.lhs->a[rdim]->a[0], {}));
+                out << "    const double x_[" << n << "] = {";
+                for (int e = 0; e < n; e++) {
+                    auto ref = std::make_shared<Expr>(*d.lhs);
+                    ref->a[rdim] = mk_num((double)(lo + e));
+                    out << (e ? ", " : "") << gen_dbl(ref, env);
+                }
+                out << "};\n    const double p_[" << n << "] = {";
+                for (int e = 0; e < n; e++) out << (e ? ", " : "") << gen_dbl(d.mean_elems[e], env);
+                out << "};\n    return apt::dmulti_log<" << n << ">(x_, p_, " << gen_dbl(d.iargs[0], env) << ");\n";
             } else if (d.dist == "dcat") {
                 out << "    const double p_[" << d.mvn_n << "] = {";
                 for (int e = 0; e < d.mvn_n; e++) out << (e ? ", " : "") << gen_dbl(d.mean_elems[e], env);
@@ -1472,9 +1538,10 @@ struct Lowerer {
             << ", COUNT = " << u.count << ", AI = " << ctl.adaptInterval << ", BLKOFF = " << u.blkoff << ", EMPOFF = " << u.empoff << ";\n";
         out << "    static constexpr bool LOG = " << (ctl.log ? "true" : "false") << ", REFL = " << (ctl.reflective ? "true" : "false")
             << ", ADAPT = " << (ctl.adaptive ? "true" : "false") << ", SCALE_ONLY = " << (ctl.adaptScaleOnly ? "true" : "false")
-            << ", TEMPER_PRIORS = " << (ctl.temperPriors ? "true" : "false") << ", HAS_PARTIAL = " << (has_partial ? "true" : "false")
+            << ", TEMPER_PRIORS = " << ((u.kind == 3 ? ctl.useTempering : ctl.temperPriors) ? "true" : "false") << ", HAS_PARTIAL = " << (has_partial ? "true" : "false")
             << ", DISCRETE = " << (u.discrete ? "true" : "false") << ";\n";
         out << "    static constexpr int MAXSTEPS = " << ctl.sliceMaxSteps << ";\n";
+        out << "    static constexpr double NTOTAL = " << fmt_d(u.ntotal) << ";\n";
         out << "    static constexpr double AEXP = " << fmt_d(ctl.adaptFactorExponent) << ";\n";
         auto sw = [&](const char* name, const char* type, std::function<std::string(const Group&)> f) {
             out << "    __device__ static constexpr " << type << " " << name << "(int g) { return ";
@@ -1542,7 +1609,7 @@ struct Lowerer {
     // wide update (apt_engine.cuh::rw_update_wide): only in cluster mode, for single samplers whose dependants include
     // a FULL declaration with many more instances than one tile could stride through quickly
     bool unit_is_wide(const Unit& u, int cluster, int tiles, int W) const {
-        if (cluster <= 1 || u.count != 1 || u.kind == 2 || getenv("APTB200_NO_WIDE")) return false;
+        if (cluster <= 1 || u.count != 1 || u.kind >= 2 || getenv("APTB200_NO_WIDE")) return false;
         for (auto& g : u.groups) {
             if (!g.full) return false;  // old values of PARTIAL groups would need a second wide pass
         }
@@ -1737,11 +1804,16 @@ struct Lowerer {
                     if (g.full) maxfull = std::max(maxfull, decls[g.decl].ninst);
             const long nchains = (long)std::max(1, opts.n_ladders) * K;
             if (opts.engine == 2 || (opts.engine == 0 && !has_family && nchains <= 256 && maxfull >= 65536)) engine = 2;
-            for (auto& u : units)
+            for (auto& u : units) {
+                if (u.kind == 3) {
+                    if (opts.engine == 2) throw Error("grid engine: sampler_RW_multinomial_tempered is not supported (use engine = 1)");
+                    engine = 1;
+                }
                 if (u.kind == 2) {
                     if (opts.engine == 2) throw Error("grid engine: sampler_slice_tempered is not supported (use engine = 1)");
                     engine = 1;
                 }
+            }
             if (engine == 2) {
                 if (has_family) throw Error("grid engine: sampler families are not supported yet (use engine = 1)");
                 const long big_min = opts.engine == 2 ? 256 : 8192;
@@ -1873,7 +1945,7 @@ struct Lowerer {
             } else {
                 out << "    if (active) for (int k = c.tile_id; k < K; k += c.ntiles) {\n";
                 while (ui < units.size() && units[ui].count == 1 && !unit_is_wide(units[ui], cluster, tiles, W)) {
-                    out << "      apt::" << (units[ui].kind == 2 ? "slice_update" : "rw_update") << "<Model, S" << ui << ">(c, D, k, 0);\n";
+                    out << "      apt::" << (units[ui].kind == 2 ? "slice_update" : units[ui].kind == 3 ? "multinomial_update" : "rw_update") << "<Model, S" << ui << ">(c, D, k, 0);\n";
                     ui++;
                 }
                 out << "    }\n";
@@ -1946,6 +2018,11 @@ struct Lowerer {
             out << " (void)L0; (void)L1; (void)L2; apt::dpois_pre(" << gen_dbl(d.lhs, decl_env(d)) << ", out + 2 * i); break; }\n";
         }
         out << "      default: break;\n    }\n  }\n";
+        // entries of the per-rung sampler block state that sampler$reset() leaves alone (the multinomial sampler's u, APT:1133-1142)
+        out << "  __host__ __device__ static constexpr bool blk_keep(int i) { return ";
+        for (auto& u : units)
+            if (u.kind == 3) out << "i == " << u.blkoff << " || ";
+        out << "false; }\n";
         out << "  __device__ static __forceinline__ int mon(int c) { return MON_TAB[c]; }\n";
         out << "  __device__ static __forceinline__ int mon2(int c) { return MON2_TAB[c]; }\n";
         out << body.str();

@@ -9,6 +9,8 @@
  *   sampler_RW_tempered          APT_functions.R:649-761
  *   sampler_RW_block_tempered    APT_functions.R:770-889
  *   sampler_slice_tempered       APT_functions.R:898-995
+ *   sampler_RW_multinomial_tempered APT_functions.R:1005-1145
+ *   calculateWAIC                APT_functions.R:593-635
  *   sampler indexing             APT_functions.R:281-287
  * plus the nimble behaviours those lines call into (calculateDiff, getLogProb, decide, decideAndJump,
  * setAndCalculateDiff, calcAdaptationFactor, rmnorm_chol, rcat, nimCopy, initializeModel), restated from
@@ -44,7 +46,7 @@
 enum { OP_END = 0, OP_CONST, OP_LOOP, OP_LOAD0, OP_LOAD1, OP_LOAD2, OP_ADD, OP_SUB, OP_MUL, OP_DIV, OP_POW, OP_NEG,
        OP_EXP, OP_LOG, OP_ABS, OP_SQRT, OP_ILOGIT, OP_LOGIT, OP_PHI, OP_ICLOGLOG, OP_CLOGLOG, OP_LOG1P, OP_STEP,
        OP_MIN, OP_MAX, OP_INPROD, OP_SUM, OP_LGAMMA };
-enum { D_NORM = 0, D_UNIF, D_GAMMA, D_BETA, D_BINOM, D_POIS, D_MNORM_CHOL, D_EXP, D_CAT };
+enum { D_NORM = 0, D_UNIF, D_GAMMA, D_BETA, D_BINOM, D_POIS, D_MNORM_CHOL, D_EXP, D_CAT, D_MULTI };
 
 /* declaration record layout (ints) */
 enum { R_KIND = 0, R_DIST, R_NLOOP, R_LO0, R_LO1, R_LO2, R_HI0, R_HI1, R_HI2, R_VAR, R_LNDIM, R_LIDX0, R_LIDX1,
@@ -75,6 +77,7 @@ typedef struct {
     double adapt_exp, scale0;
     double* propcov0;
     int lower_code, upper_code;
+    double ntotal;           /* sampler_RW_multinomial_tempered: Ntotal <- sum(values(model, target)) at setup (APT:1024) */
     int max_steps, discrete; /* sampler_slice_tempered: control$sliceMaxSteps (APT:912), model$isDiscrete(target) (APT:926) */
     int ncopyv, ncopylp;
     int *copyv, *copylp;
@@ -85,6 +88,8 @@ typedef struct {
     double sumJumps;      /* slice sampler (APT:925) */
     int timesRan, timesAccepted, timesAdapted;
     double *propCov, *chol, *cholScaled, *empir;
+    double u;   /* multinomial sampler: recycled uniform on (0, pi) (APT:1040); < 0 = not drawn yet */
+    double* mn; /* multinomial sampler: 8 matrices d x d (APT:1029-1036) */
 } orc_sstate;
 
 typedef struct {
@@ -265,6 +270,16 @@ static double calc_node(orc_ctx* c, int d, int inst) {
             for (int i = 0; i < n; i++) ch[i + j * n] = *vref(c, off + (ac[2] - 1 + i) + (ac[4] - 1 + j) * nrow);
         int prec = (int)eval(c, a[2 * ARGREC + 1]);
         lp = apt_dmnorm_chol_log(x, mu, ch, n, prec, wk);
+    } else if (r[R_DIST] == D_MULTI) { /* x[lo:hi] ~ dmulti(prob = vector slice, size = scalar) */
+        int n = lhs_len(r);
+        double x[64], pr[64];
+        const int* ap = &a[0];
+        double other = ap[6] >= 0 ? eval(c, ap[6]) : 0;
+        for (int e = 0; e < n && e < 64; e++) {
+            x[e] = *vref(c, lhs_index(c, r, e));
+            pr[e] = slice_get(c, ap, other, e);
+        }
+        lp = apt_dmulti_log(x, pr, n, eval(c, a[ARGREC + 1]));
     } else if (r[R_DIST] == D_CAT) {
         double x = *vref(c, lhs_index(c, r, 0));
         const int* ap = &a[0];
@@ -428,6 +443,12 @@ int orc_spec_set(const orc_model* m, orc_sspec* specs, int s, int kind, int d, c
     return 0;
 }
 
+/* sampler_RW_multinomial_tempered (kind 3): temper_priors of orc_spec_set carries control$useTempering */
+int orc_spec_set_multinomial(orc_sspec* specs, int s, double ntotal) {
+    specs[s].ntotal = ntotal;
+    return 0;
+}
+
 /* extra control of sampler_slice_tempered (kind 2); scale0 of orc_spec_set carries control$width */
 int orc_spec_set_slice(orc_sspec* specs, int s, int max_steps, int discrete) {
     specs[s].max_steps = max_steps; specs[s].discrete = discrete;
@@ -441,6 +462,13 @@ static void sstate_reset(const orc_sspec* p, orc_sstate* s) {
         memcpy(s->propCov, p->propcov0, sizeof(double) * d * d);
         apt_chol_upper(s->propCov, s->chol, d);
         for (int i = 0; i < d * d; i++) s->cholScaled[i] = s->chol[i] * s->scale;
+    }
+    if (p->kind == 3) { /* reset (APT:1133-1142): u is NOT reset */
+        int dd = p->d * p->d;
+        for (int i = 0; i < dd; i++) {
+            s->mn[i] = 0; s->mn[dd + i] = 0; s->mn[2 * dd + i] = 0; s->mn[3 * dd + i] = 0; s->mn[4 * dd + i] = 0;
+            s->mn[5 * dd + i] = 1; s->mn[6 * dd + i] = 1; s->mn[7 * dd + i] = 0.2;
+        }
     }
 }
 
@@ -490,6 +518,7 @@ orc_ladder* orc_ladder_new(const orc_model* m, const orc_sspec* specs, int NS, c
                 st->cholScaled = (double*)malloc(sizeof(double) * d * d);
                 st->empir = (double*)calloc((size_t)p->adapt_interval * d, sizeof(double));
             }
+            if (p->kind == 3) { st->mn = (double*)calloc((size_t)8 * p->d * p->d, sizeof(double)); st->u = -1.0; }
             sstate_reset(p, st);
         }
     L->totalIters = 1;   /* APT:321 */
@@ -501,7 +530,7 @@ orc_ladder* orc_ladder_new(const orc_model* m, const orc_sspec* specs, int NS, c
 void orc_ladder_free(orc_ladder* L) {
     if (!L) return;
     for (int k = 0; k < L->K; k++) { free(L->rung[k].mut); free(L->rung[k].lp); free(L->saved[k].mut); free(L->saved[k].lp); }
-    for (int i = 0; i < L->K * L->NS; i++) { free(L->ss[i].propCov); free(L->ss[i].chol); free(L->ss[i].cholScaled); free(L->ss[i].empir); }
+    for (int i = 0; i < L->K * L->NS; i++) { free(L->ss[i].propCov); free(L->ss[i].chol); free(L->ss[i].cholScaled); free(L->ss[i].empir); free(L->ss[i].mn); }
     free(L->rung); free(L->saved); free(L->model.mut); free(L->model.lp); free(L->ss);
     free(L->Temps); free(L->invTemps); free(L->TempsCurrent); free(L->logProbTemps); free(L->pSwap);
     free(L->temporary); free(L->accCountSwap); free(L->mon); free(L->mon2);
@@ -747,6 +776,92 @@ static int run_slice(orc_ladder* L, int s, int tt, orc_buf* model, orc_buf* save
     return ncalls & 0xFF;
 }
 
+/* sampler_RW_multinomial_tempered$run (APT:1054-1082), generateProposalVector (APT:1087-1098),
+   adaptiveProcedure (APT:1099-1129).  Randoms of sub-proposal q (0-based, in loop order): slot block q, words (0,1) ->
+   the uniform inverted by rbinom, words (2,3) -> the acceptance uniform; the recycled u (APT:1040) is drawn as
+   pi * U(words 0,1 of block 0x7FFF) at the sampler's first update.  Returns the number of accepted sub-proposals. */
+#define APT_SLOT_MULTI_U0 0x7FFFu
+static int g_multi_exact_reverse = 0;
+void orc_set_multinomial_exact_reverse(int on) { g_multi_exact_reverse = on; }
+static int run_multinomial(orc_ladder* L, int s, int tt, orc_buf* model, orc_buf* saved, double temperature) {
+    const orc_sspec* p = &L->specs[s];
+    orc_sstate* st = &L->ss[s + tt * L->NS];
+    orc_ctx c; c.m = L->m; c.mut = model->mut; c.lp = model->lp;
+    const int d = p->d, dd = d * d;
+    double *timesRan = st->mn, *AcceptRates = st->mn + dd, *ScaleShifts = st->mn + 2 * dd, *totalAdapted = st->mn + 3 * dd,
+           *timesAccepted = st->mn + 4 * dd, *EN = st->mn + 5 * dd, *ENDelta = st->mn + 6 * dd, *Rescale = st->mn + 7 * dd;
+    const double Pi = 3.14159265358979323846, PiOver2 = Pi / 2, Ntotal = p->ntotal, NOverL = Ntotal / d;
+    uint32_t w[4];
+    if (st->u < 0) { /* u <- runif(1, 0, Pi)  (APT:1040) */
+        apt_slot_words(L->seed, L->ladder, L->rngIter, (uint32_t)s, (uint32_t)tt, APT_SLOT_MULTI_U0, w);
+        st->u = Pi * apt_u53(w[0], w[1]);
+    }
+    double u = st->u;
+    double prop[64];
+    int q = 0, naccept = 0;
+    for (int iFROM = 1; iFROM <= d; iFROM++)
+        for (int iTO = 1; iTO <= d - 1; iTO++, q++) {
+            int iFrom, iTo;
+            if (u > PiOver2) {
+                iFrom = iFROM; iTo = iTO;
+                if (iFrom == iTo) iTo = d;
+                u = 2 * (u - PiOver2);
+            } else {
+                iFrom = iTO; iTo = iFROM;
+                if (iFrom == iTo) iFrom = d;
+                u = 2 * (PiOver2 - u);
+            }
+            const int ft = (iFrom - 1) + (iTo - 1) * d, tf = (iTo - 1) + (iFrom - 1) * d;
+            apt_slot_words(L->seed, L->ladder, L->rngIter, (uint32_t)s, (uint32_t)tt, (uint32_t)q, w);
+            /* generateProposalVector(iFrom, iTo) */
+            for (int e = 0; e < d; e++) prop[e] = model->mut[p->tgt[e]];
+            double pSwap = fmin(1, fmax(1, EN[ft]) / prop[iFrom - 1]);
+            double nSwap = apt_rbinom_inv(prop[iFrom - 1], pSwap, apt_u53(w[0], w[1]));
+            double lpProp = apt_dbinom_log(nSwap, prop[iFrom - 1], pSwap);
+            prop[iFrom - 1] -= nSwap;
+            prop[iTo - 1] += nSwap;
+            /* APT:1094 divides by propVector[iTo] + nSwap AFTER propVector[iTo] was incremented (APT:1093), i.e. by
+               x_to + 2 nSwap, while lpRev (APT:1095) is evaluated at size x_to + nSwap: the proposal ratio is not the
+               exact reverse probability and the chain's stationary law deviates slightly from the posterior.  Restated
+               as the reference has it; the test-only switch below evaluates the exact reverse proposal instead, which
+               pins the rest of the restatement against an enumerated posterior (tests/test_oracle_engine.py). */
+            double pRevSwap = fmin(1, fmax(1, EN[tf]) / (prop[iTo - 1] + (g_multi_exact_reverse ? 0.0 : nSwap)));
+            double lpRev = apt_dbinom_log(nSwap, prop[iTo - 1], pRevSwap);
+            /* my_setAndCalculateDiff$run(propValueVector) */
+            for (int e = 0; e < d; e++) model->mut[p->tgt[e]] = prop[e];
+            double diff = calculate_diff(&c, p->calc_decl, p->calc_inst, p->ncalc);
+            double lpMHR = p->temper_priors ? diff / temperature + lpRev - lpProp : diff + lpRev - lpProp;
+            int jump = decide(lpMHR, apt_u53(w[2], w[3])); /* my_decideAndJump$run(lpMHR, 0, 0, 0) */
+            if (jump) copy_nodes(p, model, saved); else copy_nodes(p, saved, model);
+            naccept += jump;
+            if (p->adaptive) { /* adaptiveProcedure(jump, iFrom, iTo) */
+                timesRan[ft] += 1;
+                if (jump) timesAccepted[ft] += 1;
+                if (fmod(timesRan[ft], (double)p->adapt_interval) == 0) {
+                    totalAdapted[ft] += 1;
+                    double accRate = timesAccepted[ft] / timesRan[ft];
+                    AcceptRates[ft] = accRate;
+                    if (accRate > 0.5) EN[ft] = fmin(Ntotal, EN[ft] + ENDelta[ft] / totalAdapted[ft]);
+                    else EN[ft] = fmax(1, EN[ft] - ENDelta[ft] / totalAdapted[ft]);
+                    if (accRate < Rescale[ft] || accRate > (1 - Rescale[ft])) {
+                        if (EN[ft] > 1 && EN[ft] < Ntotal) {
+                            ScaleShifts[ft] += 1;
+                            ENDelta[ft] = fmin(NOverL, ENDelta[ft] * totalAdapted[ft] / 10);
+                            ENDelta[tf] = ENDelta[ft];
+                            Rescale[ft] = 0.2 * pow(0.95, ScaleShifts[ft]);
+                        }
+                    }
+                    if (EN[ft] < 1) EN[ft] = 1;
+                    EN[tf] = EN[ft];
+                    timesRan[ft] = 0;
+                    timesAccepted[ft] = 0;
+                }
+            }
+        }
+    st->u = u;
+    return naccept & 0xFF;
+}
+
 /* ------------------------------------------------------------------ swap machinery */
 /* pSwapCalc  (APT:556-576) */
 static void pswap_calc(orc_ladder* L) {
@@ -836,6 +951,7 @@ int orc_ladder_run(orc_ladder* L, long niter, int reset, int resetMV, int resetT
             for (int s = 0; s < NS; s++) {
                 int jump = L->specs[s].kind == 0 ? run_scalar(L, s, tt, model, saved, L->Temps[tt])
                          : L->specs[s].kind == 1 ? run_block(L, s, tt, model, saved, L->Temps[tt])
+                         : L->specs[s].kind == 3 ? run_multinomial(L, s, tt, model, saved, L->Temps[tt])
                                                  : run_slice(L, s, tt, model, saved, L->Temps[tt]);
                 if (L->recDec) L->recDec[((size_t)L->itRun * K + tt) * NS + s] = (unsigned char)jump;
             }
@@ -1005,4 +1121,6 @@ const double* orc_ladder_ptr(const orc_ladder* L, int what) {
 const double* orc_ladder_rung_state(const orc_ladder* L, int tt) { return L->rung[tt].mut; }
 double orc_ladder_scale(const orc_ladder* L, int tt, int s) { return L->ss[s + tt * L->NS].scale; }
 const double* orc_ladder_propcov(const orc_ladder* L, int tt, int s) { return L->ss[s + tt * L->NS].propCov; }
+const double* orc_ladder_multinomial_state(const orc_ladder* L, int tt, int s) { return L->ss[s + tt * L->NS].mn; }
+double orc_ladder_multinomial_u(const orc_ladder* L, int tt, int s) { return L->ss[s + tt * L->NS].u; }
 long orc_ladder_total_iters(const orc_ladder* L) { return L->totalIters; }

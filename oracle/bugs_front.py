@@ -21,8 +21,8 @@ import numpy as np
 OPS = dict(END=0, CONST=1, LOOP=2, LOAD0=3, LOAD1=4, LOAD2=5, ADD=6, SUB=7, MUL=8, DIV=9, POW=10, NEG=11,
            EXP=12, LOG=13, ABS=14, SQRT=15, ILOGIT=16, LOGIT=17, PHI=18, ICLOGLOG=19, CLOGLOG=20, LOG1P=21,
            STEP=22, MIN=23, MAX=24, INPROD=25, SUM=26, LGAMMA=27)
-DISTS = dict(dnorm=0, dunif=1, dgamma=2, dbeta=3, dbinom=4, dpois=5, dmnorm=6, dexp=7, dcat=8)
-DISCRETE_DISTS = ("dcat", "dbinom", "dpois")  # model$isDiscrete(target), APT_functions.R:926
+DISTS = dict(dnorm=0, dunif=1, dgamma=2, dbeta=3, dbinom=4, dpois=5, dmnorm=6, dexp=7, dcat=8, dmulti=9)
+DISCRETE_DISTS = ("dcat", "dbinom", "dpois", "dmulti")  # model$isDiscrete(target), APT_functions.R:926
 DREC, MAXARGS, ARGREC = 80, 6, 8
 R_KIND, R_DIST, R_NLOOP, R_LO0, R_HI0, R_VAR, R_LNDIM, R_LIDX0, R_LRDIM, R_LRLO, R_LRHI, R_NARGS, R_ARGS = \
     0, 1, 2, 3, 6, 9, 10, 11, 13, 14, 15, 16, 17
@@ -266,6 +266,8 @@ class OracleModel:
                     cargs = [kw["scale"]] if "scale" in kw else [("bin", "/", one, kw.get("rate", args[0] if args else None))]
                 elif dist == "dcat":  # nimbleAPT/demo/APT_demo.R:84
                     cargs = [kw.get("prob", args[0] if args else None)]
+                elif dist == "dmulti":  # target of sampler_RW_multinomial_tempered, APT_functions.R:1046
+                    cargs = [kw.get("prob", args[0] if args else None), kw.get("size", args[1] if len(args) > 1 else None)]
                 elif dist == "dmnorm":
                     mean = kw.get("mean", args[0] if args else None)
                     assert "cholesky" in kw, "oracle front end supports dmnorm(mean, cholesky=, prec_param=) only"
@@ -510,7 +512,7 @@ class OracleModel:
             r[R_NARGS] = len(d["args"])
             for a, t in enumerate(d["args"]):
                 base = R_ARGS + a * ARGREC
-                if d["stoch"] and (d["dist"] == "dmnorm" or d["dist"] == "dcat") and a == 0:
+                if d["stoch"] and d["dist"] in ("dmnorm", "dcat", "dmulti") and a == 0:
                     rec, other = self._slice_rec(t, loopnames, None)
                     if other is not None:
                         rec[6] = self.compile_scalar(other, loopnames)
@@ -655,6 +657,34 @@ class OracleModel:
                         return ("num", 0.0), ("num", 1.0), subst
                     return ("num", -inf), ("num", inf), subst
         raise KeyError("target has no stochastic declaration")
+
+    def target_dist(self, target_idx):
+        """model$getDistribution(target) of the node that owns this element (APT_functions.R:1046)."""
+        for d in self.cdecls:
+            v = self.vars[d["lhs"][1]]
+            if not (d["stoch"] and v.role == "param"):
+                continue
+            env, n = self._inst_env(d)
+            base, cnt, stride = self.lhs_elements(d, env, n)
+            for e in range(cnt):
+                if np.any(v.off + base + e * stride == target_idx):
+                    return d["dist"]
+        raise KeyError("target has no stochastic declaration")
+
+    def target_nodes(self, target_idx):
+        """unique(model$expandNodeNames(target)): the (declaration, instance) pairs owning the target elements."""
+        nodes = set()
+        for di, d in enumerate(self.cdecls):
+            v = self.vars[d["lhs"][1]]
+            if not (d["stoch"] and v.role == "param"):
+                continue
+            env, n = self._inst_env(d)
+            base, cnt, stride = self.lhs_elements(d, env, n)
+            for e in range(cnt):
+                for t in target_idx:
+                    for w in np.nonzero(v.off + base + e * stride == t)[0]:
+                        nodes.add((di, int(w)))
+        return nodes
 
     def is_discrete(self, target_idx):
         """model$isDiscrete(target) for a scalar target (APT_functions.R:926)."""

@@ -62,6 +62,16 @@ def lib():
         L.orc_ladder_propcov.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.orc_ladder_total_iters.restype = C.c_long
         L.orc_ladder_total_iters.argtypes = [C.c_void_p]
+        L.orc_spec_set_multinomial.argtypes = [C.c_void_p, C.c_int, C.c_double]
+        L.orc_ladder_multinomial_state.restype = dp
+        L.orc_ladder_multinomial_state.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.orc_ladder_multinomial_u.restype = C.c_double
+        L.orc_ladder_multinomial_u.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.orc_set_multinomial_exact_reverse.argtypes = [C.c_int]
+        L.apt_dmulti_log.restype = C.c_double
+        L.apt_dmulti_log.argtypes = [dp, dp, C.c_int, C.c_double]
+        L.apt_rbinom_inv.restype = C.c_double
+        L.apt_rbinom_inv.argtypes = [C.c_double] * 3
         L.orc_ladder_waic.restype = C.c_double
         L.orc_ladder_waic.argtypes = [C.c_void_p, C.c_long, C.c_int, ip, dp]
         for f in ("apt_dnorm_log", "apt_dunif_log", "apt_dgamma_log", "apt_dbeta_log", "apt_dbinom_log"):
@@ -87,7 +97,8 @@ def _da(a):
 
 
 SAMPLER_KINDS = {"sampler_RW_tempered": 0, "RW_tempered": 0, "sampler_RW_block_tempered": 1, "RW_block_tempered": 1,
-                 "sampler_slice_tempered": 2, "slice_tempered": 2}
+                 "sampler_slice_tempered": 2, "slice_tempered": 2,
+                 "sampler_RW_multinomial_tempered": 3, "RW_multinomial_tempered": 3}
 
 
 class OracleAPT:
@@ -105,6 +116,10 @@ class OracleAPT:
             kind = SAMPLER_KINDS[s["type"]]
             if kind == 2:  # sampler_slice_tempered never reads temperPriors (APT_functions.R:909-912)
                 ctl.setdefault("temperPriors", True)
+            if kind == 3:  # sampler_RW_multinomial_tempered reads useTempering instead (APT_functions.R:1015)
+                if "useTempering" not in ctl:
+                    raise ValueError("control$useTempering unspecified in sampler_RW_multinomial_tempered")
+                ctl["temperPriors"] = bool(ctl["useTempering"])
             if "temperPriors" not in ctl:  # APT_functions.R:660,781
                 raise ValueError("control$temperPriors unspecified in %s" % s["type"])
             tgt = om.expand_target(s["target"])
@@ -112,6 +127,13 @@ class OracleAPT:
                 raise ValueError("cannot use slice sampler on more than one target node")
             if kind == 0 and len(tgt) > 1:  # APT_functions.R:682
                 raise ValueError("cannot use RW sampler on more than one target; try RW_block sampler")
+            if kind == 3:
+                if om.target_dist(tgt[0]) != "dmulti":  # APT_functions.R:1046
+                    raise ValueError("can only use RW_multinomial sampler for multinomial distributions")
+                if len(om.target_nodes(tgt)) > 1:  # APT_functions.R:1047
+                    raise ValueError("cannot use RW_multinomial sampler on more than one target")
+                if ctl.get("adaptive", True) and int(ctl.get("adaptInterval", 200)) < 100:  # APT_functions.R:1048
+                    raise ValueError("adaptInterval < 100 is not recommended for RW_multinomial sampler")
             cd, ci, td, ti = om.dependencies(tgt)
             lower = upper = -1
             if kind == 0 and ctl.get("reflective", False):
@@ -160,6 +182,8 @@ class OracleAPT:
                            int(bool(ctl.get("adaptive", True))), int(bool(ctl.get("adaptScaleOnly", False))),
                            int(ctl.get("adaptInterval", 200)), int(bool(ctl["temperPriors"])), afe, scale, pcp,
                            sp["lower"], sp["upper"])
+            if sp["kind"] == 3:  # Ntotal <- sum(values(model, target)) at setup (APT_functions.R:1024)
+                L.orc_spec_set_multinomial(self.specs, i, float(sum(om.arena0[t_] for t_ in sp["tgt"])))
             if sp["kind"] == 2:
                 L.orc_spec_set_slice(self.specs, i, int(ctl.get("sliceMaxSteps", 100)), int(om.is_discrete(sp["tgt"][0])))
         self.monitors = list(monitors)
@@ -262,6 +286,13 @@ class OracleAPT:
 
     def scale(self, ladder, tt, s):
         return lib().orc_ladder_scale(self.ladders[ladder], tt, s)
+
+    def multinomialState(self, ladder, tt, s, d):
+        """[u, timesRan, AcceptRates, ScaleShifts, totalAdapted, timesAccepted, ENSwapMatrix, ENSwapDeltaMatrix,
+        RescaleThreshold] of a sampler_RW_multinomial_tempered (APT_functions.R:1029-1040); matrices column-major."""
+        p = lib().orc_ladder_multinomial_state(self.ladders[ladder], tt, s)
+        m = np.ctypeslib.as_array(p, shape=(8 * d * d,)).copy()
+        return np.concatenate([[lib().orc_ladder_multinomial_u(self.ladders[ladder], tt, s)], m])
 
     def propCov(self, ladder, tt, s, d):
         p = lib().orc_ladder_propcov(self.ladders[ladder], tt, s)

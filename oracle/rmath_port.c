@@ -228,6 +228,51 @@ double apt_dcat_log(double x, const double* prob, int K) {
 }
 
 /*
+ * nimble's dmulti(x, size, prob, K, give_log) [NIMBLE-UNVERIFIED, restated from its documented behaviour: "prob" is
+ * normalised internally; sum(x) must equal size]: lgamma(size + 1) + sum_i (x_i log(prob_i / sum(prob)) - lgamma(x_i + 1)),
+ * terms with x_i = 0 and prob_i = 0 skipped.  Target distribution of sampler_RW_multinomial_tempered (APT:1046).
+ */
+double apt_dmulti_log(const double* x, const double* prob, int K, double size) {
+    double sumProb = 0.0, sumX = 0.0;
+    if (isnan(size)) return size;
+    for (int i = 0; i < K; i++) {
+        if (isnan(prob[i])) return prob[i];
+        if (isnan(x[i])) return x[i];
+        sumProb += prob[i];
+        sumX += x[i];
+    }
+    for (int i = 0; i < K; i++)
+        if (x[i] < 0 || x[i] != floor(x[i])) return NEG_INF;
+    if (sumX > size + 10 * 2.220446049250313e-16 || sumX < size - 10 * 2.220446049250313e-16) return NEG_INF;
+    double lp = lgamma(size + 1.0);
+    for (int i = 0; i < K; i++)
+        if (!(x[i] == 0.0 && prob[i] == 0.0)) lp += x[i] * log(prob[i] / sumProb) - lgamma(x[i] + 1.0);
+    return lp;
+}
+
+/*
+ * rbinom(1, size, prob) by inversion of ONE uniform (R's rbinom consumes a data-dependent number of draws from its
+ * sequential stream, which a slot-addressed generator cannot reproduce; include/aptb200.h documents the convention):
+ * the smallest k with u <= P(X <= k), the pmf walked from k = 0 by its recurrence, on the smaller of prob / 1 - prob.
+ * size <= 1000 (no underflow of P(X = 0)).
+ */
+double apt_rbinom_inv(double n, double p, double u) {
+    if (n <= 0 || p <= 0) return 0.0;
+    if (p >= 1) return n;
+    const int flip = p > 0.5;
+    const double pp = flip ? 1.0 - p : p;
+    const double r = pp / (1.0 - pp);
+    double f = exp(n * log1p(-pp));
+    double k = 0.0;
+    while (u > f && k < n) {
+        u -= f;
+        k += 1.0;
+        f *= r * ((n - k + 1.0) / k);
+    }
+    return flip ? n - k : k;
+}
+
+/*
  * nimble's dmnorm_chol(x, mean, chol, n, prec_param, give_log) [NIMBLE-UNVERIFIED, restated from its
  * documented behaviour]: chol is the UPPER Cholesky factor U (U'U = cov or precision), column-major.
  *   dens = -n*log(sqrt(2pi)) + (prec_param ? +1 : -1) * sum_i log U_ii

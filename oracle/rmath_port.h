@@ -17,6 +17,8 @@ double apt_dbinom_log(double x, double n, double p);
 double apt_dpois_log(double x, double lambda);
 double apt_dexp_log(double x, double scale);
 double apt_dcat_log(double x, const double* prob, int K);
+double apt_dmulti_log(const double* x, const double* prob, int K, double size);
+double apt_rbinom_inv(double n, double p, double u);
 double apt_dmnorm_chol_log(const double* x, const double* mean, const double* chol, int n, int prec_param,
                            double* work);
 int apt_chol_upper(const double* A, double* U, int n);

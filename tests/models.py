@@ -196,3 +196,50 @@ def demo_wrong_k_posterior(spec):
     lw = np.array(lw)
     pk = np.trapezoid(np.exp(lw - lw.max()), g, axis=1)
     return pk / pk.sum()
+
+
+def multinomial_latent(Lc=4, N=30, K=5, adaptInterval=100):
+    """Latent counts x[1:Lc] ~ dmulti(prob, N) observed through Poisson counts, one sampler_RW_multinomial_tempered
+    (APT_functions.R:1005-1145) plus a scalar sampler on the rate multiplier.  Small enough for the exact posterior of
+    x (all compositions of N into Lc parts) to be enumerated."""
+    rng = np.random.default_rng(DATA_SEED + 31)
+    prob = np.array([0.1, 0.2, 0.3, 0.4])[:Lc]
+    prob = prob / prob.sum()
+    y = np.array([2.0, 9.0, 6.0, 14.0])[:Lc]
+    code = """{
+    x[1:Lc] ~ dmulti(prob = prob[1:Lc], size = N)
+    for (j in 1:Lc) {
+        y[j] ~ dpois(0.5 + a * x[j])
+    }
+    a ~ dgamma(shape = 4, rate = 4)
+    }"""
+    x0 = np.array([N - 3.0 * (Lc - 1)] + [3.0] * (Lc - 1))
+    return dict(code=code, constants=dict(Lc=Lc, N=N, prob=prob), data=dict(y=y),
+                inits=dict(x=x0, a=np.array(1.0)),
+                samplers=[dict(target="x[1:%d]" % Lc, type="sampler_RW_multinomial_tempered",
+                               control=dict(useTempering=True, adaptInterval=adaptInterval)),
+                          dict(target="a", type="sampler_RW_tempered", control=dict(temperPriors=True, log=True, scale=0.3))],
+                monitors=["x", "a"], Temps=np.exp(np.linspace(0.0, np.log(8.0), K)), ULT=1e6)
+
+
+def multinomial_latent_posterior(spec):
+    """Exact posterior mean of x (and of a) in multinomial_latent(): every composition of N into Lc parts is enumerated,
+    a ~ dgamma(4, 4) is integrated on a grid."""
+    import itertools
+    from scipy import special
+    c, y = spec["constants"], spec["data"]["y"]
+    Lc, N, prob = int(c["Lc"]), int(c["N"]), np.asarray(c["prob"], dtype=float)
+    comps = np.array([np.diff(np.concatenate([[-1], cuts, [N + Lc - 1]])) - 1
+                      for cuts in itertools.combinations(range(N + Lc - 1), Lc - 1)], dtype=float)
+    lprior = special.gammaln(N + 1) + np.sum(comps * np.log(prob / prob.sum()) - special.gammaln(comps + 1), axis=1)
+    a = np.linspace(1e-4, 12.0, 4001)
+    lpa = 3 * np.log(a) - 4 * a                                      # dgamma(shape = 4, rate = 4) up to a constant
+    lam = 0.5 + a[None, :, None] * comps[:, None, :]                 # [composition, a, j]
+    ll = np.sum(y * np.log(lam) - lam, axis=2) + lpa[None, :]        # dpois up to a constant
+    m = ll.max()
+    wa = np.exp(ll - m)                                              # [composition, a]
+    w = np.exp(lprior - lprior.max())[:, None] * wa
+    Z = np.trapezoid(w.sum(axis=0), a)
+    ex = np.array([np.trapezoid((w * comps[:, j][:, None]).sum(axis=0), a) for j in range(Lc)]) / Z
+    ea = np.trapezoid(w.sum(axis=0) * a, a) / Z
+    return ex, ea

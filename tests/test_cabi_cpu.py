@@ -70,13 +70,40 @@ def test_control_validation_mirrors_reference():
     with pytest.raises(nb.AptError, match="propCov matrix must be symmetric"):  # APT:817
         nb.buildAPT(conf, Temps=[1, 2, 3])
     with pytest.raises(ValueError, match="unsupported sampler type"):
-        conf.addSampler("theta[1]", type="sampler_RW_multinomial_tempered", control=dict(temperPriors=True))
+        conf.addSampler("theta[1]", type="sampler_AF_slice", control=dict(temperPriors=True))
     conf.removeSamplers()
     conf.addSampler("theta[1:2]", type="sampler_slice_tempered", control={})
     with pytest.raises(nb.AptError, match="cannot use slice sampler on more than one target node"):  # APT:928
         nb.buildAPT(conf, Temps=[1, 2, 3])
     with pytest.raises(TypeError, match="conf must either be a nimbleModel or a MCMCconf"):  # APT:252
         nb.buildAPT("not a conf", Temps=[1, 2])
+
+
+def test_multinomial_sampler_lowers_and_setup_checks():
+    """sampler_RW_multinomial_tempered (APT:1005-1145): lowering of a dmulti target and the setup code's checks."""
+    spec = models.multinomial_latent()
+    apt = build_engine(spec, compileOnly=True)
+    src = apt.lowered_source()
+    assert "apt::multinomial_update<Model, S0>" in src and "apt::dmulti_log<4>" in src and "NTOTAL = 30" in src
+    assert "blk_keep(int i) { return i == 0 ||" in src  # sampler$reset() leaves u alone (APT:1133-1142)
+    assert os.path.exists(apt.modulePath)
+
+    def bad(samplers, **kw):
+        b = dict(spec)
+        b["samplers"] = samplers
+        return build_engine(b, compileOnly=True, **kw)
+    with pytest.raises(ValueError, match="unknown control option"):
+        bad([dict(target="x[1:4]", type="sampler_RW_multinomial_tempered", control=dict(temperPriors=True))])
+    with pytest.raises(nb.AptError, match="useTempering unspecified in sampler_RW_multinomial_tempered"):  # APT:1015
+        bad([dict(target="x[1:4]", type="sampler_RW_multinomial_tempered", control={})])
+    with pytest.raises(nb.AptError, match="can only use RW_multinomial sampler for multinomial distributions"):  # APT:1046
+        bad([dict(target="a", type="sampler_RW_multinomial_tempered", control=dict(useTempering=True))])
+    with pytest.raises(nb.AptError, match="adaptInterval < 100 is not recommended"):  # APT:1048
+        bad([dict(target="x[1:4]", type="sampler_RW_multinomial_tempered", control=dict(useTempering=True, adaptInterval=50))])
+    with pytest.raises(nb.AptError, match="whole multinomial node"):
+        bad([dict(target="x[1:3]", type="sampler_RW_multinomial_tempered", control=dict(useTempering=True))])
+    with pytest.raises(nb.AptError, match="grid engine: sampler_RW_multinomial_tempered is not supported"):
+        bad(spec["samplers"], engine=2)
 
 
 def test_demo_model_lowers_with_slice_sampler():

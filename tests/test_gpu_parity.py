@@ -28,6 +28,8 @@ SMALL = {
     # the reference's demo model (demo/APT_demo.R:83-92,173-177): dcat + dexp, a discrete node sampled by
     # sampler_slice_tempered, elements of constant arrays selected by that node, scalar + block RW samplers
     "demo": lambda: models.demo_wrong(),
+    # sampler_RW_multinomial_tempered (APT:1005-1145) on a latent dmulti node + a log-scale scalar sampler
+    "multinom": lambda: models.multinomial_latent(),
     "mixed": lambda: models.mixed_dists(),  # dbinom(size>1) dpois dgamma dbeta dexp dunif dnorm(tau) + all sampler options
 }
 BUILD_KW = {"c4cluster": dict(clusterCtas=4, lanesPerChain=32), "c3grid": dict(engine=2), "c3tile16": dict(engine=2), "c3tile4": dict(engine=2)}
@@ -49,6 +51,13 @@ def test_logprob_matches_oracle(name):
         states[:, 0] = rng.integers(1, 11, size=states.shape[0])  # k inside its support ...
         states[:3, 0] = [0.0, 11.0, 2.5]                           # ... and outside (dcat: -Inf on both sides)
         states[:, 2] = np.abs(states[:, 2]) + 0.05                 # sigma0 > 0
+    if name == "multinom":
+        states[:, :4] = rng.multinomial(30, [0.25] * 4, size=states.shape[0])  # compositions of N ...
+        states[0, :4] = [30.0, 0.0, 0.0, 0.0]
+        states[1, :4] = [10.0, 10.0, 5.0, 4.0]    # ... sum(x) != size, a non-integer and a negative cell: -Inf on both sides
+        states[2, :4] = [7.5, 7.5, 7.0, 8.0]
+        states[3, :4] = [-1.0, 11.0, 10.0, 10.0]
+        states[:, 4] = np.abs(states[:, 4]) + 0.05
     if name == "mixed":
         states = np.abs(states) + 0.05
         states[:, 0] = np.clip(states[:, 0], 0.02, 0.98)  # p in (0,1)
@@ -99,3 +108,7 @@ def test_decisions_bit_identical(name, inject):
         for k in range(eng.nTemps):
             for s in range(sc.shape[1]):
                 assert np.isclose(sc[k, s], orc.scale(l, k, s), rtol=1e-9)
+        if name == "multinom":  # u, timesRan ... RescaleThreshold of every rung (APT:1029-1040), adapted four times
+            bs = eng.blockState(l)
+            for k in range(eng.nTemps):
+                np.testing.assert_allclose(bs[k, :1 + 8 * 16], orc.multinomialState(l, k, 0, 4), rtol=1e-9, atol=0)

@@ -123,3 +123,39 @@ def test_dcat_unnormalised_and_edges():
     for x in (0.0, 6.0, -1.0, 2.5):
         assert L.apt_dcat_log(x, pp, 5) == -np.inf
     assert np.isnan(L.apt_dcat_log(float("nan"), pp, 5))
+
+
+def test_dmulti_and_rbinom_inversion():
+    """nimble's dmulti (target of sampler_RW_multinomial_tempered, APT:1046) against scipy; rbinom by inversion of one
+    uniform (include/aptb200.h) against the quantile function."""
+    import ctypes as C
+    from scipy import stats
+    L = lib()
+    dp = C.POINTER(C.c_double)
+    rng = np.random.default_rng(3)
+    for K in (2, 4, 9):
+        p = rng.random(K) + 0.05
+        for n in (0, 1, 7, 60):
+            x = rng.multinomial(n, p / p.sum()).astype(float)
+            got = L.apt_dmulti_log(x.ctypes.data_as(dp), p.ctypes.data_as(dp), K, float(n))  # unnormalised prob
+            assert close(got, stats.multinomial.logpmf(x, n, p / p.sum()), rtol=1e-12, atol=1e-12)
+            if n:
+                assert L.apt_dmulti_log(x.ctypes.data_as(dp), p.ctypes.data_as(dp), K, float(n + 1)) == -np.inf
+        x = np.array([1.5] + [0.0] * (K - 1))
+        assert L.apt_dmulti_log(x.ctypes.data_as(dp), p.ctypes.data_as(dp), K, 1.5) == -np.inf
+    p0 = np.array([0.0, 1.0, 1.0])
+    x0 = np.array([0.0, 2.0, 3.0])
+    assert close(L.apt_dmulti_log(x0.ctypes.data_as(dp), p0.ctypes.data_as(dp), 3, 5.0),
+                 stats.multinomial.logpmf(x0, 5, p0 / 2), rtol=1e-12, atol=1e-12)
+    for n in (1, 5, 37, 400, 1000):
+        for pr in (0.003, 0.2, 0.5, 0.77, 0.999):
+            u = rng.random(200)
+            got = np.array([L.apt_rbinom_inv(float(n), pr, ui) for ui in u])
+            # prob > 0.5: the walk runs on n - X ~ Binom(n, 1 - prob) (fewer steps) and n minus its quantile is returned
+            q, walked = (1 - pr, n - got) if pr > 0.5 else (pr, got)
+            ref = stats.binom.ppf(u, n, q) if pr <= 0.5 else n - stats.binom.ppf(u, n, q)
+            cdf_lo = stats.binom.cdf(walked - 1, n, q)
+            cdf_hi = stats.binom.cdf(walked, n, q)
+            near_edge = (np.abs(u - cdf_lo) < 1e-9) | (np.abs(u - cdf_hi) < 1e-9)
+            assert np.all((got == ref) | near_edge), (n, pr)
+    assert L.apt_rbinom_inv(0.0, 0.3, 0.5) == 0.0 and L.apt_rbinom_inv(9.0, 1.0, 0.5) == 9.0 and L.apt_rbinom_inv(9.0, 0.0, 0.5) == 0.0

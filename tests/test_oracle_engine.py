@@ -100,6 +100,53 @@ def test_demo_model_slice_sampler_exact_posterior():
         build_oracle(bad)
 
 
+def test_multinomial_sampler_exact_posterior_and_reference_quirk():
+    """sampler_RW_multinomial_tempered (APT:1005-1145) on a latent dmulti node whose posterior is enumerated exactly
+    (models.multinomial_latent_posterior).  With the exact reverse proposal (test-only switch) the restatement
+    reproduces the posterior; restated as the reference has it (APT:1093-1095: pRevSwap computed from x_to + 2 nSwap)
+    the stationary law is measurably off, which is what parity with the reference means for this sampler."""
+    from oracle.oracle import lib
+    spec = models.multinomial_latent()
+    ex, ea = models.multinomial_latent_posterior(spec)
+    exact = np.append(ex, ea)
+    L, niter, burn = 32, 10000, 1000
+    z = {}
+    for mode in (1, 0):
+        lib().orc_set_multinomial_exact_reverse(mode)
+        try:
+            o = build_oracle(spec, nLadders=L)
+            o.run(niter, nthreads=8)
+        finally:
+            lib().orc_set_multinomial_exact_reverse(0)
+        means = np.zeros((L, 5))
+        for l in range(L):
+            S = o.samples(l)[burn:]
+            x = S[:, :4]
+            assert np.all(x == np.floor(x)) and x.min() >= 0 and np.all(x.sum(axis=1) == 30)  # moves keep sum(x) = Ntotal
+            means[l] = S.mean(axis=0)
+        mean, mcse = means.mean(axis=0), means.std(axis=0, ddof=1) / np.sqrt(L)
+        z[mode] = (mean - exact) / mcse
+        st = o.multinomialState(0, 0, 0, 4)
+        u, EN = st[0], st[1 + 5 * 16:1 + 6 * 16].reshape(4, 4, order="F")
+        assert 0 <= u <= np.pi and np.allclose(EN, EN.T) and EN.min() >= 1 and EN.max() <= 30 and EN.max() > 1  # APT:1108-1125
+    assert np.all(np.abs(z[1]) <= 4), z[1]
+    assert np.abs(z[0]).max() > 6, z[0]  # the reference's proposal ratio leaves a bias far outside Monte-Carlo error
+
+
+def test_multinomial_sampler_setup_checks():
+    spec = models.multinomial_latent()
+    bad = dict(spec)
+    bad["samplers"] = [dict(target="x[1:4]", type="sampler_RW_multinomial_tempered", control={})]
+    with pytest.raises(ValueError, match="useTempering unspecified"):  # APT:1015
+        build_oracle(bad)
+    bad["samplers"] = [dict(target="a", type="sampler_RW_multinomial_tempered", control=dict(useTempering=True))]
+    with pytest.raises(ValueError, match="multinomial distributions"):  # APT:1046
+        build_oracle(bad)
+    bad["samplers"] = [dict(target="x[1:4]", type="sampler_RW_multinomial_tempered", control=dict(useTempering=True, adaptInterval=50))]
+    with pytest.raises(ValueError, match="adaptInterval < 100"):  # APT:1048
+        build_oracle(bad)
+
+
 def test_sampler_validation_errors():
     spec = models.c2_mixture(K=4)
     bad = dict(spec)
