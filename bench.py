@@ -12,6 +12,7 @@ process at N=1 and reported as `roofline_c3`.
 
 value     = tempered MH updates / s over all GPUs, device time (CUDA events on the engine's stream, max over ranks)
 e2e       = the same through the public API with HOST buffers: data + inits uploaded, run, mvSamples fetched to host
+            (N > 1: every rank's traces gathered over NCCL to rank 0 and copied to its host memory, inside the timed region)
 roofline  = dominant kernel of the timed region; for c2 the kernel is FP64-pipe bound, so the
             roofline is flop-based against the FP64 FMA peak measured live; roofline_c3 is the HBM one.
 --impl reference times the CPU oracle (restated reference, NOT nimble itself: R/nimble are absent).
@@ -285,7 +286,7 @@ def main():
     nmon = len(eng.monitorNames)
     rows = args.steps // thin
     pinned = None
-    if dist is not None:  # page-locked destination of the gathered traces, allocated once outside the timed region
+    if dist is not None and rank == 0:  # page-locked destination of the gathered traces, allocated once outside the timed region
         import torch
         pinned = torch.empty(world * L * rows * nmon, dtype=torch.float64, pin_memory=True).numpy()
 
@@ -293,13 +294,17 @@ def main():
         eng.setData("y", y)                      # H2D: observations
         eng.setInits(th0)                        # H2D: initial values
         eng.run(steps, thin=thin)                # reset=TRUE run from the uploaded state
-        if dist is not None:                     # NCCL all-gather of every rank's traces, then D2H into pinned host memory
-            r_ = steps // thin
-            allbuf = pinned[:world * L * r_ * nmon]
+        if dist is not None:                     # NCCL gather of every rank's traces to rank 0 (the process that hands them to
+            r_ = steps // thin                   # the user), one D2H into pinned host memory there
             got = C.c_int64()
-            _lib.check(_lib.lib().apt_comm_allgather_samples(eng._h, 0, allbuf.ctypes.data_as(C.POINTER(C.c_double)), allbuf.size, C.byref(got)))
-            sa = allbuf.reshape(world * L, r_, nmon)
-            return sa[rank * L:(rank + 1) * L], sa
+            if rank == 0:
+                allbuf = pinned[:world * L * r_ * nmon]
+                _lib.check(_lib.lib().apt_comm_gather_samples(eng._h, 0, 0, allbuf.ctypes.data_as(C.POINTER(C.c_double)), allbuf.size, C.byref(got)))
+                assert got.value == allbuf.size
+                sa = allbuf.reshape(world * L, r_, nmon)
+                return sa[:L], sa
+            _lib.check(_lib.lib().apt_comm_gather_samples(eng._h, 0, 0, None, 0, C.byref(got)))
+            return None, None
         sm = eng.mvSamples.matrix(-1)            # D2H: thinned traces of every local ladder
         return sm, sm
 
@@ -309,6 +314,9 @@ def main():
     samples, samples_all = e2e_once(args.steps)
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     barrier()
+    if samples is None:  # ranks other than 0: own traces for the pooled statistic below, outside the timed region
+        samples = eng.mvSamples.matrix(-1)
+        samples_all = samples
     h2d = (y.nbytes + th0.nbytes) * world
     d2h = samples_all.nbytes
     burn = samples.shape[1] // 4

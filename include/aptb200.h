@@ -226,6 +226,10 @@ int apt_comm_unique_id(unsigned char id_out[128]);
 int apt_comm_init(apt_engine* e, int world_size, int rank, const unsigned char unique_id[128]);
 /* all-gather of mvSamples over ranks: out [world][L][rows][n_monitors] on every rank (host memory) */
 int apt_comm_allgather_samples(apt_engine* e, int what, double* out, int64_t capacity, int64_t* n_written);
+/* gather of mvSamples to ONE rank (grouped ncclSend / ncclRecv over NVLink, one device-to-host copy on the root):
+ * out [world][L][rows][n_monitors] on rank `root` only (n_written = 0 and out untouched elsewhere).  The reference's
+ * user reads as.matrix(cAPT$mvSamples) in one R session (vignette:141), i.e. on one host process. */
+int apt_comm_gather_samples(apt_engine* e, int what, int root, double* out, int64_t capacity, int64_t* n_written);
 /* sum-all-reduce of a small host vector of pooled statistics (moments, ESS accumulators, swap counts) */
 int apt_comm_allreduce_sum(apt_engine* e, double* inout, int64_t n);
 int apt_comm_finalize(apt_engine* e);

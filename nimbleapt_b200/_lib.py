@@ -43,7 +43,7 @@ EXPORTS = ["apt_last_error", "apt_version", "apt_sampler_control_default", "apt_
            "apt_model_add_sampler", "apt_model_remove_samplers", "apt_model_set_monitors", "apt_model_set_thin",
            "apt_model_names", "apt_model_lower", "apt_model_compile", "apt_build", "apt_free", "apt_run", "apt_info", "apt_get",
            "apt_get_timing", "apt_logprob", "apt_waic", "apt_set_inits", "apt_set_array", "apt_comm_unique_id", "apt_comm_init",
-           "apt_comm_allgather_samples", "apt_comm_allreduce_sum", "apt_comm_finalize"]
+           "apt_comm_allgather_samples", "apt_comm_gather_samples", "apt_comm_allreduce_sum", "apt_comm_finalize"]
 
 _lib = None
 
@@ -86,6 +86,7 @@ def lib():
     L.apt_comm_unique_id.argtypes = [C.POINTER(C.c_ubyte)]
     L.apt_comm_init.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_ubyte)]
     L.apt_comm_allgather_samples.argtypes = [vp, C.c_int, dp, C.c_int64, C.POINTER(C.c_int64)]
+    L.apt_comm_gather_samples.argtypes = [vp, C.c_int, C.c_int, dp, C.c_int64, C.POINTER(C.c_int64)]
     L.apt_comm_allreduce_sum.argtypes = [vp, dp, C.c_int64]
     L.apt_comm_finalize.argtypes = [vp]
     _lib = L

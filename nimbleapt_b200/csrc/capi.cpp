@@ -395,6 +395,10 @@ struct NcclFns {
     int (*CommDestroy)(void*);
     int (*AllGather)(const void*, void*, size_t, int, void*, void*);
     int (*AllReduce)(const void*, void*, size_t, int, int, void*, void*);
+    int (*Send)(const void*, size_t, int, int, void*, void*);
+    int (*Recv)(void*, size_t, int, int, void*, void*);
+    int (*GroupStart)(void);
+    int (*GroupEnd)(void);
     const char* (*GetErrorString)(int);
 };
 static NcclFns g_nccl{};
@@ -429,6 +433,10 @@ static void load_nccl() {
     g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))s("ncclCommDestroy");
     g_nccl.AllGather = (decltype(g_nccl.AllGather))s("ncclAllGather");
     g_nccl.AllReduce = (decltype(g_nccl.AllReduce))s("ncclAllReduce");
+    g_nccl.Send = (decltype(g_nccl.Send))s("ncclSend");
+    g_nccl.Recv = (decltype(g_nccl.Recv))s("ncclRecv");
+    g_nccl.GroupStart = (decltype(g_nccl.GroupStart))s("ncclGroupStart");
+    g_nccl.GroupEnd = (decltype(g_nccl.GroupEnd))s("ncclGroupEnd");
     g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))s("ncclGetErrorString");
     const char* rts[] = {"libcudart.so.12", "libcudart.so"};
     for (auto n : rts) {
@@ -503,6 +511,49 @@ int apt_comm_allgather_samples(apt_engine* e, int what, double* out, int64_t cap
     }
     NCCL_OK(g_nccl.AllGather(dptr, e->gather_buf, (size_t)n_local, 8 /* ncclFloat64 */, e->comm, stream));
     RT_OK(g_rt.MemcpyAsync(out, e->gather_buf, (size_t)total * 8, 2 /* D2H */, stream));
+    RT_OK(g_rt.StreamSynchronize(stream));
+    if (n_written) *n_written = total;
+    API_END
+}
+
+// Gather to ONE rank: the host process that hands results to the user (the reference's user sits in one R session)
+// is the only one that needs every rank's traces in host memory.  With the all-gather above every rank copies
+// world x its own share over PCIe into the same host memory at the same time, which is what limited the end-to-end
+// figure at 8 GPUs; here the other ranks only send their device-resident trace over NVLink (grouped ncclSend/ncclRecv)
+// and the device-to-host copy happens once.
+int apt_comm_gather_samples(apt_engine* e, int what, int root, double* out, int64_t capacity, int64_t* n_written) {
+    API_BEGIN
+    if (!e->comm) throw Error("apt_comm_init has not been called");
+    if (root < 0 || root >= e->world) throw Error("root is not a rank of the communicator");
+    RT_OK(g_rt.SetDevice(e->device));
+    if (!e->fn.device_ptr) throw Error("module lacks aptmod_device_ptr");
+    void* dptr = nullptr; int64_t n_local = 0; void* stream = nullptr;
+    if (e->fn.device_ptr(e->mod, what, &dptr, &n_local, &stream)) throw Error("trace not available on the device");
+    if (n_written) *n_written = 0;
+    if (e->rank != root) {
+        NCCL_OK(g_nccl.Send(dptr, (size_t)n_local, 8 /* ncclFloat64 */, root, e->comm, stream));
+        RT_OK(g_rt.StreamSynchronize(stream));
+        return 0;
+    }
+    const int64_t total = n_local * e->world;
+    if (total > capacity) throw Error("output buffer too small");
+    if ((size_t)total * 8 > e->gather_cap) {
+        if (e->gather_buf) g_rt.Free(e->gather_buf);
+        e->gather_buf = nullptr; e->gather_cap = 0;
+        RT_OK(g_rt.Malloc(&e->gather_buf, (size_t)total * 8));
+        e->gather_cap = (size_t)total * 8;
+    }
+    // the root's own share goes straight to the caller's buffer while the peers' shares arrive over NVLink
+    RT_OK(g_rt.MemcpyAsync(out + (size_t)root * n_local, dptr, (size_t)n_local * 8, 2 /* D2H */, stream));
+    NCCL_OK(g_nccl.GroupStart());
+    for (int r = 0; r < e->world; r++)
+        if (r != root)
+            NCCL_OK(g_nccl.Recv((double*)e->gather_buf + (size_t)r * n_local, (size_t)n_local, 8, r, e->comm, stream));
+    NCCL_OK(g_nccl.GroupEnd());
+    if (root > 0) RT_OK(g_rt.MemcpyAsync(out, e->gather_buf, (size_t)root * n_local * 8, 2, stream));
+    if (root + 1 < e->world)
+        RT_OK(g_rt.MemcpyAsync(out + (size_t)(root + 1) * n_local, (double*)e->gather_buf + (size_t)(root + 1) * n_local,
+                               (size_t)(e->world - root - 1) * n_local * 8, 2, stream));
     RT_OK(g_rt.StreamSynchronize(stream));
     if (n_written) *n_written = total;
     API_END
