@@ -286,7 +286,7 @@ def main():
     nmon = len(eng.monitorNames)
     rows = args.steps // thin
     pinned = None
-    if dist is not None and rank == 0:  # page-locked destination of the gathered traces, allocated once outside the timed region
+    if rank == 0:  # page-locked destination of the (gathered) traces, allocated once outside the timed region
         import torch
         pinned = torch.empty(world * L * rows * nmon, dtype=torch.float64, pin_memory=True).numpy()
 
@@ -305,7 +305,7 @@ def main():
                 return sa[:L], sa
             _lib.check(_lib.lib().apt_comm_gather_samples(eng._h, 0, 0, None, 0, C.byref(got)))
             return None, None
-        sm = eng.mvSamples.matrix(-1)            # D2H: thinned traces of every local ladder
+        sm = eng.mvSamples.matrix(-1, out=pinned[:L * (steps // thin) * nmon])  # D2H: thinned traces of every local ladder
         return sm, sm
 
     e2e_once(args.steps)  # untimed warm-up of the same call sequence at the same size (first NCCL collective sets up its channels, trace and gather buffers reach their final size)

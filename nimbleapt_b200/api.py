@@ -139,8 +139,11 @@ class _Samples:
     def __init__(self, apt, what, names):
         self._apt, self._what, self.names = apt, what, names
 
-    def matrix(self, ladder=0):
-        return self._apt._get_trace(self._what, ladder, len(self.names))
+    def matrix(self, ladder=0, out=None):
+        """as.matrix(cAPT$mvSamples) of one ladder ([rows, monitors]) or of all local ladders (ladder = -1:
+        [ladders, rows, monitors]).  `out`: optional caller-allocated flat float64 destination (the C ABI always
+        writes into caller-allocated memory; page-locked memory makes the device-to-host copy several times faster)."""
+        return self._apt._get_trace(self._what, ladder, len(self.names), out)
 
     def __array__(self, dtype=None, copy=None):
         return self.matrix(0)
@@ -257,16 +260,20 @@ class APT:
     def info(self, what):
         return int(lib().apt_info(self._h, what))
 
-    def _get(self, what, ladder, n):
-        out = np.empty(max(int(n), 1), dtype=np.float64)
+    def _get(self, what, ladder, n, out=None):
+        if out is None:
+            out = np.empty(max(int(n), 1), dtype=np.float64)
+        else:  # caller-allocated destination (e.g. page-locked memory): flat float64, at least n elements
+            if out.dtype != np.float64 or not out.flags.c_contiguous or out.ndim != 1 or out.size < n:
+                raise ValueError("out must be a flat, contiguous float64 array of at least %d elements" % n)
         got = C.c_int64()
         check(lib().apt_get(self._h, what, ladder, _dp(out), int(n), C.byref(got)))
         return out[:got.value]
 
-    def _get_trace(self, what, ladder, cols):
+    def _get_trace(self, what, ladder, cols, out=None):
         rows = self.info(INFO_ROWS2 if what in (APT_SAMPLES2, APT_SAMPLES2_TMAX) else INFO_ROWS)
         nl = self.nLadders if ladder < 0 else 1
-        a = self._get(what, ladder, nl * rows * cols)
+        a = self._get(what, ladder, nl * rows * cols, out)
         return a.reshape((nl, rows, cols) if ladder < 0 else (rows, cols))
 
     def __del__(self):

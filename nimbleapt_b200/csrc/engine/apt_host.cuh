@@ -235,9 +235,13 @@ struct Engine {
 
     void set_model_theta(const double* th, int ladder) {
         APT_CUDA(cudaSetDevice(device));
-        for (int l = 0; l < L; l++)
-            if (ladder < 0 || ladder == l)
-                APT_CUDA(cudaMemcpyAsync(model_theta.p + (size_t)l * P, th, P * sizeof(double), cudaMemcpyHostToDevice, stream));
+        if (ladder >= L) throw ApiError{"ladder index out of range"};
+        APT_CUDA(cudaMemcpyAsync(model_theta.p + (size_t)std::max(ladder, 0) * P, th, P * sizeof(double), cudaMemcpyHostToDevice, stream));
+        if (ladder < 0 && L > 1) {
+            const size_t total = (size_t)L * P;
+            replicate_row0_kernel<<<(unsigned)std::min<size_t>((total + 255) / 256, 1184), 256, 0, stream>>>(model_theta.p, P, total);
+            APT_CUDA(cudaGetLastError());
+        }
         APT_CUDA(cudaStreamSynchronize(stream));
     }
     void set_array(int idx, const double* v, int64_t n) {

@@ -50,6 +50,37 @@ def test_continuation_and_thinning():
     np.testing.assert_allclose(eng.modelState(0), orc.rung_state(0, 0), rtol=1e-8)  # APT:548
 
 
+def test_set_inits_all_ladders_and_caller_allocated_traces():
+    """apt_set_inits with ladder = -1 puts the same values into every ladder's model (one upload, replicated on the
+    device), ladder = l only into that one; every rung of a ladder starts from them (APT:370-372).  Traces can be
+    fetched into caller-allocated memory (the C ABI never allocates for the caller)."""
+    spec = models.c2_mixture(n=20, K=8, tmax=200.0)
+    L = 5
+    eng = build_engine(spec, nLadders=L)
+    th = np.array([1.25, -0.5])
+    eng.setInits(th)
+    eng.run(0)
+    for l in range(L):
+        np.testing.assert_array_equal(eng.rungStates(l), np.tile(th, (8, 1)))
+    th3 = np.array([-2.0, 0.75])
+    eng.setInits(th3, ladder=3)
+    eng.run(0)
+    for l in range(L):
+        np.testing.assert_array_equal(eng.rungStates(l), np.tile(th3 if l == 3 else th, (8, 1)))
+        np.testing.assert_array_equal(eng.modelState(l), th3 if l == 3 else th)
+    with pytest.raises(nb.AptError, match="ladder index out of range"):
+        eng.setInits(th, ladder=L)
+    eng.run(60, thin=3)
+    ref = eng.mvSamples.matrix(-1)
+    buf = np.full(L * 20 * 2 + 7, np.nan)
+    got = eng.mvSamples.matrix(-1, out=buf)
+    assert got.shape == (L, 20, 2) and np.shares_memory(got, buf)
+    np.testing.assert_array_equal(got, ref)
+    assert np.all(np.isnan(buf[L * 20 * 2:]))
+    with pytest.raises(ValueError, match="out must be"):
+        eng.mvSamples.matrix(-1, out=np.empty(10))
+
+
 @pytest.mark.parametrize("variant", ["temperPriorsFalse", "logScale", "reflective", "scaleOnly", "nonAdaptive", "identityPropCov",
                                      "sliceContinuous", "slicePartial"])
 def test_control_options(variant):
