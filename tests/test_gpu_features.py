@@ -82,9 +82,35 @@ def test_set_inits_all_ladders_and_caller_allocated_traces():
 
 
 @pytest.mark.parametrize("variant", ["temperPriorsFalse", "logScale", "reflective", "scaleOnly", "nonAdaptive", "identityPropCov",
-                                     "sliceContinuous", "slicePartial"])
+                                     "sliceContinuous", "slicePartial", "multinomNoTempering", "multinomNonAdaptive",
+                                     "multinomInLoop"])
 def test_control_options(variant):
-    if variant == "sliceContinuous":
+    if variant in ("multinomNoTempering", "multinomNonAdaptive"):
+        # sampler_RW_multinomial_tempered with useTempering = FALSE (APT:1074) / adaptive = FALSE (APT:1077)
+        spec = dict(models.multinomial_latent(K=4))
+        ctl = dict(useTempering=variant != "multinomNoTempering", adaptive=variant != "multinomNonAdaptive", adaptInterval=100)
+        spec["samplers"] = [dict(spec["samplers"][0], control=ctl), spec["samplers"][1]]
+    elif variant == "multinomInLoop":
+        # two dmulti nodes declared in a loop (rows of a matrix), each with its own multinomial sampler: the prior term of a
+        # sampler is ONE instance of the declaration (a PARTIAL group), 5 cells, different totals
+        code = """{
+        for (g in 1:2) {
+            x[g, 1:5] ~ dmulti(prob = prob[1:5], size = N[g])
+            for (j in 1:5) {
+                y[g, j] ~ dpois(0.25 + a * x[g, j])
+            }
+        }
+        a ~ dgamma(shape = 4, rate = 4)
+        }"""
+        x0 = np.array([[4.0, 4.0, 4.0, 4.0, 4.0], [1.0, 2.0, 3.0, 4.0, 2.0]])
+        spec = dict(code=code, constants=dict(N=np.array([20.0, 12.0]), prob=np.array([0.3, 0.1, 0.2, 0.25, 0.15])),
+                    data=dict(y=np.array([[3.0, 0.0, 6.0, 9.0, 1.0], [0.0, 2.0, 5.0, 1.0, 4.0]])),
+                    inits=dict(x=x0, a=np.array(1.0)),
+                    samplers=[dict(target="x[1, 1:5]", type="sampler_RW_multinomial_tempered", control=dict(useTempering=True, adaptInterval=100)),
+                              dict(target="x[2, 1:5]", type="sampler_RW_multinomial_tempered", control=dict(useTempering=True, adaptInterval=100)),
+                              dict(target="a", type="sampler_RW_tempered", control=dict(temperPriors=True, log=True, scale=0.3))],
+                    monitors=["x", "a"], Temps=np.array([1.0, 2.0, 4.0]), ULT=1e6)
+    elif variant == "sliceContinuous":
         # sampler_slice_tempered on a continuous node (APT:898-995): stepping out, shrinkage, width adaptation
         spec = dict(models.c2_mixture(n=20, K=4, tmax=30.0))
         spec["samplers"] = [dict(target="theta[1]", type="sampler_slice_tempered", control=dict(width=0.5, sliceMaxSteps=10, adaptInterval=50)),
