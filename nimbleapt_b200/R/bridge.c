@@ -1,7 +1,9 @@
 /* bridge.c — thin .Call bridge between R and libaptb200.so (include/aptb200.h).
  *
- * NOT compiled in this image (no R headers: SURVEY.md F7); build where R exists with
+ * This image has no R; build where R exists with
  *     R CMD SHLIB bridge.c -I../../include -L.. -laptb200
+ * Here it is compiled (-Wall -Werror) and executed against tests/rstub/, a stand-in for the entry points of R's C
+ * API used below (tests/test_r_bridge.py: marshalling, errors, interrupts, finalizers; CPU and GPU).
  * Pure marshalling: every R object is allocated by R, the library only fills caller-allocated buffers, a non-zero
  * status becomes Rf_error() AFTER the library call has returned (no longjmp across the C ABI).
  * Replaces the external-pointer plumbing that nimble generates for a compiled buildAPT object
