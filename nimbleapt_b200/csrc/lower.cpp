@@ -1602,6 +1602,40 @@ struct Lowerer {
             }
         }
         out << "    }\n";
+        if (multi > 1 && unit_is_multi_capable(u)) {
+            // the same sums for CH chains at once: the data a lane loads for a row is used by CH dot products; per chain the
+            // terms are added in the order of eval()
+            out << "    template <int CH, class C> __device__ static __forceinline__ void eval_multi(const Data& D, const double* const (&thv)[CH], const C& c, double (&accv)[CH][NG]) {\n";
+            for (size_t g = 0; g < u.groups.size(); g++) {
+                const Group& gr = u.groups[g];
+                const CDecl& d = decls[gr.decl];
+                const std::string gs = std::to_string(g);
+                if (is_fused_bern(d) && d.ninst >= 512) {
+                    auto call = [&](const char* fn, const std::string& thname, const std::string& idx) {
+                        std::string cs = lp_call(gr.decl, idx);  // "lp_d<di>(D, th, ...)"
+                        cs.replace(0, 4, fn);
+                        const size_t pos = cs.find("(D, th,");
+                        if (pos == std::string::npos) throw Error("internal: unexpected lp_call form");
+                        cs.replace(pos, 7, "(D, " + thname + ",");
+                        return cs;
+                    };
+                    out << "      { int q = c.rank;\n";
+                    out << "        for (; q + 3 * C::W < " << d.ninst << "; q += 4 * C::W) {\n          double y_[4], e_[4][CH], a_[CH];\n";
+                    out << "          _Pragma(\"unroll\") for (int u_ = 0; u_ < 4; ++u_) {\n            y_[u_] = " << call("y_d", "thv[0]", "q + u_ * C::W") << ";\n";
+                    out << "            _Pragma(\"unroll\") for (int ch_ = 0; ch_ < CH; ++ch_) e_[u_][ch_] = " << call("eta_d", "thv[ch_]", "q + u_ * C::W") << ";\n          }\n";
+                    out << "          _Pragma(\"unroll\") for (int ch_ = 0; ch_ < CH; ++ch_) a_[ch_] = accv[ch_][" << gs << "];\n";
+                    out << "          apt::bern_logit_tile<4, CH>(y_, e_, a_);\n";
+                    out << "          _Pragma(\"unroll\") for (int ch_ = 0; ch_ < CH; ++ch_) accv[ch_][" << gs << "] = a_[ch_];\n        }\n";
+                    out << "        for (; q < " << d.ninst << "; q += C::W)\n          _Pragma(\"unroll\") for (int ch_ = 0; ch_ < CH; ++ch_) accv[ch_][" << gs << "] += "
+                        << call("lp_d", "thv[ch_]", "q") << ";\n      }\n";
+                } else {
+                    out << "      _Pragma(\"unroll\") for (int ch_ = 0; ch_ < CH; ++ch_) {\n        const double* th = thv[ch_];\n    ";
+                    emit_inst_loop(gr.decl, "accv[ch_][" + gs + "]");
+                    out << "      }\n";
+                }
+            }
+            out << "    }\n";
+        }
         emit_big_eval(u);
         out << "  };\n";
     }
@@ -1616,6 +1650,19 @@ struct Lowerer {
         long mx = 0;
         for (auto& g : u.groups) mx = std::max(mx, decls[g.decl].ninst);
         return mx >= 32L * W;
+    }
+    // Chains per tile (G::MULTI).  A ladder of many rungs whose only sampler has a large fused Bernoulli-logit likelihood
+    // over data shared by all rungs (config 5: 64 rungs x 1024 rows) lets each tile advance MULTI chains together: the
+    // rows of X a lane loads feed MULTI dot products (apt_engine.cuh::rw_update_multi), as in the grid engine's tiles.
+    int multi = 1;
+    bool unit_is_multi_capable(const Unit& u) {
+        if (u.count != 1 || u.kind > 1) return false;
+        int nbern = 0;
+        for (auto& g : u.groups) {
+            if (!g.full) return false;
+            if (is_fused_bern(decls[g.decl]) && decls[g.decl].ninst >= 512) nbern++;
+        }
+        return nbern == 1;
     }
     void choose_shape(int& W, int& tiles, int& teams, bool& smem_state) {
         long ndep = 1, items = K;
@@ -1638,6 +1685,26 @@ struct Lowerer {
         // several CTAs per SM overlap one ladder's swap phase with another's sweep; a ladder with thousands of
         // concurrent sampler-family members (config 4: 24 rungs x 1000 random effects) gets the widest CTA instead
         int maxthreads = opts.cta_threads > 0 ? opts.cta_threads : (items >= 4096 ? 1024 : 256);
+        multi = 1;
+        {
+            const int want = getenv("APTB200_MULTI") ? atoi(getenv("APTB200_MULTI")) : -1;  // -1: automatic, 0 / 1: off
+            const bool capable = units.size() == 1 && unit_is_multi_capable(units[0]) && opts.cluster_ctas <= 1 && opts.engine != 2;
+            if (capable && want != 0 && want != 1) {
+                const int ch = want > 1 ? want : 2;
+                // automatic: only when the rungs do not all fit into one CTA at the chosen width anyway
+                if ((ch == 2 || ch == 4) && K % ch == 0 && (want > 1 || (long)K * W > maxthreads)) multi = ch;
+            }
+            if (multi > 1) {
+                // measured on config 5 (64 rungs x 1024 rows, 2048 ladders; scratch/tune_c5_multi*.sh): 2 chains per tile,
+                // 8 lanes, 128-thread CTAs, 5 CTAs per SM (96 registers): 1.26e8 updates/s against 8.8e7 for one chain
+                // per 32-lane tile in 256-thread CTAs and 1.0e8 for the best single-chain shape; 4 chains per tile
+                // need 128 registers and lose more in occupancy than they save in loads (1.1e8)
+                items = K / multi;
+                if (opts.cta_threads <= 0) maxthreads = 128;
+                if (opts.lanes_per_chain <= 0)
+                    while (W > 8 && items * W > maxthreads) W /= 2;
+            }
+        }
         tiles = (int)std::min<long>(items, std::max(1, maxthreads / W));
         int team_threads = ((tiles * W + 31) / 32) * 32;
         teams = team_threads == 32 ? 4 : 1;
@@ -1792,6 +1859,7 @@ struct Lowerer {
                 if (teams != 1 && opts.cluster_ctas > 1) throw Error("cluster_ctas > 1 needs a CTA-wide team (lanes_per_chain * chains in flight > 32)");
                 cluster = opts.cluster_ctas;
             }
+            if (multi > 1) cluster = 1;
             if (cluster > 1) smem_state = false;
         }
         // ---- engine selection.  Grid engine: few chains, at least one declaration too large for one CTA per
@@ -1942,6 +2010,9 @@ struct Lowerer {
                 // chain at a time (K x W lanes could not cover the latency of thousands of terms per lane)
                 out << "    for (int k = 0; k < K; k++) apt::rw_update_wide<Model, S" << ui << ">(c, D, k, active);\n";
                 ui++;
+            } else if (multi > 1 && unit_is_multi_capable(units[ui])) {
+                out << "    if (active) for (int k = c.tile_id * MULTI; k < K; k += c.ntiles * MULTI) apt::rw_update_multi<Model, S" << ui << ", MULTI>(c, D, k);\n";
+                ui++;
             } else {
                 out << "    if (active) for (int k = c.tile_id; k < K; k += c.ntiles) {\n";
                 while (ui < units.size() && units[ui].count == 1 && !unit_is_wide(units[ui], cluster, tiles, W)) {
@@ -1982,16 +2053,17 @@ struct Lowerer {
             out << "  static constexpr bool HAS_LP_MON = " << (lpmon ? "true" : "false") << ";\n";
         }
         out << "  static constexpr int NARR = " << used_arrays.size() << ", NIARR = " << iarrays.size() << ", BLKSZ = " << BLKSZ << ", EMPSZ = " << EMPSZ << ";\n";
-        out << "  static constexpr int TILES_PER_LADDER = " << tiles << ", TEAMS_PER_CTA = " << teams << ", CLUSTER = " << (engine == 1 ? cluster : 1) << ";\n";
+        out << "  static constexpr int TILES_PER_LADDER = " << tiles << ", TEAMS_PER_CTA = " << teams << ", CLUSTER = " << (engine == 1 ? cluster : 1) << ", MULTI = " << multi << ";\n";
         {
             // resident CTAs per SM the ladder kernel is compiled for (register cap = 64K / (LADDER_MINB * CTA)): as many
             // as shared memory admits, but never fewer than 64 registers per thread
             const int team_threads = ((tiles * W + 31) / 32) * 32, cta = team_threads * teams;
             const bool logtab = team_threads != 32 && K <= 32;
             const long psize = logtab ? 2L * K * K : ((long)K * (K - 1) / 2 + 1) / 2 * 2;
-            const long team_bytes = ((7L * K + psize + (long)tiles * 2 * DMAX + (smem_state && engine == 1 ? (long)K * (P + ND) : 0)) * 8 + 2L * K * 4 + 15) / 16 * 16;
+            const long team_bytes = ((7L * K + psize + (long)tiles * multi * 2 * DMAX + (smem_state && engine == 1 ? (long)K * (P + ND) : 0)) * 8 + 2L * K * 4 + 15) / 16 * 16;
             long minb = 232448 / (team_bytes * teams + 1024);
             minb = std::max(1L, std::min(minb, (long)(1024 / cta)));
+            if (multi > 1) minb = std::min(minb, 5L);  // two chains per tile need ~96 registers
             if (const char* e = getenv("APTB200_LADDER_MINB")) minb = std::max(0, atoi(e));  // 0 = no register cap
             out << "  static constexpr int LADDER_MINB = " << minb << ";\n";
         }

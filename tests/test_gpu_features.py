@@ -240,6 +240,24 @@ def test_multinomial_sampler_posterior_and_reset():
     np.testing.assert_array_equal(bs[:, 1 + 7 * 16:1 + 8 * 16], 0.2)
 
 
+@pytest.mark.parametrize("multi", [0, 4])
+def test_multi_chain_tiles_switch(multi, monkeypatch):
+    """G::MULTI (chains advanced together by one tile, apt_engine.cuh::rw_update_multi): the automatic choice (2) is
+    covered by tests/test_gpu_parity.py[c5multi]; here the same model with the feature off and with 4 chains per tile,
+    each against the oracle (decisions bit-identical, traces, adapted scales and proposal covariances)."""
+    monkeypatch.setenv("APTB200_MULTI", str(multi))
+    spec = models.c5_small_logistic(N=602, p=6, K=16)
+    eng, orc = _both(spec, L=2)
+    assert ("MULTI = %d" % max(multi, 1)) in eng.lowered_source()
+    _run_both(eng, orc, 450, 9)
+    for l in range(2):
+        np.testing.assert_allclose(eng.mvSamples.matrix(l), orc.samples(l), rtol=1e-8, atol=1e-10)
+        bs = eng.blockState(l)
+        for k in range(16):
+            assert np.isclose(eng.scales(l)[k, 0], orc.scale(l, k, 0), rtol=1e-9)
+            np.testing.assert_allclose(bs[k, :36].reshape(6, 6, order="F"), orc.propCov(l, k, 0, 6), rtol=1e-7, atol=1e-12)
+
+
 def test_c4_family_medium():
     """Mixed scalar family / block / log-scale samplers at a size where the family spans several tiles."""
     spec = models.c4_glmm(G=60, per=20, K=6)

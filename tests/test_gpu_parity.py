@@ -16,6 +16,9 @@ SMALL = {
     "c1": lambda: models.c1_vignette(nObs=100, K=8),
     "c2": lambda: models.c2_mixture(n=20, K=32),
     "c5": lambda: models.c5_small_logistic(N=256, p=8, K=8),
+    # many rungs over shared data: each tile advances 4 chains together through one pass over the rows (G::MULTI,
+    # apt_engine.cuh::rw_update_multi); N is not a multiple of the 4-row blocks, so the remainder path runs too
+    "c5multi": lambda: models.c5_small_logistic(N=602, p=6, K=16),
     "c4": lambda: models.c4_glmm(G=20, per=10, K=4),
     "c3s": lambda: models.logistic(2000, 5, 4),
     "c3grid": lambda: models.logistic(2000, 5, 4),  # same model through the grid-wide engine (engine = 2)
