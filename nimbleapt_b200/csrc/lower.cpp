@@ -1695,7 +1695,7 @@ struct Lowerer {
                 if ((ch == 2 || ch == 4) && K % ch == 0 && (want > 1 || (long)K * W > maxthreads)) multi = ch;
             }
             if (multi > 1) {
-                // measured on config 5 (64 rungs x 1024 rows, 2048 ladders; scratch/tune_c5_multi*.sh): 2 chains per tile,
+                // measured on config 5 (64 rungs x 1024 rows, 2048 ladders; tools/tune_c5_multi.sh): 2 chains per tile,
                 // 8 lanes, 128-thread CTAs, 5 CTAs per SM (96 registers): 1.26e8 updates/s against 8.8e7 for one chain
                 // per 32-lane tile in 256-thread CTAs and 1.0e8 for the best single-chain shape; 4 chains per tile
                 // need 128 registers and lose more in occupancy than they save in loads (1.1e8)
