@@ -1115,7 +1115,11 @@ struct Lowerer {
                     std::string ev = "e" + std::to_string(tmp_id++);
                     std::string A = gen_slice_elem(e->a[0], ev, env, la), B = gen_slice_elem(e->a[1], ev, env, lb);
                     if (la != lb) throw Error("inprod arguments have different lengths: " + to_string(e));
-                    return "[&]() { double s_ = 0.0;\n_Pragma(\"unroll 5\")\n for (int " + ev + " = 0; " + ev + " < " + std::to_string(la) + "; ++" + ev +
+                    // chains per tile: a short product is unrolled completely, so that the loads of the data row are common
+                    // subexpressions of the CH products eval_multi forms from it (config 5: 1.26e8 -> 1.6e8 updates/s; the
+                    // single-chain code, which holds 8 rows per lane in 64 registers, loses by it: 8.8e7 -> 6.6e7)
+                    const std::string unroll = (multi > 1 && la <= 16) ? "unroll" : "unroll 5";
+                    return "[&]() { double s_ = 0.0;\n_Pragma(\"" + unroll + "\")\n for (int " + ev + " = 0; " + ev + " < " + std::to_string(la) + "; ++" + ev +
                            ") s_ += " + A + " * " + B + "; return s_; }()";
                 }
                 if (e->name == "sum" && e->a.size() == 1) {
@@ -1696,13 +1700,13 @@ struct Lowerer {
             }
             if (multi > 1) {
                 // measured on config 5 (64 rungs x 1024 rows, 2048 ladders; tools/tune_c5_multi.sh): 2 chains per tile,
-                // 8 lanes, 128-thread CTAs, 5 CTAs per SM (96 registers): 1.26e8 updates/s against 8.8e7 for one chain
-                // per 32-lane tile in 256-thread CTAs and 1.0e8 for the best single-chain shape; 4 chains per tile
-                // need 128 registers and lose more in occupancy than they save in loads (1.1e8)
+                // 4 lanes, 128-thread CTAs (all 64 rungs in flight), 4 CTAs per SM (128 registers): 1.72e8 updates/s
+                // against 8.8e7 for one chain per 32-lane tile in 256-thread CTAs and 1.0e8 for the best single-chain
+                // shape; 4 chains per tile lose more in occupancy than they save in loads (1.4e8 at best)
                 items = K / multi;
                 if (opts.cta_threads <= 0) maxthreads = 128;
                 if (opts.lanes_per_chain <= 0)
-                    while (W > 8 && items * W > maxthreads) W /= 2;
+                    while (W > 4 && items * W > maxthreads) W /= 2;
             }
         }
         tiles = (int)std::min<long>(items, std::max(1, maxthreads / W));
@@ -2063,7 +2067,7 @@ struct Lowerer {
             const long team_bytes = ((7L * K + psize + (long)tiles * multi * 2 * DMAX + (smem_state && engine == 1 ? (long)K * (P + ND) : 0)) * 8 + 2L * K * 4 + 15) / 16 * 16;
             long minb = 232448 / (team_bytes * teams + 1024);
             minb = std::max(1L, std::min(minb, (long)(1024 / cta)));
-            if (multi > 1) minb = std::min(minb, 5L);  // two chains per tile need ~96 registers
+            if (multi > 1) minb = std::min(minb, (long)std::max(1, 512 / cta));  // two chains per tile: 128 registers
             if (const char* e = getenv("APTB200_LADDER_MINB")) minb = std::max(0, atoi(e));  // 0 = no register cap
             out << "  static constexpr int LADDER_MINB = " << minb << ";\n";
         }
