@@ -1927,6 +1927,7 @@ struct Lowerer {
             }
         }
 
+        if (engine == 2) multi = 1;  // chains per tile belong to the ladder-resident engine
         std::ostringstream body;
         std::swap(out, body);  // emit model body first to learn which arrays are used
         emit_lp_functions();

@@ -106,6 +106,25 @@ def test_multinomial_sampler_lowers_and_setup_checks():
         bad(spec["samplers"], engine=2)
 
 
+def test_chains_per_tile_lowering(monkeypatch):
+    """G::MULTI (lower.cpp::choose_shape): many rungs over a shared Bernoulli-logit likelihood -> two chains per tile,
+    generated eval_multi with the short inner product unrolled completely; off by switch, off for few rungs, off for the
+    grid engine."""
+    spec = models.c5_small_logistic(N=602, p=6, K=16)
+    src = build_engine(spec, nLadders=4, compileOnly=True).lowered_source()
+    assert "MULTI = 2" in src and "apt::rw_update_multi<Model, S0, MULTI>(c, D, k)" in src
+    assert "eval_multi(const Data& D, const double* const (&thv)[CH]" in src and "apt::bern_logit_tile<4, CH>(y_, e_, a_)" in src
+    assert '_Pragma("unroll")\n for (int e' in src and '_Pragma("unroll 5")' not in src
+    monkeypatch.setenv("APTB200_MULTI", "0")
+    src0 = build_engine(spec, nLadders=4, compileOnly=True).lowered_source()
+    assert "MULTI = 1" in src0 and "rw_update_multi" not in src0 and '_Pragma("unroll 5")' in src0
+    monkeypatch.delenv("APTB200_MULTI")
+    few = build_engine(models.c5_small_logistic(N=602, p=6, K=4), nLadders=64, compileOnly=True).lowered_source()
+    assert "MULTI = 1" in few  # 4 rungs x 32 lanes fit one CTA: nothing to share
+    grid = build_engine(spec, nLadders=1, compileOnly=True, engine=2).lowered_source()
+    assert "MULTI = 1" in grid and "ENGINE = 2" in grid
+
+
 def test_demo_model_lowers_with_slice_sampler():
     """demo/APT_demo.R:83-92,173-177: dcat, a constant array indexed by the sampled node, sampler_slice_tempered."""
     apt = build_engine(models.demo_wrong(), compileOnly=True)
