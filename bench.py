@@ -293,6 +293,13 @@ def main():
     def e2e_once(steps):
         eng.setData("y", y)                      # H2D: observations
         eng.setInits(th0)                        # H2D: initial values
+        if dist is None:
+            # one process: the thinned traces are copied back to page-locked host memory asynchronously, piece by piece,
+            # while the run is still sampling (apt_run_args.samples_out); complete when run() returns
+            out = pinned[:L * (steps // thin) * nmon]
+            eng.run(steps, thin=thin, samplesOut=out)
+            sm = out.reshape(L, steps // thin, nmon)
+            return sm, sm
         eng.run(steps, thin=thin)                # reset=TRUE run from the uploaded state
         if dist is not None:                     # NCCL gather of every rank's traces to rank 0 (the process that hands them to
             r_ = steps // thin                   # the user), one D2H into pinned host memory there
@@ -305,8 +312,6 @@ def main():
                 return sa[:L], sa
             _lib.check(_lib.lib().apt_comm_gather_samples(eng._h, 0, 0, None, 0, C.byref(got)))
             return None, None
-        sm = eng.mvSamples.matrix(-1, out=pinned[:L * (steps // thin) * nmon])  # D2H: thinned traces of every local ladder
-        return sm, sm
 
     e2e_once(args.steps)  # untimed warm-up of the same call sequence at the same size (first NCCL collective sets up its channels, trace and gather buffers reach their final size)
     barrier()

@@ -127,6 +127,13 @@ typedef struct {
     const double* inject_normals;  /* test hook [niter][L][K][NU][DMAX] */
     const double* inject_accept_u; /* test hook [niter][L][K][NU] */
     const double* inject_swap_u;   /* test hook [niter][L][K][2] */
+    /* asynchronous copy-back of the thinned output: when non-null, the rows of mvSamples THIS run writes are copied
+     * into this host buffer, laid out [n_ladders][niter / thin][n_monitors], in pieces on a second stream while the
+     * next piece of the run is still sampling (the run is split into at least 4 launches); complete when apt_run
+     * returns.  Page-locked memory makes the copies truly asynchronous.  Rows of earlier runs (reset = FALSE) are not
+     * included; apt_get(APT_SAMPLES) still returns everything. */
+    double* samples_out;
+    int64_t samples_out_capacity;  /* in doubles */
 } apt_run_args;
 
 typedef struct {

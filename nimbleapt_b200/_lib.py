@@ -29,7 +29,8 @@ class RunArgs(C.Structure):
                 ("tuneTemper1", C.c_double), ("tuneTemper2", C.c_double), ("progressBar", C.c_int),
                 ("thin", C.c_int), ("thin2", C.c_int), ("should_abort", ABORT_FN), ("abort_arg", C.c_void_p),
                 ("iters_per_launch", C.c_int), ("inject_normals", C.POINTER(C.c_double)),
-                ("inject_accept_u", C.POINTER(C.c_double)), ("inject_swap_u", C.POINTER(C.c_double))]
+                ("inject_accept_u", C.POINTER(C.c_double)), ("inject_swap_u", C.POINTER(C.c_double)),
+                ("samples_out", C.POINTER(C.c_double)), ("samples_out_capacity", C.c_int64)]
 
 
 class Timing(C.Structure):

@@ -288,7 +288,7 @@ class APT:
     # ---- cAPT$run  (APT_functions.R:336-549)
     def run(self, niter, reset=True, resetMV=False, resetTempering=False, simulateAll=False, time=False,
             adaptTemps=True, printTemps=False, tuneTemper1=10, tuneTemper2=1, progressBar=True, thin=-1, thin2=-1,
-            itersPerLaunch=0, _inject=None):
+            itersPerLaunch=0, samplesOut=None, _inject=None):
         ra = RunArgs()
         lib().apt_run_args_default(C.byref(ra))
         ra.niter, ra.reset, ra.resetMV, ra.resetTempering = int(niter), int(bool(reset)), int(bool(resetMV)), int(bool(resetTempering))
@@ -302,6 +302,13 @@ class APT:
                     a = np.ascontiguousarray(_inject[key], dtype=np.float64)
                     keep.append(a)
                     setattr(ra, field, _dp(a))
+        if samplesOut is not None:
+            # asynchronous copy-back (apt_run_args.samples_out): this run's rows of mvSamples, [ladders][niter / thin][monitors],
+            # arrive in the caller's flat float64 buffer piece by piece while the run is still sampling
+            if samplesOut.dtype != np.float64 or not samplesOut.flags.c_contiguous or samplesOut.ndim != 1:
+                raise ValueError("samplesOut must be a flat, contiguous float64 array")
+            ra.samples_out = _dp(samplesOut)
+            ra.samples_out_capacity = samplesOut.size
         check(lib().apt_run(self._h, C.byref(ra)))
 
     def getTimes(self):

@@ -302,6 +302,7 @@ int apt_run(apt_engine* e, const apt_run_args* args) {
     ra.thin = args->thin; ra.thin2 = args->thin2;
     ra.tabZ = args->inject_normals; ra.tabU = args->inject_accept_u; ra.tabS = args->inject_swap_u;
     ra.should_abort = args->should_abort; ra.abort_arg = args->abort_arg; ra.iters_per_launch = args->iters_per_launch;
+    ra.samples_out = args->samples_out; ra.samples_out_cap = args->samples_out_capacity;
     char err[2048] = {0};
     if (e->fn.run(e->mod, &ra, err, sizeof err)) throw Error(err);
     if (args->printTemps) {  // nimPrint(iter, " ", totalIters-1, " ", size_mvSamples, " ", size_mvSamples2, asRow(Temps))  APT:524

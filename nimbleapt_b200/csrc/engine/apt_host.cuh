@@ -102,6 +102,18 @@ struct Engine {
     double ULT = 1e6;
     int monitor_tmax = 1, record = 0, thin_conf = 1, thin2_conf = 1;
     cudaStream_t stream = nullptr;
+    // asynchronous copy-back of the rows a run writes (aptmod_run_args.samples_out): second stream, issued per launch chunk
+    cudaStream_t copy_stream = nullptr;
+    double* so_ptr = nullptr;
+    long long so_nr = 0, so_off = 0;
+    int so_thin = 1;
+    void copy_rows_async(long long it0, long long it1) {
+        if (!so_ptr) return;
+        const long long r0 = it0 / so_thin, r1 = it1 / so_thin;  // rows of this run written by iterations [it0, it1)
+        if (r1 <= r0) return;
+        APT_CUDA(cudaMemcpy2DAsync(so_ptr + (size_t)r0 * G::NMON, (size_t)so_nr * G::NMON * 8, samples.p + (size_t)(so_off + r0) * G::NMON,
+                                   (size_t)cap * G::NMON * 8, (size_t)(r1 - r0) * G::NMON * 8, L, cudaMemcpyDeviceToHost, copy_stream));
+    }
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::vector<DevBuf<double>> arrays;
     std::vector<DevBuf<int>> iarrays;
@@ -231,6 +243,7 @@ struct Engine {
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
         if (stream) cudaStreamDestroy(stream);
+        if (copy_stream) cudaStreamDestroy(copy_stream);
     }
 
     void set_model_theta(const double* th, int ladder) {
@@ -331,6 +344,14 @@ struct Engine {
         }
         if (nr > ttcap) { temptraj.alloc((size_t)L * nr * K); ttcap = nr; }
         rows = off + nr; rows2 = off2 + nr2; ttrows = nr;
+        so_ptr = (ra->samples_out && nr > 0 && G::NMON > 0) ? ra->samples_out : nullptr;
+        if (so_ptr) {
+            if ((long long)L * nr * G::NMON > ra->samples_out_cap) throw ApiError{"samples_out: buffer too small for n_ladders x (niter / thin) x n_monitors doubles"};
+            if (!copy_stream) APT_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+            so_nr = nr; so_off = off; so_thin = thin;
+        }
+        // with a host destination the run is split into at least 4 launches, so that copying a piece overlaps the next
+        const long long so_chunk = so_ptr ? std::max<long long>(thin, ((ra->niter + 3) / 4 + thin - 1) / thin * thin) : 0;
         refresh_lpd();
         // test hooks
         const size_t nz = (size_t)ra->niter * L * K * G::NU;
@@ -358,6 +379,7 @@ struct Engine {
             aborted = run_grid(a, ra);
         } else {
             long long chunk = ra->iters_per_launch > 0 ? ra->iters_per_launch : 4096;
+            if (so_chunk > 0 && ra->iters_per_launch <= 0) chunk = std::min(chunk, so_chunk);
             const int grid = (L + SH::TEAMS - 1) / SH::TEAMS;
             for (long long it0 = 0; it0 < ra->niter; it0 += chunk) {
                 if (ra->should_abort && ra->should_abort(ra->abort_arg)) { aborted = true; break; }
@@ -383,6 +405,7 @@ struct Engine {
                 timing.kernel_ms += ms; timing.main_kernel_ms += ms; timing.launches++; timing.main_launches++;
                 rngIter += (uint64_t)(a.it1 - a.it0);
                 totalIters += (a.it1 - a.it0);
+                copy_rows_async(a.it0, a.it1);
             }
         }
         // APT:548: the model is left parameterised with the T=1 state
@@ -390,6 +413,7 @@ struct Engine {
         APT_CUDA(cudaGetLastError());
         timing.launches++;
         APT_CUDA(cudaStreamSynchronize(stream));
+        if (so_ptr) { so_ptr = nullptr; APT_CUDA(cudaStreamSynchronize(copy_stream)); }
         launches_total += timing.launches;
         if (aborted) throw ApiError{"run interrupted by the caller"};
     }
@@ -448,6 +472,7 @@ struct Engine {
                 timing.kernel_ms += ms; timing.main_kernel_ms += ms; timing.launches += nl; timing.main_launches += nl - 1;
                 rngIter += (uint64_t)(it1 - it0);
                 totalIters += (it1 - it0);
+                copy_rows_async(it0, it1);
                 if (g.dbg) {
                     auto v = d2h(g_dbg.p, 80);
                     fprintf(stderr, "[aptb200] finishing CTA cycles: stream %lld cta-reduce+ticket %lld reduce %lld finish %lld ladder %lld propose %lld total %lld (delta CTA %lld)\n", v[6] - v[5], v[0] - v[6], v[1] - v[0], v[2] - v[1], v[3] - v[2], v[4] - v[3], v[4] - v[5], v[7]);

@@ -6,7 +6,7 @@
 #define APT_MODULE_ABI_H
 #include <stdint.h>
 
-#define APTMOD_ABI_VERSION 4
+#define APTMOD_ABI_VERSION 5
 
 #ifdef __cplusplus
 extern "C" {
@@ -44,6 +44,8 @@ typedef struct {
     int (*should_abort)(void*);    /* polled between kernel launches (APT_functions.R:415 checkInterrupt) */
     void* abort_arg;
     int iters_per_launch;          /* 0 = default */
+    double* samples_out;           /* host destination of this run's mvSamples rows [L][niter/thin][NMON], or null */
+    int64_t samples_out_cap;       /* doubles */
 } aptmod_run_args;
 
 enum {

@@ -81,6 +81,35 @@ def test_set_inits_all_ladders_and_caller_allocated_traces():
         eng.mvSamples.matrix(-1, out=np.empty(10))
 
 
+@pytest.mark.parametrize("engine", ["ladder", "grid"])
+def test_asynchronous_copy_back_of_samples(engine):
+    """apt_run_args.samples_out: the rows a run writes arrive in the caller's host buffer piece by piece on a second
+    stream while the run goes on; when run() returns they equal what apt_get(APT_SAMPLES) returns -- for launch chunks
+    that are not multiples of the thinning interval, for a continued run (only its own rows), on both engines."""
+    if engine == "ladder":
+        spec, L, kw = models.c2_mixture(n=20, K=8, tmax=200.0), 5, {}
+    else:
+        spec, L, kw = models.logistic(2000, 5, 4), 1, dict(engine=2)
+    eng = build_engine(spec, nLadders=L, **kw)
+    nmon = len(eng.monitorNames)
+    out = np.full(L * 57 * nmon + 3, np.nan)
+    eng.run(403, thin=7, samplesOut=out)                       # default: at least 4 launches
+    ref = eng.mvSamples.matrix(-1)
+    assert ref.shape == (L, 57, nmon) and eng.getTimes()["main_launches"] >= 4
+    np.testing.assert_array_equal(out[:L * 57 * nmon].reshape(L, 57, nmon), ref)
+    assert np.all(np.isnan(out[L * 57 * nmon:]))
+    out2 = np.full(L * 18 * nmon, np.nan)
+    eng.run(130, reset=False, thin=7, itersPerLaunch=10, samplesOut=out2)  # chunks of 10 iterations, rows every 7
+    full = eng.mvSamples.matrix(-1)
+    assert full.shape == (L, 57 + 18, nmon)
+    np.testing.assert_array_equal(out2.reshape(L, 18, nmon), full[:, 57:, :])
+    np.testing.assert_array_equal(full[:, :57, :], ref)
+    with pytest.raises(nb.AptError, match="samples_out: buffer too small"):
+        eng.run(70, thin=7, samplesOut=np.empty(L * 10 * nmon - 1))
+    with pytest.raises(ValueError, match="samplesOut must be"):
+        eng.run(70, thin=7, samplesOut=np.empty((L, 10 * nmon)))
+
+
 @pytest.mark.parametrize("variant", ["temperPriorsFalse", "logScale", "reflective", "scaleOnly", "nonAdaptive", "identityPropCov",
                                      "sliceContinuous", "slicePartial", "multinomNoTempering", "multinomNonAdaptive",
                                      "multinomInLoop"])
