@@ -287,6 +287,32 @@ def test_multi_chain_tiles_switch(multi, monkeypatch):
             np.testing.assert_allclose(bs[k, :36].reshape(6, 6, order="F"), orc.propCov(l, k, 0, 6), rtol=1e-7, atol=1e-12)
 
 
+_CHAIN = {}
+
+
+@pytest.mark.parametrize("variant", ["logfree", "literal"])
+def test_swap_chain_without_logs_decides_like_the_literal_expression(variant, monkeypatch):
+    """The proposal ratio of the swap move (APT:462) is formed from per-row log(1 / rowsum) instead of two logarithms per
+    proposal (apt_engine.cuh::ladder_step); -DAPT_CHAIN_LITERAL keeps the reference's expression.  Both kernels must take
+    the same 2.4 million swap decisions (partners and accept flags) and end in the same states, on an adapted 32-rung
+    ladder whose hot rungs sit on the uniform fallback (APT:571-573) and whose numerators underflow to 0."""
+    if variant == "literal":
+        monkeypatch.setenv("APTB200_EXTRA_NVCC_FLAGS", "-DAPT_CHAIN_LITERAL")
+    spec = models.c2_mixture(n=20, K=32)
+    L, niter = 25, 3000
+    eng = build_engine(spec, nLadders=L, record=True)
+    eng.run(niter, thin=10)
+    rec = np.stack([eng.swapRecord(l, niter) for l in range(L)])
+    assert rec.shape == (L, niter, 32)
+    _CHAIN[variant] = (rec, eng.mvSamples.matrix(-1), np.stack([eng.TempsLadder(l) for l in range(L)]))
+    if len(_CHAIN) == 2:
+        a, b = _CHAIN["logfree"], _CHAIN["literal"]
+        assert (a[0] >> 16).mean() > 0.05                      # swaps do get accepted
+        np.testing.assert_array_equal(a[0], b[0])
+        np.testing.assert_array_equal(a[1], b[1])
+        np.testing.assert_array_equal(a[2], b[2])
+
+
 def test_c4_family_medium():
     """Mixed scalar family / block / log-scale samplers at a size where the family spans several tiles."""
     spec = models.c4_glmm(G=60, per=20, K=6)
