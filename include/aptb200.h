@@ -178,6 +178,9 @@ enum {
 const char* apt_last_error(void);
 const char* apt_version(void);
 
+/* sizeof of the ABI structs as this library was compiled: 0 apt_sampler_control, 1 apt_build_opts, 2 apt_run_args, 3 apt_timing
+ * (a binding that mirrors the structs by hand -- ctypes, an FFI -- checks its own layout against these) */
+int64_t apt_abi_sizeof(int which);
 void apt_sampler_control_default(apt_sampler_control* c);
 void apt_build_opts_default(apt_build_opts* o);
 void apt_run_args_default(apt_run_args* a);

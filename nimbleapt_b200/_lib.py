@@ -39,7 +39,7 @@ class Timing(C.Structure):
 
 
 # every symbol include/aptb200.h declares
-EXPORTS = ["apt_last_error", "apt_version", "apt_sampler_control_default", "apt_build_opts_default",
+EXPORTS = ["apt_last_error", "apt_version", "apt_abi_sizeof", "apt_sampler_control_default", "apt_build_opts_default",
            "apt_run_args_default", "apt_model_create", "apt_model_free", "apt_model_set_array",
            "apt_model_add_sampler", "apt_model_remove_samplers", "apt_model_set_monitors", "apt_model_set_thin",
            "apt_model_names", "apt_model_lower", "apt_model_compile", "apt_build", "apt_free", "apt_run", "apt_info", "apt_get",
@@ -60,6 +60,13 @@ def lib():
     dp, vp = C.POINTER(C.c_double), C.c_void_p
     L.apt_last_error.restype = C.c_char_p
     L.apt_version.restype = C.c_char_p
+    L.apt_abi_sizeof.restype = C.c_int64
+    L.apt_abi_sizeof.argtypes = [C.c_int]
+    # the ctypes mirrors above must have the layout the library was compiled with
+    for which, cls in ((0, SamplerControl), (1, BuildOpts), (2, RunArgs), (3, Timing)):
+        if L.apt_abi_sizeof(which) != C.sizeof(cls):
+            raise AptError("ABI mismatch: %s is %d bytes here, %d in libaptb200.so (rebuild nimbleapt_b200/csrc)"
+                           % (cls.__name__, C.sizeof(cls), L.apt_abi_sizeof(which)))
     L.apt_sampler_control_default.argtypes = [C.POINTER(SamplerControl)]
     L.apt_build_opts_default.argtypes = [C.POINTER(BuildOpts)]
     L.apt_run_args_default.argtypes = [C.POINTER(RunArgs)]

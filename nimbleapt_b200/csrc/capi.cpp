@@ -64,6 +64,15 @@ extern "C" {
 const char* apt_last_error(void) { return g_err.c_str(); }
 const char* apt_version(void) { return "aptb200 0.1 (sm_100a)"; }
 
+int64_t apt_abi_sizeof(int which) {
+    switch (which) {
+        case 0: return (int64_t)sizeof(apt_sampler_control);
+        case 1: return (int64_t)sizeof(apt_build_opts);
+        case 2: return (int64_t)sizeof(apt_run_args);
+        case 3: return (int64_t)sizeof(apt_timing);
+        default: return -1;
+    }
+}
 void apt_sampler_control_default(apt_sampler_control* c) {
     c->log = 0; c->reflective = 0; c->adaptive = 1; c->adaptScaleOnly = 0; c->adaptInterval = 200;
     c->adaptFactorExponent = 0.8; c->scale = 1.0; c->temperPriors = -1; c->propCov = nullptr; c->propCov_dim = 0;

@@ -24,6 +24,20 @@ def test_exports_match_header():
     assert declared == set(_lib.EXPORTS)
 
 
+def test_struct_layouts_match_the_library():
+    """The ctypes mirrors of the ABI structs (nimbleapt_b200/_lib.py) have the sizes the library was compiled with."""
+    import ctypes as C
+    from nimbleapt_b200 import _lib
+    L = _lib.lib()
+    for which, cls in ((0, _lib.SamplerControl), (1, _lib.BuildOpts), (2, _lib.RunArgs), (3, _lib.Timing)):
+        assert L.apt_abi_sizeof(which) == C.sizeof(cls), cls.__name__
+    assert L.apt_abi_sizeof(99) == -1
+    ra = _lib.RunArgs()
+    L.apt_run_args_default(C.byref(ra))
+    assert (ra.reset, ra.adaptTemps, ra.thin, ra.thin2, ra.tuneTemper1, ra.tuneTemper2) == (1, 1, -1, -1, 10.0, 1.0)  # APT:336-348
+    assert not ra.samples_out and ra.samples_out_capacity == 0
+
+
 def test_lowering_emits_expected_cuda():
     spec = models.c4_glmm(G=20, per=10, K=4)
     m = nb.nimbleModel(spec["code"], spec["constants"], spec["data"], spec["inits"])
