@@ -33,6 +33,8 @@ def lib():
         L.orc_model_free.argtypes = [C.c_void_p]
         L.orc_model_logprob.restype = C.c_double
         L.orc_model_logprob.argtypes = [C.c_void_p, dp, dp]
+        L.orc_model_logprob_ld.restype = C.c_double
+        L.orc_model_logprob_ld.argtypes = [C.c_void_p, dp, dp]
         L.orc_specs_new.restype = C.c_void_p
         L.orc_specs_new.argtypes = [C.c_int]
         L.orc_spec_set.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, ip, C.c_int, ip, ip, C.c_int, ip,
@@ -311,11 +313,13 @@ class OracleAPT:
                                   out.ctypes.data_as(C.POINTER(C.c_double)))
         return (w, out[1], out[2]) if np.isfinite(w) or w != w else (w, float("nan"), float("nan"))
 
-    def logprob(self, theta):
-        """Whole-model log probability at PARAM vector theta; returns (total, per-declaration sums)."""
+    def logprob(self, theta, extended=False):
+        """Whole-model log probability at PARAM vector theta; returns (total, per-declaration sums).  extended=True adds
+        the same node terms in long double instead of sequentially in double like model$getLogProb()."""
         full = self.om.arena0[:self.om.nmut].copy()
         full[:len(theta)] = theta
         a, ap = _da(full)
         out = np.zeros(len(self.om.decl_recs))
-        tot = lib().orc_model_logprob(self.model, ap, out.ctypes.data_as(C.POINTER(C.c_double)))
+        fn = lib().orc_model_logprob_ld if extended else lib().orc_model_logprob
+        tot = fn(self.model, ap, out.ctypes.data_as(C.POINTER(C.c_double)))
         return tot, out

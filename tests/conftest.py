@@ -11,6 +11,7 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a B200 (run with `pytest -m gpu` under gpurun)")
+    config.addinivalue_line("markers", "slow: full-size oracle parity (the CPU oracle takes up to a minute per case); part of `-m gpu`")
 
 
 @pytest.fixture(scope="session", autouse=True)

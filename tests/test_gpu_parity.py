@@ -8,7 +8,7 @@ import pytest
 
 import models
 import nimbleapt_b200 as nb
-from helpers import build_engine, build_oracle, run_pair
+from helpers import assert_run_parity, build_engine, build_oracle, run_pair
 
 pytestmark = pytest.mark.gpu
 
@@ -82,35 +82,8 @@ def test_decisions_bit_identical(name, inject):
     spec = SMALL[name]()
     niter, L = 450, 2  # crosses two sampler adaptations (adaptInterval = 200)
     eng, orc, recs = run_pair(spec, niter, L=L, inject=inject, build_kw=BUILD_KW.get(name))
+    assert_run_parity(eng, orc, recs, spec, name, niter, L)
     for l in range(L):
-        dec_o, swap_o = recs[l]
-        dec_e = eng.decisions(l, niter)
-        swap_e = eng.swapRecord(l, niter)
-        assert dec_e.shape == dec_o.shape
-        nbad = int((dec_e != dec_o).sum())
-        assert nbad == 0, "%s ladder %d: %d accept decisions differ (first at %s)" % (name, l, nbad, np.argwhere(dec_e != dec_o)[:3])
-        # swap phase: accept/reject flags identical everywhere, partners identical wherever a swap was accepted.
-        # The partner of a REJECTED proposal may differ in a vanishing fraction of cases: when every
-        # exp(-|lp_i - lp_j|) of a row lies in the denormal range, CUDA's and glibc's exp() round differently
-        # and the normalised row (APT:560-569) is not reproducible across math libraries.
-        assert np.array_equal(swap_e >> 16, swap_o >> 16), "%s ladder %d: swap accept decisions differ" % (name, l)
-        tgt_bad = (swap_e & 0xffff) != (swap_o & 0xffff)
-        assert not np.any(tgt_bad & ((swap_o >> 16) == 1)), "%s ladder %d: accepted swap partners differ" % (name, l)
-        assert tgt_bad.mean() <= 1e-3, "%s ladder %d: %d proposed partners differ" % (name, l, tgt_bad.sum())
-        np.testing.assert_allclose(eng.rungStates(l), np.stack([orc.rung_state(l, k) for k in range(eng.nTemps)]), rtol=1e-8, atol=1e-10)
-        np.testing.assert_allclose(eng.TempsLadder(l), orc.Temps(l), rtol=1e-9)
-        np.testing.assert_allclose(eng.mvSamples.matrix(l), orc.samples(l), rtol=1e-8, atol=1e-10)
-        np.testing.assert_allclose(eng.mvSamplesTmax.matrix(l), orc.samplesTmax(l), rtol=1e-8, atol=1e-10)
-        if spec.get("monitors2"):  # logProb_* monitors of the demo model: per-node log-probabilities of the saved state
-            assert eng.monitorNames2 == orc.mon2_labels
-            np.testing.assert_allclose(eng.mvSamples2.matrix(l), orc.samples2(l), rtol=1e-9, atol=1e-9)
-        np.testing.assert_allclose(eng.logProbsLadder(l), orc.logProbs(l), rtol=1e-10)
-        np.testing.assert_allclose(eng.tempTrajLadder(l), orc.tempTraj(l), rtol=1e-9)
-        np.testing.assert_array_equal(eng.accCountSwapLadder(l), orc.accCountSwap(l))
-        sc = eng.scales(l)
-        for k in range(eng.nTemps):
-            for s in range(sc.shape[1]):
-                assert np.isclose(sc[k, s], orc.scale(l, k, s), rtol=1e-9)
         if name == "multinom":  # u, timesRan ... RescaleThreshold of every rung (APT:1029-1040), adapted four times
             bs = eng.blockState(l)
             for k in range(eng.nTemps):

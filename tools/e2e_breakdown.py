@@ -3,7 +3,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
 import numpy as np
 import bench
-from helpers import build_engine
+from nimbleapt_b200.workloads import build_engine
 spec, L, thin = bench.workload_spec("c2")
 eng = build_engine(spec, nLadders=L)
 y = np.ascontiguousarray(spec["data"]["y"])

@@ -1,7 +1,7 @@
 import sys
 sys.path.insert(0, '.'); sys.path.insert(0, 'tests')
 import numpy as np, models
-from helpers import build_engine
+from nimbleapt_b200.workloads import build_engine
 spec = models.logistic(1000000, 50, 16, seed_off=3)
 eng = build_engine(spec, engine=2)
 eng.run(10)

@@ -1,7 +1,7 @@
 import sys, os, time
 sys.path.insert(0, "."); sys.path.insert(0, "tests")
 import numpy as np, models
-from helpers import build_engine
+from nimbleapt_b200.workloads import build_engine
 L = int(os.environ.get("C5_L", "2048"))
 kw = {}
 if os.environ.get("C5_W"): kw["lanesPerChain"] = int(os.environ["C5_W"])
