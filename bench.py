@@ -1,18 +1,21 @@
 #!/usr/bin/env python
 """bench.py — headline measurement for the tempered-MH hot path (BASELINE.json metric).
 
-    python bench.py --gpus N --steps K --warmup W [--workload c2|c3|c5] [--impl reference]
+    python bench.py --gpus N --steps K --warmup W [--workload c1|c2|c3|c4|c5] [--impl reference]
 
 A "step" is one APT iteration of the workload: every rung of every ladder runs each of its tempered samplers once
 (APT_functions.R:435-448), then the swap phase, ladder adaptation and thinned output.  Workload at every N is
 BASELINE.json configs[1] ("c2": 2-D bimodal mixture, 32 temperatures x 4096 independent ladders per GPU, scalar
-RW_tempered; weak scaling: ladders are sharded across GPUs, no collective on the data path).  The HBM-bound
-likelihood kernel of configs[2] ("c3": logistic regression N=1e6, p=50, 16 temperatures) is timed in the same
-process at N=1 and reported as `roofline_c3`.
+RW_tempered; weak scaling: ladders are sharded across GPUs, no collective on the data path).  Beside the headline the
+line carries: `roofline_c3` (N = 1: the HBM-bound likelihood kernel of configs[2], logistic N = 1e6, p = 50, 16
+temperatures, with its own CPU baseline), `scale_c5` (every N: BASELINE's weak-scaling configuration configs[4], 8192
+ladders x 64 temperatures per GPU) and `ess` (ESS/sec from a run long enough to estimate it).
 
 value     = tempered MH updates / s over all GPUs, device time (CUDA events on the engine's stream, max over ranks)
-e2e       = the same through the public API with HOST buffers: data + inits uploaded, run, mvSamples fetched to host
-            (N > 1: every rank's traces gathered over NCCL to rank 0 and copied to its host memory, inside the timed region)
+e2e       = the same through the public API with HOST buffers: data + inits uploaded, run, mvSamples delivered to host
+            memory of rank 0 (N = 1: copied back piece by piece while the run samples; N > 1: every rank's rows travel over
+            NCCL to rank 0 piece by piece while the run samples, apt_run_args.gather), all inside the timed region; median
+            of 5 passes of K steps each (every pass listed in e2e.passes_s)
 roofline  = dominant kernel of the timed region; for c2 the kernel is FP64-pipe bound, so the
             roofline is flop-based against the FP64 FMA peak measured live; roofline_c3 is the HBM one.
 --impl reference times the CPU oracle (restated reference, NOT nimble itself: R/nimble are absent).
@@ -25,14 +28,15 @@ import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-for p in (ROOT, os.path.join(ROOT, "tests")):
-    if p not in sys.path:
-        sys.path.insert(0, p)
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 
 # algorithmic fp64 flops per tempered update (SURVEY.md §8d "n*c_dens + c_rng"): counted from the lowered code
 FLOPS_PER_UPDATE = {"c2": 20 * 8 + 150, "c5": 1024 * (2 * 8 + 60) + 8 * 8 + 300}
+ESS_ITERS = {"c1": 10000, "c2": 2000, "c5": 2000, "c4": 600, "c3": 600}  # iterations of the ESS side measurement
+ESS_MIN_ROWS = 50
 
 
 def _peaks():
@@ -92,18 +96,24 @@ class ClockSampler:
 
 
 def workload_spec(name):
-    import models
+    """(spec, ladders per GPU, thin, engine) of BASELINE.json's configurations (nimbleapt_b200/workloads.py)."""
+    from nimbleapt_b200 import workloads as w
+    if name == "c1":
+        return w.c1_vignette(nObs=100, K=8), 1, 1, 0
     if name == "c2":
-        return models.c2_mixture(n=20, K=32), 4096, 10
-    if name == "c5":
-        return models.c5_small_logistic(N=1024, p=8, K=64), 8192, 10
+        return w.c2_mixture(n=20, K=32), 4096, 10, 0
     if name == "c3":
-        return models.c3_logistic(), 1, 1
+        return w.c3_logistic(), 1, 1, 2
+    if name == "c4":
+        return w.c4_glmm(), 64, 1, 0
+    if name == "c5":
+        return w.c5_small_logistic(N=1024, p=8, K=64), 8192, 10, 0
     raise SystemExit("unknown workload " + name)
 
 
 def ess_batch_means(x):
-    """ESS by non-overlapping batch means (sqrt(n) batches); applied identically to GPU and CPU traces."""
+    """ESS by non-overlapping batch means (sqrt(n) batches); applied identically to GPU and CPU traces
+    (coda::effectiveSize of demo/APT_demo.R:203 is not available here)."""
     n = len(x)
     b = max(2, int(np.sqrt(n)))
     m = n // b
@@ -115,25 +125,58 @@ def ess_batch_means(x):
     return float(n * v / vb) if vb > 0 else float(n)
 
 
+def ess_of_traces(workload, traces):
+    """Mean over ladders of the ESS of the first monitored column (|.| for the sign-symmetric posteriors of c1 / c2) after
+    discarding the first quarter; None + reason when there are too few rows to estimate anything."""
+    rows = traces.shape[1]
+    burn = rows // 4
+    if rows - burn < ESS_MIN_ROWS:
+        return None, "only %d post-burn-in rows (< %d): ESS not estimable" % (rows - burn, ESS_MIN_ROWS)
+    f = np.abs if workload in ("c1", "c2") else (lambda a: a)
+    nl = min(traces.shape[0], 64)
+    return float(np.mean([ess_batch_means(f(traces[l, burn:, 0])) for l in range(nl)])), None
+
+
+def _oracle(spec, nl):
+    from oracle.oracle import OracleAPT
+    return OracleAPT(spec["code"], spec["constants"], spec["data"], spec["inits"], spec["samplers"], spec["monitors"], (),
+                     spec["Temps"], spec["ULT"], True, nl, 11, 0)
+
+
+def cpu_ess(workload, cores):
+    """ESS/sec of the CPU arm: `cores` ladders (one per thread) x ESS_ITERS iterations, wall clock; config 3 is skipped
+    (600 iterations of the serial reference would take an hour)."""
+    if workload == "c3":
+        return {"ess_per_sec": None, "reason": "600 iterations of the N = 1e6 model take ~1 h on the CPU: not measured"}
+    spec, _, thin, _ = workload_spec(workload)
+    nl = 1 if workload == "c1" else (min(cores, 8) if workload == "c4" else cores)
+    niter = ESS_ITERS[workload] if workload != "c4" else 120
+    orc = _oracle(spec, nl)
+    t0 = time.perf_counter()
+    orc.run(niter, thin=thin, nthreads=cores)
+    dt = time.perf_counter() - t0
+    tr = np.stack([orc.samples(l) for l in range(nl)])
+    ess, why = ess_of_traces(workload, tr)
+    return {"ess_per_sec": None if ess is None else ess * nl / dt, "reason": why, "iterations": niter, "ladders": nl,
+            "rows": int(tr.shape[1]), "seconds": dt, "estimator": "batch means, first monitored column, first quarter discarded"}
+
+
 def run_reference(args, rank, world):
     """--impl reference: the CPU restatement of the reference's algorithm (oracle) on all host threads."""
     if rank != 0:
         return
-    from oracle.oracle import OracleAPT, lib
-    spec, _, thin = workload_spec(args.workload)
+    from oracle.oracle import lib
+    spec, Lfull, thin, _ = workload_spec(args.workload)
     cores = lib().orc_max_threads()
     # a step = one APT iteration over a sample of `nl` independent ladders of the workload.  The sample is sized so
     # that the whole run is about 20 s of CPU work at the port's typical rate (REF_RATE updates/s on all threads) —
     # large enough that thread start-up does not dominate a step, bounded so the run ends within minutes.
-    _, Lfull, _ = workload_spec(args.workload)
     upl = len(spec["Temps"]) * max(1, len(spec["samplers"]))
-    REF_RATE = {"c2": 1.5e7, "c5": 2.5e6, "c3": 6.0}[args.workload]
+    REF_RATE = {"c1": 1.0e6, "c2": 1.5e7, "c5": 2.5e6, "c3": 6.0, "c4": 1.0e5}[args.workload]
     nl = int(REF_RATE * 20.0 / ((args.steps + max(1, args.warmup)) * upl))
-    nl = max(1 if args.workload == "c3" else cores, min(Lfull, nl))
-    orc = OracleAPT(spec["code"], spec["constants"], spec["data"], spec["inits"], spec["samplers"], spec["monitors"], (),
-                    spec["Temps"], spec["ULT"], True, nl, 11, 0)
+    nl = max(1 if args.workload in ("c3", "c1") else min(cores, Lfull), min(Lfull, nl))
+    orc = _oracle(spec, nl)
     K, NS = orc.K, orc.NS
-    # a step = one APT iteration over the sample of `nl` ladders
     orc.run(max(1, args.warmup), thin=thin, nthreads=cores)
     t0 = time.perf_counter()
     orc.run(args.steps, reset=False, thin=thin, nthreads=cores)
@@ -148,39 +191,55 @@ def run_reference(args, rank, world):
                                        "restated CPU baseline, not nimble" % (nl, cores, args.steps)},
             "e2e": {"value": val, "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
+    if not args.no_ess:
+        line["ess"] = cpu_ess(args.workload, cores)
     print(json.dumps(line))
 
 
-def cpu_baseline(workload, seconds=15.0):
-    from oracle.oracle import OracleAPT, lib
-    spec, _, thin = workload_spec(workload)
+def cpu_baseline(workload, seconds=15.0, with_ess=True):
+    """The oracle ("port": restated reference, not nimble) on all host threads over a bounded sample of the workload."""
+    from oracle.oracle import lib
+    spec, _, thin, _ = workload_spec(workload)
     cores = lib().orc_max_threads()
-    nl = cores * 2
-    orc = OracleAPT(spec["code"], spec["constants"], spec["data"], spec["inits"], spec["samplers"], spec["monitors"], (),
-                    spec["Temps"], spec["ULT"], True, nl, 11, 0)
+    if workload == "c3":
+        # one tempered update = one serial pass over 1e6 x 50 doubles (APT:825): ~0.15 s each.  Sample: 4 ladders side by
+        # side (the data are shared, like replicas of the run on one host) x 2 iterations after 1 untimed one.
+        nl = min(4, cores)
+        orc = _oracle(spec, nl)
+        K, NS = orc.K, orc.NS
+        orc.run(1, thin=thin, nthreads=nl)
+        t0 = time.perf_counter(); orc.run(2, reset=False, thin=thin, nthreads=nl); dt = time.perf_counter() - t0
+        o1 = _oracle(spec, 1)
+        t1 = time.perf_counter(); o1.run(1, thin=thin, nthreads=1); d1 = time.perf_counter() - t1
+        return {"value": 2 * nl * K * NS / dt, "unit": "updates/s", "cores": nl, "kind": "port",
+                "single_core_value": K * NS / d1,
+                "sample": "%d independent ladders x 2 iterations x %d rungs on %d threads (%.1f s); restated CPU baseline, not nimble" % (nl, K, nl, dt)}
+    nl = 1 if workload == "c1" else (min(cores, 8) if workload == "c4" else cores * 2)
+    orc = _oracle(spec, nl)
     K, NS = orc.K, orc.NS
-    orc.run(50, thin=thin, nthreads=cores)
-    t0 = time.perf_counter(); orc.run(200, reset=False, thin=thin, nthreads=cores); dt = time.perf_counter() - t0
-    niter = int(max(200, min(200000, 200 * seconds / max(dt, 1e-3))))
+    n0 = 4 if workload == "c4" else 200
+    orc.run(max(1, n0 // 4), thin=thin, nthreads=cores)
+    t0 = time.perf_counter(); orc.run(n0, reset=False, thin=thin, nthreads=cores); dt = time.perf_counter() - t0
+    niter = int(max(n0, min(200000, n0 * seconds / max(dt, 1e-3))))
     t0 = time.perf_counter(); orc.run(niter, reset=False, thin=thin, nthreads=cores); dt = time.perf_counter() - t0
     # single-thread figure as well (the reference itself is serial, APT:435-448)
-    o1 = OracleAPT(spec["code"], spec["constants"], spec["data"], spec["inits"], spec["samplers"], spec["monitors"], (),
-                   spec["Temps"], spec["ULT"], True, 1, 11, 0)
-    n1 = max(200, niter // 8)
+    o1 = _oracle(spec, 1)
+    n1 = max(n0 // 2, niter // 8)
     t1 = time.perf_counter(); o1.run(n1, thin=thin, nthreads=1); d1 = time.perf_counter() - t1
-    return {"value": niter * nl * K * NS / dt, "unit": "updates/s", "cores": cores, "kind": "port",
-            "single_core_value": n1 * K * NS / d1,
-            "sample": "%d independent ladders x %d iterations on %d threads (%.1f s); restated CPU baseline, not nimble" % (nl, niter, cores, dt)}
+    out = {"value": niter * nl * K * NS / dt, "unit": "updates/s", "cores": min(cores, nl), "kind": "port",
+           "single_core_value": n1 * K * NS / d1,
+           "sample": "%d independent ladders x %d iterations on %d threads (%.1f s); restated CPU baseline, not nimble" % (nl, niter, min(cores, nl), dt)}
+    if with_ess:
+        out["ess"] = cpu_ess(workload, cores)
+    return out
 
 
 def c3_roofline(device, passes=400):
     """HBM-bound likelihood pass of config 3 (grid engine): algorithmic bytes 8*N*(p+1) per pass / device time.
-    Measured at the default 16 rungs per pass (most updates/s; FP64 work per pass exceeds the HBM time there) and at
-    8 rungs per pass (two passes per iteration; the setting where the pass is closest to HBM-bound)."""
-    from helpers import build_engine
-    import models
+    Measured at the default 16 rungs per pass and at 8 rungs per pass (two passes per iteration)."""
+    from nimbleapt_b200.workloads import build_engine, logistic
     N, p, K = 1000000, 50, 16
-    spec = models.logistic(N, p, K, seed_off=3)
+    spec = logistic(N, p, K, seed_off=3)
     peak, how = _peaks()
     by = 8.0 * N * (p + 1)
     res = {}
@@ -191,7 +250,7 @@ def c3_roofline(device, passes=400):
         t = eng.getTimes()
         first = t["main_kernel_ms"] / max(1, t["main_launches"])
         # steady state: once the ladder has adapted (hot rungs at T ~ 1e5) a fraction of the terms takes the branch that
-        # reproduces the reference's own rounding for y = 0, eta > 8, which costs ~20 % more per pass
+        # reproduces the reference's own rounding for y = 0, eta > 8
         eng.run(1200, reset=False)
         eng.run(passes, reset=False)
         t = eng.getTimes()
@@ -202,13 +261,133 @@ def c3_roofline(device, passes=400):
         del eng
     r = res[16]
     return {"bound": "hbm", "achieved": r["achieved"], "peak": peak, "unit": "GB/s", "frac": r["frac"],
-            "traffic": 413.7e6, "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture (profiles/r1_c3_grid_pass_kernel.md)",
+            "traffic": 413.7e6, "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture (profiles/)",
             "peak_source": how, "kernel": "apt::grid_pass_kernel", "ms_per_launch": r["ms_per_launch"], "launches": r["launches"],
             "algorithmic_bytes_per_launch": by, "rungs_per_pass": 16, "updates_per_s": r["updates_per_s"],
             "timed": "400 passes after 1620 iterations (adapted ladder); first_400_iterations = iterations 21..420",
             "first_400_iterations": r["first_400_iterations"],
             "rungs_per_pass_8": res[8],
             "workload": "c3: logistic N=1e6 p=50, 16 temperatures, 1 ladder, sampler_RW_block_tempered; inputs (408 MB) larger than L2"}
+
+
+class Ranks:
+    """torch.distributed is plumbing only: rendezvous, barrier, max over ranks, broadcast of the ncclUniqueId."""
+
+    def __init__(self, rank, world, local):
+        self.rank, self.world, self.local, self.dist = rank, world, local, None
+        if world > 1:
+            import torch
+            import torch.distributed as dist
+            torch.cuda.set_device(local)
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            self.dist = dist
+
+    def barrier(self):
+        if self.dist is not None:
+            import torch
+            torch.cuda.synchronize()
+            self.dist.barrier()
+
+    def max(self, x):
+        if self.dist is None:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def comm_init(self, eng):
+        if self.dist is None:
+            return
+        obj = [eng.commUniqueId() if self.rank == 0 else None]
+        self.dist.broadcast_object_list(obj, src=0)
+        eng.commInit(self.world, self.rank, obj[0])
+
+    def close(self):
+        if self.dist is not None:
+            self.dist.destroy_process_group()
+
+
+def pinned_buffer(n):
+    import torch
+    return torch.empty(max(int(n), 1), dtype=torch.float64, pin_memory=True).numpy()
+
+
+def measure(rk, workload, L, steps, warmup, thin, engine, reps=5, clock_index=None):
+    """Device-timed K steps, then end-to-end passes of K steps each through the public API with host buffers."""
+    import nimbleapt_b200 as nb
+    from nimbleapt_b200.workloads import build_engine, initial_values
+    spec = workload_spec(workload)[0]
+    K = len(spec["Temps"])
+    eng = build_engine(spec, nLadders=L, ladder0=rk.rank * L, device=rk.local, engine=engine)
+    NU = eng.info(nb.api.INFO_N_UNITS)
+    # ---------------- device-resident timed region
+    eng.run(warmup, thin=thin)
+    rk.barrier()
+    cs = ClockSampler(rk.local if clock_index is None else clock_index)
+    with cs:
+        eng.run(steps, reset=False, thin=thin)
+        tm = eng.getTimes()
+    rk.barrier()
+    dev_s = rk.max(tm["kernel_ms"] * 1e-3)
+    updates_total = float(steps) * L * K * NU * rk.world
+    # ---------------- end to end through the public API with host buffers
+    rk.comm_init(eng)
+    yname = next(iter(spec["data"]))
+    y = np.ascontiguousarray(spec["data"][yname])
+    th0 = initial_values(spec)
+    nmon = len(eng.monitorNames)
+    rows = steps // thin
+    pinned = pinned_buffer(rk.world * L * rows * nmon) if rk.rank == 0 else None  # allocated once, outside the timed region
+
+    def e2e_once():
+        t = [time.perf_counter()]
+        eng.setData(yname, y)                    # H2D: observations
+        eng.setInits(th0)                        # H2D: initial values
+        t.append(time.perf_counter())
+        # the thinned traces arrive in page-locked host memory of rank 0 piece by piece while the run is still sampling:
+        # one process: second stream (apt_run_args.samples_out); N > 1: NCCL to rank 0 between the pieces, then the same copy
+        eng.run(steps, thin=thin, samplesOut=pinned, gatherRoot=0 if rk.dist is not None else None)
+        t.append(time.perf_counter())
+        return t
+
+    e2e_once()  # untimed pass of the same call sequence (first NCCL operations set up their channels, buffers reach their size)
+    passes, breakdown = [], []
+    for _ in range(reps):
+        rk.barrier()
+        t = e2e_once()
+        passes.append(rk.max(t[-1] - t[0]))
+        tt = eng.getTimes()
+        breakdown.append({"upload_ms": 1e3 * (t[1] - t[0]), "run_wall_ms": tt["run_wall_ms"], "kernel_ms": tt["kernel_ms"],
+                          "gather_tail_ms": tt["gather_tail_ms"]})
+    rk.barrier()
+    mid = int(np.argsort(passes)[len(passes) // 2])
+    e2e_s = passes[mid]
+    res = {"eng": eng, "spec": spec, "K": K, "NU": NU, "tm": tm, "dev_s": dev_s, "updates_total": updates_total, "e2e_s": e2e_s,
+           "passes": passes, "breakdown": breakdown[mid], "clocks": cs.summary(),
+           "h2d": (y.nbytes + th0.nbytes) * rk.world, "d2h": rk.world * L * rows * nmon * 8, "nmon": nmon, "rows": rows}
+    if rk.rank == 0 and rows > 0:
+        res["samples_all"] = pinned[:rk.world * L * rows * nmon].reshape(rk.world * L, rows, nmon)
+    return res
+
+
+def gpu_ess(rk, workload, eng, L, thin):
+    """ESS/sec of the device arm from a run long enough to estimate it (ESS_ITERS iterations, end to end)."""
+    niter = ESS_ITERS[workload]
+    rows, nmon = niter // thin, len(eng.monitorNames)
+    pinned = pinned_buffer(rk.world * L * rows * nmon) if rk.rank == 0 else None
+    rk.barrier()
+    t0 = time.perf_counter()
+    eng.run(niter, thin=thin, samplesOut=pinned, gatherRoot=0 if rk.dist is not None else None)
+    dt = rk.max(time.perf_counter() - t0)
+    if rk.rank != 0:
+        return None
+    tr = pinned[:rk.world * L * rows * nmon].reshape(rk.world * L, rows, nmon)
+    ess, why = ess_of_traces(workload, tr)
+    f = np.abs if workload in ("c1", "c2") else (lambda a: a)
+    return {"ess_per_sec": None if ess is None else ess * L * rk.world / dt, "reason": why, "iterations": niter,
+            "ladders": L * rk.world, "rows": rows, "seconds": dt, "pooled_mean_col0": float(f(tr[:, rows // 4:, 0]).mean()),
+            "estimator": "batch means, first monitored column, first quarter discarded"}
 
 
 def main():
@@ -221,6 +400,8 @@ def main():
     ap.add_argument("--ladders", type=int, default=0, help="ladders per GPU (default: workload's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-c3", action="store_true")
+    ap.add_argument("--no-c5", action="store_true")
+    ap.add_argument("--no-ess", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
@@ -231,136 +412,69 @@ def main():
         return
 
     import nimbleapt_b200 as nb
-    from nimbleapt_b200 import _lib
-    from helpers import build_engine
-    dist = None
-    if world > 1:
-        import torch
-        import torch.distributed as dist
-        torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    spec, L, thin = workload_spec(args.workload)
+    rk = Ranks(rank, world, local)
+    spec, L, thin, engine = workload_spec(args.workload)
     if args.ladders > 0:
         L = args.ladders
-    K = len(spec["Temps"])
-    eng = build_engine(spec, nLadders=L, ladder0=rank * L, device=local, engine=2 if args.workload == "c3" else 0)
-    NU = eng.info(nb.api.INFO_N_UNITS)
-
-    def barrier():
-        if dist is not None:
-            import torch
-            torch.cuda.synchronize()
-            dist.barrier()
-
-    def max_over_ranks(x):
-        if dist is None:
-            return x
-        import torch
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    # ---------------- device-resident timed region
-    eng.run(args.warmup, thin=thin)
-    barrier()
-    with ClockSampler(local) as cs:
-        eng.run(args.steps, reset=False, thin=thin)
-        tm = eng.getTimes()
-    barrier()
-    dev_s = max_over_ranks(tm["kernel_ms"] * 1e-3)
-    updates_total = float(args.steps) * L * K * NU * world
-    value = updates_total / dev_s
-    # ---------------- NCCL communicator inside the library (gathers of traces / pooled statistics only, §8e)
-    C = _lib.C
-    if dist is not None:
-        uid = (C.c_ubyte * 128)()
-        if rank == 0:
-            _lib.check(_lib.lib().apt_comm_unique_id(uid))
-        obj = [bytes(uid)]
-        dist.broadcast_object_list(obj, src=0)
-        uid = (C.c_ubyte * 128)(*obj[0])
-        _lib.check(_lib.lib().apt_comm_init(eng._h, world, rank, uid))
-    # ---------------- end to end through the public API with host buffers
-    y = np.ascontiguousarray(spec["data"]["y"])
-    th0 = np.concatenate([np.ravel(spec["inits"][k], order="F") for k in spec["inits"]])
-    nmon = len(eng.monitorNames)
-    rows = args.steps // thin
-    pinned = None
-    if rank == 0:  # page-locked destination of the (gathered) traces, allocated once outside the timed region
-        import torch
-        pinned = torch.empty(world * L * rows * nmon, dtype=torch.float64, pin_memory=True).numpy()
-
-    def e2e_once(steps):
-        eng.setData("y", y)                      # H2D: observations
-        eng.setInits(th0)                        # H2D: initial values
-        if dist is None:
-            # one process: the thinned traces are copied back to page-locked host memory asynchronously, piece by piece,
-            # while the run is still sampling (apt_run_args.samples_out); complete when run() returns
-            out = pinned[:L * (steps // thin) * nmon]
-            eng.run(steps, thin=thin, samplesOut=out)
-            sm = out.reshape(L, steps // thin, nmon)
-            return sm, sm
-        eng.run(steps, thin=thin)                # reset=TRUE run from the uploaded state
-        if dist is not None:                     # NCCL gather of every rank's traces to rank 0 (the process that hands them to
-            r_ = steps // thin                   # the user), one D2H into pinned host memory there
-            got = C.c_int64()
-            if rank == 0:
-                allbuf = pinned[:world * L * r_ * nmon]
-                _lib.check(_lib.lib().apt_comm_gather_samples(eng._h, 0, 0, allbuf.ctypes.data_as(C.POINTER(C.c_double)), allbuf.size, C.byref(got)))
-                assert got.value == allbuf.size
-                sa = allbuf.reshape(world * L, r_, nmon)
-                return sa[:L], sa
-            _lib.check(_lib.lib().apt_comm_gather_samples(eng._h, 0, 0, None, 0, C.byref(got)))
-            return None, None
-
-    e2e_once(args.steps)  # untimed warm-up of the same call sequence at the same size (first NCCL collective sets up its channels, trace and gather buffers reach their final size)
-    barrier()
-    t0 = time.perf_counter()
-    samples, samples_all = e2e_once(args.steps)
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
-    barrier()
-    if samples is None:  # ranks other than 0: own traces for the pooled statistic below, outside the timed region
-        samples = eng.mvSamples.matrix(-1)
-        samples_all = samples
-    h2d = (y.nbytes + th0.nbytes) * world
-    d2h = samples_all.nbytes
-    burn = samples.shape[1] // 4
-    ess = float(np.mean([ess_batch_means(np.abs(samples[l, burn:, 0])) for l in range(min(L, 64))]))
-    pooled = np.array([np.abs(samples[:, burn:, 0]).sum(), float(samples[:, burn:, 0].size)])
-    if dist is not None:                     # pooled statistic by NCCL all-reduce(sum)
-        buf = np.ascontiguousarray(pooled)
-        _lib.check(_lib.lib().apt_comm_allreduce_sum(eng._h, buf.ctypes.data_as(C.POINTER(C.c_double)), buf.size))
-        pooled = buf
+    m = measure(rk, args.workload, L, args.steps, args.warmup, thin, engine)
+    eng, tm, K, NU = m["eng"], m["tm"], m["K"], m["NU"]
+    value = m["updates_total"] / m["dev_s"]
+    ess = None if args.no_ess else gpu_ess(rk, args.workload, eng, L, thin)
+    fp64_peak = eng.info(nb.api.INFO_FP64_GFLOPS) / 1e3 if (rank == 0 and args.workload in FLOPS_PER_UPDATE) else None
+    engine_kind = "grid" if eng.info(nb.api.INFO_ENGINE) == 2 else "ladder-resident"
+    if world > 1:
+        eng.commFinalize()
+    del eng, m["eng"]
+    # ---------------- BASELINE's weak-scaling configuration (configs[4]) beside the headline, at every N
+    scale_c5 = None
+    if not args.no_c5 and args.workload != "c5":
+        try:
+            s5, L5, thin5, e5 = workload_spec("c5")
+            st5 = 40
+            m5 = measure(rk, "c5", L5, st5, 10, thin5, e5, reps=3)
+            scale_c5 = {"workload": "c5", "ladders_per_gpu": L5, "temperatures": m5["K"], "steps": st5, "warmup": 10,
+                        "value": m5["updates_total"] / m5["dev_s"], "unit": "updates/s", "ms_per_step": 1e3 * m5["dev_s"] / st5,
+                        "e2e": {"value": m5["updates_total"] / m5["e2e_s"], "seconds": m5["e2e_s"], "passes_s": m5["passes"]},
+                        "e2e_breakdown": m5["breakdown"]}
+            if world > 1:
+                m5["eng"].commFinalize()
+            del m5
+        except Exception as e:  # keep the headline line even if the side measurement fails
+            scale_c5 = {"error": str(e)[:300]}
     if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
+        rk.close()
         return
-    clocks = cs.summary()
-    flops = FLOPS_PER_UPDATE.get(args.workload, 0) * updates_total / world
+    flops = FLOPS_PER_UPDATE.get(args.workload, 0) * m["updates_total"] / world
     line = {"metric": "tempered MH updates/sec", "value": value, "unit": "updates/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": 1e3 * m["dev_s"] / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": args.workload, "ladders_per_gpu": L, "temperatures": K, "samplers_per_rung": NU, "thin": thin,
-                       "engine": "grid" if eng.info(nb.api.INFO_ENGINE) == 2 else "ladder-resident",
+                       "engine": engine_kind,
                        "l2": ("inputs (408 MB design matrix) larger than the 126 MB L2: every pass re-streams them from HBM"
                               if args.workload == "c3" else
                               "working set is shared-memory resident; traces stream to HBM (no L2 reuse to flush)")},
-            "e2e": {"value": updates_total / e2e_s, "unit": "updates/s", "h2d_bytes_per_step": h2d / args.steps,
-                    "d2h_bytes_per_step": d2h / args.steps, "seconds": e2e_s},
-            "gpu_launches": int(tm["launches"]), "clocks": clocks,
-            "ess_per_sec": ess * L * world / e2e_s, "pooled_abs_theta1_mean": float(pooled[0] / pooled[1]),
-            "swap_proposals_per_sec": float(args.steps) * L * K * world / dev_s}
+            "e2e": {"value": m["updates_total"] / m["e2e_s"], "unit": "updates/s", "h2d_bytes_per_step": m["h2d"] / args.steps,
+                    "d2h_bytes_per_step": m["d2h"] / args.steps, "seconds": m["e2e_s"], "passes_s": m["passes"],
+                    "timing": "median of %d end-to-end passes of %d steps each, max over ranks per pass" % (len(m["passes"]), args.steps)},
+            "e2e_breakdown": m["breakdown"],
+            "gpu_launches": int(tm["launches"]), "clocks": m["clocks"],
+            "swap_proposals_per_sec": float(args.steps) * L * K * world / m["dev_s"]}
+    if ess is not None:
+        line["ess"] = ess
+        line["ess_per_sec"] = ess["ess_per_sec"]
+    if scale_c5 is not None:
+        line["scale_c5"] = scale_c5
     if args.workload in FLOPS_PER_UPDATE:
         tf = flops / (tm["kernel_ms"] * 1e-3) / 1e12
-        pk = eng.info(nb.api.INFO_FP64_GFLOPS) / 1e3  # measured live: pure DFMA kernel, CUDA events (no FP64 peak in MEASURED_PEAKS.json)
-        line["roofline"] = {"bound": "fp64", "achieved": tf, "peak": pk, "unit": "TFLOP/s", "frac": tf / pk, "traffic": None,
+        line["roofline"] = {"bound": "fp64", "achieved": tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": tf / fp64_peak, "traffic": None,
                             "peak_source": "measured in this run: 16 independent DFMA chains per thread, 2 x 256 threads per SM, best of 3 (apt_info APT_INFO_FP64_PEAK_GFLOPS)",
                             "kernel": "apt::ladder_kernel", "algorithmic_flops_per_update": FLOPS_PER_UPDATE[args.workload],
                             "note": "small-model kernel: bound by issue slots / FP64 dependent-issue latency, not by HBM (SURVEY.md §8d); most executed instructions are not algorithmic flops (Philox, Box-Muller, swap phase); HBM roofline: roofline_c3"}
     if world == 1 and not args.no_c3 and args.workload != "c3":
         try:
-            del eng
             line["roofline_c3"] = c3_roofline(local)
+            if not args.no_cpu_baseline:
+                line["roofline_c3"]["cpu_baseline"] = cpu_baseline("c3")
         except Exception as e:  # keep the headline line even if the side measurement fails
             line["roofline_c3"] = {"error": str(e)[:200]}
     if args.workload == "c3":
@@ -368,12 +482,12 @@ def main():
         by = 8.0 * 1000000 * 51
         ms = tm["main_kernel_ms"] / max(1, tm["main_launches"])
         line["roofline"] = {"bound": "hbm", "achieved": by / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                            "frac": by / (ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": how, "kernel": "apt::grid_pass_kernel"}
+                            "frac": by / (ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": how, "kernel": "apt::grid_pass_kernel",
+                            "algorithmic_bytes_per_launch": by, "ms_per_launch": ms}
     if world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline(args.workload if args.workload != "c3" else "c2")
+        line["cpu_baseline"] = cpu_baseline(args.workload, with_ess=not args.no_ess)
     print(json.dumps(line))
-    if dist is not None:
-        dist.destroy_process_group()
+    rk.close()
 
 
 if __name__ == "__main__":

@@ -134,6 +134,14 @@ typedef struct {
      * included; apt_get(APT_SAMPLES) still returns everything. */
     double* samples_out;
     int64_t samples_out_capacity;  /* in doubles */
+    /* multi-GPU: gather != 0 (needs apt_comm_init; every rank of the communicator calls apt_run with the same niter, thin,
+     * gather and gather_root) sends the rows of mvSamples THIS run writes to rank gather_root piece by piece over NCCL
+     * while the run goes on; on the root they arrive in samples_out, laid out [ladders of rank 0 | rank 1 | ...][niter / thin]
+     * [n_monitors] (ranks may hold different numbers of ladders), complete when apt_run returns.  Other ranks' samples_out
+     * is ignored.  The reference's user reads as.matrix(cAPT$mvSamples) in ONE R session (vignette:141): the root is that
+     * process.  An interrupted run (should_abort) must be interrupted on every rank at the same piece. */
+    int gather;
+    int gather_root;
 } apt_run_args;
 
 typedef struct {
@@ -141,6 +149,9 @@ typedef struct {
     double main_kernel_ms;  /* device time of the dominant kernel only */
     int64_t launches;       /* kernels launched by the last run */
     int64_t main_launches;  /* launches of the dominant kernel */
+    double run_wall_ms;     /* host clock around the whole apt_run call */
+    double gather_tail_ms;  /* host clock from the end of sampling to the end of apt_run: what was left of the copy-back /
+                               gather once the last launch had finished */
 } apt_timing;
 
 /* what to fetch with apt_get */
@@ -234,10 +245,12 @@ int apt_set_array(apt_engine* e, const char* name, const double* values, int64_t
  * rank 0 obtained from apt_comm_unique_id and broadcast out of band (e.g. torch.distributed / MPI / file). */
 int apt_comm_unique_id(unsigned char id_out[128]);
 int apt_comm_init(apt_engine* e, int world_size, int rank, const unsigned char unique_id[128]);
-/* all-gather of mvSamples over ranks: out [world][L][rows][n_monitors] on every rank (host memory) */
+/* all-gather of mvSamples over ranks: out [ladders of rank 0 | rank 1 | ...][rows][n_monitors] on every rank (host memory) */
 int apt_comm_allgather_samples(apt_engine* e, int what, double* out, int64_t capacity, int64_t* n_written);
 /* gather of mvSamples to ONE rank (grouped ncclSend / ncclRecv over NVLink, one device-to-host copy on the root):
- * out [world][L][rows][n_monitors] on rank `root` only (n_written = 0 and out untouched elsewhere).  The reference's
+ * out [ladders of rank 0 | rank 1 | ...][rows][n_monitors] on rank `root` only (n_written = 0 and out untouched elsewhere);
+ * ranks may hold different numbers of ladders (apt_comm_init exchanges the counts), rows must be equal.  Gathers a whole
+ * trace AFTER the run; apt_run_args.gather moves the rows while the run is still sampling.  The reference's
  * user reads as.matrix(cAPT$mvSamples) in one R session (vignette:141), i.e. on one host process. */
 int apt_comm_gather_samples(apt_engine* e, int what, int root, double* out, int64_t capacity, int64_t* n_written);
 /* sum-all-reduce of a small host vector of pooled statistics (moments, ESS accumulators, swap counts) */

@@ -30,12 +30,13 @@ class RunArgs(C.Structure):
                 ("thin", C.c_int), ("thin2", C.c_int), ("should_abort", ABORT_FN), ("abort_arg", C.c_void_p),
                 ("iters_per_launch", C.c_int), ("inject_normals", C.POINTER(C.c_double)),
                 ("inject_accept_u", C.POINTER(C.c_double)), ("inject_swap_u", C.POINTER(C.c_double)),
-                ("samples_out", C.POINTER(C.c_double)), ("samples_out_capacity", C.c_int64)]
+                ("samples_out", C.POINTER(C.c_double)), ("samples_out_capacity", C.c_int64),
+                ("gather", C.c_int), ("gather_root", C.c_int)]
 
 
 class Timing(C.Structure):
     _fields_ = [("kernel_ms", C.c_double), ("main_kernel_ms", C.c_double), ("launches", C.c_int64),
-                ("main_launches", C.c_int64)]
+                ("main_launches", C.c_int64), ("run_wall_ms", C.c_double), ("gather_tail_ms", C.c_double)]
 
 
 # every symbol include/aptb200.h declares

@@ -288,7 +288,7 @@ class APT:
     # ---- cAPT$run  (APT_functions.R:336-549)
     def run(self, niter, reset=True, resetMV=False, resetTempering=False, simulateAll=False, time=False,
             adaptTemps=True, printTemps=False, tuneTemper1=10, tuneTemper2=1, progressBar=True, thin=-1, thin2=-1,
-            itersPerLaunch=0, samplesOut=None, _inject=None):
+            itersPerLaunch=0, samplesOut=None, gatherRoot=None, _inject=None):
         ra = RunArgs()
         lib().apt_run_args_default(C.byref(ra))
         ra.niter, ra.reset, ra.resetMV, ra.resetTempering = int(niter), int(bool(reset)), int(bool(resetMV)), int(bool(resetTempering))
@@ -309,13 +309,38 @@ class APT:
                 raise ValueError("samplesOut must be a flat, contiguous float64 array")
             ra.samples_out = _dp(samplesOut)
             ra.samples_out_capacity = samplesOut.size
+        if gatherRoot is not None:
+            # multi-GPU (after commInit): this run's rows of mvSamples travel to rank `gatherRoot` over NCCL piece by piece
+            # while the run goes on; on the root they land in samplesOut, [ladders of rank 0 | rank 1 | ...][niter / thin][monitors]
+            ra.gather, ra.gather_root = 1, int(gatherRoot)
         check(lib().apt_run(self._h, C.byref(ra)))
+
+    # ---- multi-GPU: one process per GPU, ladders sharded by global id; NCCL only gathers traces / pools statistics
+    @staticmethod
+    def commUniqueId():
+        """The 128-byte ncclUniqueId rank 0 creates and hands to the other ranks out of band."""
+        uid = (C.c_ubyte * 128)()
+        check(lib().apt_comm_unique_id(uid))
+        return bytes(uid)
+
+    def commInit(self, world_size, rank, unique_id):
+        check(lib().apt_comm_init(self._h, int(world_size), int(rank), (C.c_ubyte * 128)(*unique_id)))
+        self._comm = (int(world_size), int(rank))
+
+    def commAllReduceSum(self, vec):
+        buf = np.ascontiguousarray(vec, dtype=np.float64).copy()
+        check(lib().apt_comm_allreduce_sum(self._h, _dp(buf), buf.size))
+        return buf
+
+    def commFinalize(self):
+        check(lib().apt_comm_finalize(self._h))
 
     def getTimes(self):
         """getTimes() (APT:552-555) reports per-sampler wall times in the reference; here: CUDA-event timing."""
         t = Timing()
         check(lib().apt_get_timing(self._h, C.byref(t)))
-        return dict(kernel_ms=t.kernel_ms, main_kernel_ms=t.main_kernel_ms, launches=t.launches, main_launches=t.main_launches)
+        return dict(kernel_ms=t.kernel_ms, main_kernel_ms=t.main_kernel_ms, launches=t.launches, main_launches=t.main_launches,
+                    run_wall_ms=t.run_wall_ms, gather_tail_ms=t.gather_tail_ms)
 
     # ---- member data read after run
     @property

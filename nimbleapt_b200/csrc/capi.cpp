@@ -5,7 +5,9 @@
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <chrono>
 #include <string>
+#include <vector>
 #include "engine/apt_module_abi.h"
 #include "front.h"
 
@@ -28,6 +30,7 @@ struct ModFns {
     int (*set_model_theta)(void*, const double*, int, char*, int);
     int (*set_array)(void*, int, const double*, int64_t, char*, int);
     void (*timing_get)(void*, aptmod_timing*);
+    void* (*stream)(void*);
     int (*device_ptr)(void*, int, void**, int64_t*, void**);
     int (*waic)(void*, long long, int, double*, char*, int);
 };
@@ -37,13 +40,19 @@ struct apt_engine {
     void* mod = nullptr;
     ModFns fn{};
     Lowered low;
-    int n_ladders = 1, device = 0, enable_waic = 0;
+    int n_ladders = 1, device = 0, enable_waic = 0, thin_conf = 1;
     // NCCL (lazy)
     void* nccl_dl = nullptr;
     void* comm = nullptr;
     int world = 1, rank = 0;
-    void* gather_buf = nullptr;  // device destination of the trace all-gather, kept between calls (grow only)
+    void* gather_buf = nullptr;  // device destination of the trace gathers, kept between calls (grow only)
     size_t gather_cap = 0;
+    void* scratch = nullptr;     // small persistent device buffer: pooled statistics (all-reduce), ladder counts
+    size_t scratch_cap = 0;
+    std::vector<int64_t> peer_ladders;  // ladders held by every rank (ranks may hold different numbers)
+    void* copy_stream = nullptr;        // device-to-host copies of gathered pieces, overlapping the next piece's sampling
+    std::vector<void*> events;          // one per piece of a gathering run
+    apt_timing last{};
 };
 
 #define API_BEGIN try {
@@ -86,6 +95,7 @@ void apt_build_opts_default(apt_build_opts* o) {
 void apt_run_args_default(apt_run_args* a) {
     memset(a, 0, sizeof *a);
     a->reset = 1; a->adaptTemps = 1; a->tuneTemper1 = 10; a->tuneTemper2 = 1; a->progressBar = 1; a->thin = -1; a->thin2 = -1;
+    a->gather = 0; a->gather_root = 0;
 }
 
 int apt_model_create(const char* bugs_code, apt_model** out) {
@@ -263,6 +273,7 @@ int apt_build(apt_model* m, const double* temps, int n_temps, const apt_build_op
         e->fn.set_array = (decltype(e->fn.set_array))sym("aptmod_set_array");
         e->fn.timing_get = (decltype(e->fn.timing_get))sym("aptmod_timing_get");
         e->fn.device_ptr = (decltype(e->fn.device_ptr))dlsym(e->dl, "aptmod_device_ptr");
+        e->fn.stream = (decltype(e->fn.stream))sym("aptmod_stream");
         e->fn.waic = (decltype(e->fn.waic))sym("aptmod_waic");
         aptmod_init in{};
         in.n_ladders = o.n_ladders; in.ladder0 = o.ladder0; in.seed = o.seed; in.device = o.device;
@@ -281,6 +292,7 @@ int apt_build(apt_model* m, const double* temps, int n_temps, const apt_build_op
         char err[2048] = {0};
         if (e->fn.create(&in, &e->mod, err, sizeof err)) throw Error(err);
         e->n_ladders = o.n_ladders; e->device = o.device; e->enable_waic = o.enable_waic;
+        e->thin_conf = m->spec.thin > 0 ? m->spec.thin : 1;
         // arrays were copied to the device: drop the borrowed pointers
         e->low.arrays.clear();
     } catch (...) {
@@ -301,10 +313,25 @@ void apt_free(apt_engine* e) {
     delete e;
 }
 
+struct GatherRun;
+static int gather_chunk_cb(void* arg, const double* d_packed, int64_t n, int64_t row0, int64_t row1, void* stream);
+static void gather_run_begin(apt_engine* e, const apt_run_args* args, GatherRun& g, aptmod_run_args& ra);
+static void gather_run_end(apt_engine* e, GatherRun& g, bool run_ok);
+struct GatherRun {
+    apt_engine* e = nullptr;
+    int root = 0, piece = 0;
+    bool active = false, deliver = false;
+    double* out = nullptr;
+    int64_t nr = 0, cols = 0, sumL = 0;
+    std::vector<int64_t> loff;  // first ladder of every rank in the gathered order
+    std::string err;
+};
+
 int apt_run(apt_engine* e, const apt_run_args* args) {
     API_BEGIN
     if (!e || !args) throw Error("null argument");
     if (args->simulateAll) throw Error("simulateAll = TRUE is not supported by the device engine (set initial values with apt_set_inits)");
+    const auto t0 = std::chrono::steady_clock::now();
     aptmod_run_args ra{};
     ra.niter = args->niter; ra.reset = args->reset; ra.resetMV = args->resetMV; ra.resetTempering = args->resetTempering;
     ra.adaptTemps = args->adaptTemps; ra.tuneTemper1 = args->tuneTemper1; ra.tuneTemper2 = args->tuneTemper2;
@@ -312,8 +339,20 @@ int apt_run(apt_engine* e, const apt_run_args* args) {
     ra.tabZ = args->inject_normals; ra.tabU = args->inject_accept_u; ra.tabS = args->inject_swap_u;
     ra.should_abort = args->should_abort; ra.abort_arg = args->abort_arg; ra.iters_per_launch = args->iters_per_launch;
     ra.samples_out = args->samples_out; ra.samples_out_cap = args->samples_out_capacity;
+    GatherRun g;
+    if (args->gather) gather_run_begin(e, args, g, ra);
     char err[2048] = {0};
-    if (e->fn.run(e->mod, &ra, err, sizeof err)) throw Error(err);
+    const int rc = e->fn.run(e->mod, &ra, err, sizeof err);
+    const auto t1 = std::chrono::steady_clock::now();
+    if (g.active) gather_run_end(e, g, rc == 0);
+    const auto t2 = std::chrono::steady_clock::now();
+    if (rc) throw Error(g.err.empty() ? std::string(err) : g.err);
+    if (!g.err.empty()) throw Error(g.err);
+    aptmod_timing mt{};
+    e->fn.timing_get(e->mod, &mt);
+    e->last.kernel_ms = mt.kernel_ms; e->last.main_kernel_ms = mt.main_kernel_ms; e->last.launches = mt.launches; e->last.main_launches = mt.main_launches;
+    e->last.run_wall_ms = std::chrono::duration<double, std::milli>(t2 - t0).count();
+    e->last.gather_tail_ms = std::chrono::duration<double, std::milli>(t2 - t1).count();
     if (args->printTemps) {  // nimPrint(iter, " ", totalIters-1, " ", size_mvSamples, " ", size_mvSamples2, asRow(Temps))  APT:524
         std::vector<double> t((size_t)e->low.K);
         int64_t n = 0;
@@ -346,6 +385,7 @@ int apt_get_timing(apt_engine* e, apt_timing* t) {
     API_BEGIN
     aptmod_timing mt{};
     e->fn.timing_get(e->mod, &mt);
+    *t = e->last;  // host-clock figures of the last apt_run
     t->kernel_ms = mt.kernel_ms; t->main_kernel_ms = mt.main_kernel_ms; t->launches = mt.launches; t->main_launches = mt.main_launches;
     API_END
 }
@@ -420,8 +460,15 @@ struct RtFns {
     int (*Free)(void*);
     int (*Memcpy)(void*, const void*, size_t, int);
     int (*MemcpyAsync)(void*, const void*, size_t, int, void*);
+    int (*Memcpy2DAsync)(void*, size_t, const void*, size_t, size_t, size_t, int, void*);
     int (*DeviceSynchronize)(void);
     int (*StreamSynchronize)(void*);
+    int (*StreamCreateWithFlags)(void**, unsigned);
+    int (*StreamDestroy)(void*);
+    int (*EventCreateWithFlags)(void**, unsigned);
+    int (*EventDestroy)(void*);
+    int (*EventRecord)(void*, void*);
+    int (*StreamWaitEvent)(void*, void*, unsigned);
 };
 static RtFns g_rt{};
 
@@ -466,6 +513,13 @@ static void load_nccl() {
     g_rt.MemcpyAsync = (decltype(g_rt.MemcpyAsync))r("cudaMemcpyAsync");
     g_rt.DeviceSynchronize = (decltype(g_rt.DeviceSynchronize))r("cudaDeviceSynchronize");
     g_rt.StreamSynchronize = (decltype(g_rt.StreamSynchronize))r("cudaStreamSynchronize");
+    g_rt.Memcpy2DAsync = (decltype(g_rt.Memcpy2DAsync))r("cudaMemcpy2DAsync");
+    g_rt.StreamCreateWithFlags = (decltype(g_rt.StreamCreateWithFlags))r("cudaStreamCreateWithFlags");
+    g_rt.StreamDestroy = (decltype(g_rt.StreamDestroy))r("cudaStreamDestroy");
+    g_rt.EventCreateWithFlags = (decltype(g_rt.EventCreateWithFlags))r("cudaEventCreateWithFlags");
+    g_rt.EventDestroy = (decltype(g_rt.EventDestroy))r("cudaEventDestroy");
+    g_rt.EventRecord = (decltype(g_rt.EventRecord))r("cudaEventRecord");
+    g_rt.StreamWaitEvent = (decltype(g_rt.StreamWaitEvent))r("cudaStreamWaitEvent");
 }
 #define NCCL_OK(x)                                                                             \
     do {                                                                                       \
@@ -487,16 +541,53 @@ int apt_comm_unique_id(unsigned char id_out[128]) {
     API_END
 }
 
+static void ensure_dev(void*& buf, size_t& cap, size_t bytes) {
+    if (bytes <= cap) return;
+    if (buf) g_rt.Free(buf);
+    buf = nullptr; cap = 0;
+    RT_OK(g_rt.Malloc(&buf, bytes));
+    cap = bytes;
+}
+// rows x columns of 8-byte elements between two pitched layouts; cudaMemcpy2D rejects pitches of 2 GiB and more
+static void copy_2d(double* dst, size_t dpitch_d, const double* src, size_t spitch_d, size_t width_d, size_t height, int kind, void* stream) {
+    if (!width_d || !height) return;
+    const size_t lim = (size_t)1 << 31;
+    if (height > 1 && dpitch_d * 8 < lim && spitch_d * 8 < lim)
+        RT_OK(g_rt.Memcpy2DAsync(dst, dpitch_d * 8, src, spitch_d * 8, width_d * 8, height, kind, stream));
+    else
+        for (size_t h = 0; h < height; h++) RT_OK(g_rt.MemcpyAsync(dst + h * dpitch_d, src + h * spitch_d, width_d * 8, kind, stream));
+}
+
 int apt_comm_init(apt_engine* e, int world_size, int rank, const unsigned char unique_id[128]) {
     API_BEGIN
     load_nccl();
     if (e->comm) throw Error("communicator already initialised");
+    if (world_size < 1 || rank < 0 || rank >= world_size) throw Error("rank is not in [0, world_size)");
     nccl_uid id;
     memcpy(&id, unique_id, 128);
     RT_OK(g_rt.SetDevice(e->device));
     NCCL_OK(g_nccl.CommInitRank(&e->comm, world_size, id, rank));
     e->world = world_size; e->rank = rank;
+    // Ranks may hold different numbers of ladders (sharding.py::shard_ladders gives the first ranks one more when the
+    // total does not divide): every rank learns every rank's count once, here; the gathers size their pieces from it.
+    ensure_dev(e->scratch, e->scratch_cap, std::max<size_t>(64 * 1024, (size_t)world_size * 16));
+    void* stream = e->fn.stream(e->mod);
+    std::vector<double> cnt((size_t)world_size, 0.0);
+    cnt[(size_t)rank] = (double)e->n_ladders;
+    double* d = (double*)e->scratch;
+    RT_OK(g_rt.MemcpyAsync(d + world_size + rank, &cnt[(size_t)rank], 8, 1 /* H2D */, stream));
+    NCCL_OK(g_nccl.AllGather(d + world_size + rank, d, 1, 8 /* ncclFloat64 */, e->comm, stream));
+    RT_OK(g_rt.MemcpyAsync(cnt.data(), d, (size_t)world_size * 8, 2 /* D2H */, stream));
+    RT_OK(g_rt.StreamSynchronize(stream));
+    e->peer_ladders.assign((size_t)world_size, 0);
+    for (int r = 0; r < world_size; r++) e->peer_ladders[(size_t)r] = (int64_t)cnt[(size_t)r];
+    if (e->peer_ladders[(size_t)rank] != e->n_ladders) throw Error("NCCL all-gather of the ladder counts returned a wrong own count");
     API_END
+}
+
+// doubles of a trace held by rank r, given this rank's n_local doubles for its own ladders (same rows x columns everywhere)
+static int64_t peer_count(const apt_engine* e, int r, int64_t n_local) {
+    return n_local / std::max(1, e->n_ladders) * e->peer_ladders[(size_t)r];
 }
 
 // NCCL type/op codes: ncclFloat64 = 8, ncclSum = 0
@@ -504,22 +595,35 @@ int apt_comm_allgather_samples(apt_engine* e, int what, double* out, int64_t cap
     API_BEGIN
     if (!e->comm) throw Error("apt_comm_init has not been called");
     RT_OK(g_rt.SetDevice(e->device));
-    // stage through the getter (device -> host) is avoided: gather straight from the device-resident trace
+    // staging through the getter (device -> host) is avoided: gather straight from the device-resident trace
     if (!e->fn.device_ptr) throw Error("module lacks aptmod_device_ptr");
     void* dptr = nullptr; int64_t n_local = 0; void* stream = nullptr;
     if (e->fn.device_ptr(e->mod, what, &dptr, &n_local, &stream)) throw Error("trace not available on the device");
-    const int64_t total = n_local * e->world;
+    int64_t total = 0;
+    bool equal = true;
+    std::vector<int64_t> off((size_t)e->world);
+    for (int r = 0; r < e->world; r++) {
+        off[(size_t)r] = total;
+        total += peer_count(e, r, n_local);
+        equal &= e->peer_ladders[(size_t)r] == e->n_ladders;
+    }
     if (total > capacity) throw Error("output buffer too small");
     // the gathered traces land in a device buffer the engine keeps (a cudaMalloc / cudaFree pair per call costs
     // milliseconds and makes NCCL register a new buffer every time); the copy to the caller's host buffer is queued
     // on the same stream right behind the collective
-    if ((size_t)total * 8 > e->gather_cap) {
-        if (e->gather_buf) g_rt.Free(e->gather_buf);
-        e->gather_buf = nullptr; e->gather_cap = 0;
-        RT_OK(g_rt.Malloc(&e->gather_buf, (size_t)total * 8));
-        e->gather_cap = (size_t)total * 8;
+    ensure_dev(e->gather_buf, e->gather_cap, (size_t)std::max<int64_t>(total, 1) * 8);
+    if (equal) {
+        NCCL_OK(g_nccl.AllGather(dptr, e->gather_buf, (size_t)n_local, 8 /* ncclFloat64 */, e->comm, stream));
+    } else {  // different ladder counts: every rank sends its share to every other one (grouped point-to-point)
+        RT_OK(g_rt.MemcpyAsync((double*)e->gather_buf + off[(size_t)e->rank], dptr, (size_t)n_local * 8, 3 /* D2D */, stream));
+        NCCL_OK(g_nccl.GroupStart());
+        for (int r = 0; r < e->world; r++)
+            if (r != e->rank) {
+                NCCL_OK(g_nccl.Send(dptr, (size_t)n_local, 8, r, e->comm, stream));
+                NCCL_OK(g_nccl.Recv((double*)e->gather_buf + off[(size_t)r], (size_t)peer_count(e, r, n_local), 8, r, e->comm, stream));
+            }
+        NCCL_OK(g_nccl.GroupEnd());
     }
-    NCCL_OK(g_nccl.AllGather(dptr, e->gather_buf, (size_t)n_local, 8 /* ncclFloat64 */, e->comm, stream));
     RT_OK(g_rt.MemcpyAsync(out, e->gather_buf, (size_t)total * 8, 2 /* D2H */, stream));
     RT_OK(g_rt.StreamSynchronize(stream));
     if (n_written) *n_written = total;
@@ -530,7 +634,8 @@ int apt_comm_allgather_samples(apt_engine* e, int what, double* out, int64_t cap
 // is the only one that needs every rank's traces in host memory.  With the all-gather above every rank copies
 // world x its own share over PCIe into the same host memory at the same time, which is what limited the end-to-end
 // figure at 8 GPUs; here the other ranks only send their device-resident trace over NVLink (grouped ncclSend/ncclRecv)
-// and the device-to-host copy happens once.
+// and the device-to-host copy happens once.  This entry point gathers a WHOLE trace after the run; a run that should
+// hand its rows over while it is still sampling uses apt_run_args.gather instead (below).
 int apt_comm_gather_samples(apt_engine* e, int what, int root, double* out, int64_t capacity, int64_t* n_written) {
     API_BEGIN
     if (!e->comm) throw Error("apt_comm_init has not been called");
@@ -545,55 +650,127 @@ int apt_comm_gather_samples(apt_engine* e, int what, int root, double* out, int6
         RT_OK(g_rt.StreamSynchronize(stream));
         return 0;
     }
-    const int64_t total = n_local * e->world;
-    if (total > capacity) throw Error("output buffer too small");
-    if ((size_t)total * 8 > e->gather_cap) {
-        if (e->gather_buf) g_rt.Free(e->gather_buf);
-        e->gather_buf = nullptr; e->gather_cap = 0;
-        RT_OK(g_rt.Malloc(&e->gather_buf, (size_t)total * 8));
-        e->gather_cap = (size_t)total * 8;
-    }
+    int64_t total = 0;
+    std::vector<int64_t> off((size_t)e->world);
+    for (int r = 0; r < e->world; r++) { off[(size_t)r] = total; total += peer_count(e, r, n_local); }
+    // a root that cannot deliver still receives what its peers are sending (they would wait for ever otherwise)
+    const bool deliver = out && total <= capacity;
+    ensure_dev(e->gather_buf, e->gather_cap, (size_t)std::max<int64_t>(total, 1) * 8);
     // the root's own share goes straight to the caller's buffer while the peers' shares arrive over NVLink
-    RT_OK(g_rt.MemcpyAsync(out + (size_t)root * n_local, dptr, (size_t)n_local * 8, 2 /* D2H */, stream));
+    if (deliver) RT_OK(g_rt.MemcpyAsync(out + off[(size_t)root], dptr, (size_t)n_local * 8, 2 /* D2H */, stream));
     NCCL_OK(g_nccl.GroupStart());
     for (int r = 0; r < e->world; r++)
         if (r != root)
-            NCCL_OK(g_nccl.Recv((double*)e->gather_buf + (size_t)r * n_local, (size_t)n_local, 8, r, e->comm, stream));
+            NCCL_OK(g_nccl.Recv((double*)e->gather_buf + off[(size_t)r], (size_t)peer_count(e, r, n_local), 8, r, e->comm, stream));
     NCCL_OK(g_nccl.GroupEnd());
-    if (root > 0) RT_OK(g_rt.MemcpyAsync(out, e->gather_buf, (size_t)root * n_local * 8, 2, stream));
-    if (root + 1 < e->world)
-        RT_OK(g_rt.MemcpyAsync(out + (size_t)(root + 1) * n_local, (double*)e->gather_buf + (size_t)(root + 1) * n_local,
-                               (size_t)(e->world - root - 1) * n_local * 8, 2, stream));
+    if (deliver && root > 0) RT_OK(g_rt.MemcpyAsync(out, e->gather_buf, (size_t)off[(size_t)root] * 8, 2, stream));
+    if (deliver && root + 1 < e->world)
+        RT_OK(g_rt.MemcpyAsync(out + off[(size_t)root + 1], (double*)e->gather_buf + off[(size_t)root + 1],
+                               (size_t)(total - off[(size_t)root + 1]) * 8, 2, stream));
     RT_OK(g_rt.StreamSynchronize(stream));
+    if (!deliver) throw Error("output buffer too small");
     if (n_written) *n_written = total;
     API_END
+}
+
+// ---- apt_run_args.gather: the rows a run writes travel to the root WHILE the run goes on.  After every piece of the run
+// (the module splits it into 4-8 launches) the module packs the piece's rows on its stream and calls gather_chunk_cb:
+// a non-root rank enqueues one ncclSend of the packed piece, the root one group of ncclRecv into its gather buffer, both
+// on the engine's stream BETWEEN two sampling launches -- an NCCL kernel running beside the sampling kernel would take
+// SM slots the ladder-resident kernel needs to keep every ladder resident.  The root then copies the piece to the caller's
+// host buffer on a second stream (copy engine), which does overlap the next piece's sampling.  What is left when the
+// last launch ends is one piece's send + copy.
+static void gather_run_begin(apt_engine* e, const apt_run_args* args, GatherRun& g, aptmod_run_args& ra) {
+    if (!e->comm) throw Error("apt_run_args.gather needs a communicator: call apt_comm_init first");
+    if (args->gather_root < 0 || args->gather_root >= e->world) throw Error("gather_root is not a rank of the communicator");
+    RT_OK(g_rt.SetDevice(e->device));
+    const int thin = args->thin != -1 ? args->thin : e->thin_conf;
+    if (thin < 1) throw Error("thin and thin2 must be >= 1");
+    g.e = e; g.root = args->gather_root; g.active = true; g.piece = 0;
+    g.nr = args->niter / thin;
+    g.cols = e->fn.info(e->mod, APTMOD_INFO_NMON);
+    g.loff.assign((size_t)e->world + 1, 0);
+    for (int r = 0; r < e->world; r++) g.loff[(size_t)r + 1] = g.loff[(size_t)r] + e->peer_ladders[(size_t)r];
+    g.sumL = g.loff[(size_t)e->world];
+    g.out = args->samples_out;
+    if (e->rank == g.root) {
+        g.deliver = g.out && g.sumL * g.nr * g.cols <= args->samples_out_capacity;
+        if (!g.deliver) g.err = "samples_out: buffer too small for (ladders of all ranks) x (niter / thin) x n_monitors doubles";
+        ensure_dev(e->gather_buf, e->gather_cap, (size_t)std::max<int64_t>(g.sumL * g.nr * g.cols, 1) * 8);
+        if (!e->copy_stream) RT_OK(g_rt.StreamCreateWithFlags(&e->copy_stream, 1 /* cudaStreamNonBlocking */));
+    }
+    ra.samples_out = nullptr; ra.samples_out_cap = 0;
+    ra.chunk_cb = gather_chunk_cb; ra.chunk_arg = &g;
+}
+
+static int gather_chunk_cb(void* arg, const double* d_packed, int64_t n, int64_t row0, int64_t row1, void* stream) {
+    GatherRun& g = *static_cast<GatherRun*>(arg);
+    apt_engine* e = g.e;
+    try {
+        const int64_t w = (row1 - row0) * g.cols;  // doubles per ladder in this piece
+        if (n != w * e->n_ladders) throw Error("gather: unexpected piece size");
+        if (e->rank != g.root) {
+            NCCL_OK(g_nccl.Send(d_packed, (size_t)n, 8 /* ncclFloat64 */, g.root, e->comm, stream));
+        } else {
+            // piece layout in the gather buffer: [all ladders, rank-major][row1 - row0][cols], pieces one after the other
+            double* base = (double*)e->gather_buf + (size_t)g.sumL * row0 * g.cols;
+            RT_OK(g_rt.MemcpyAsync(base + (size_t)g.loff[(size_t)g.root] * w, d_packed, (size_t)n * 8, 3 /* D2D */, stream));
+            if (e->world > 1) {
+                NCCL_OK(g_nccl.GroupStart());
+                for (int r = 0; r < e->world; r++)
+                    if (r != g.root)
+                        NCCL_OK(g_nccl.Recv(base + (size_t)g.loff[(size_t)r] * w, (size_t)(e->peer_ladders[(size_t)r] * w), 8, r, e->comm, stream));
+                NCCL_OK(g_nccl.GroupEnd());
+            }
+            if (g.deliver) {
+                while ((int)e->events.size() <= g.piece) {
+                    void* ev = nullptr;
+                    RT_OK(g_rt.EventCreateWithFlags(&ev, 2 /* cudaEventDisableTiming */));
+                    e->events.push_back(ev);
+                }
+                RT_OK(g_rt.EventRecord(e->events[(size_t)g.piece], stream));
+                RT_OK(g_rt.StreamWaitEvent(e->copy_stream, e->events[(size_t)g.piece], 0));
+                copy_2d(g.out + (size_t)row0 * g.cols, (size_t)g.nr * g.cols, base, (size_t)w, (size_t)w, (size_t)g.sumL, 2 /* D2H */, e->copy_stream);
+            }
+        }
+        g.piece++;
+        return 0;
+    } catch (const std::exception& x) {
+        g.err = x.what();
+        return 1;
+    }
+}
+
+static void gather_run_end(apt_engine* e, GatherRun& g, bool run_ok) {
+    (void)run_ok;
+    if (e->rank == g.root && e->copy_stream) g_rt.StreamSynchronize(e->copy_stream);
 }
 
 int apt_comm_allreduce_sum(apt_engine* e, double* inout, int64_t n) {
     API_BEGIN
     if (!e->comm) throw Error("apt_comm_init has not been called");
+    if (n < 0 || (n > 0 && !inout)) throw Error("null argument");
     RT_OK(g_rt.SetDevice(e->device));
-    void* d = nullptr;
-    RT_OK(g_rt.Malloc(&d, (size_t)n * 8));
-    try {
-        RT_OK(g_rt.Memcpy(d, inout, (size_t)n * 8, 1 /* H2D */));
-        NCCL_OK(g_nccl.AllReduce(d, d, (size_t)n, 8 /* ncclFloat64 */, 0 /* ncclSum */, e->comm, nullptr));
-        RT_OK(g_rt.DeviceSynchronize());
-        RT_OK(g_rt.Memcpy(inout, d, (size_t)n * 8, 2));
-    } catch (...) {
-        g_rt.Free(d);
-        throw;
-    }
-    g_rt.Free(d);
+    // persistent device scratch and the engine's own stream: no allocation, no device-wide synchronisation per call
+    ensure_dev(e->scratch, e->scratch_cap, std::max<size_t>(64 * 1024, (size_t)n * 8));
+    void* stream = e->fn.stream(e->mod);
+    RT_OK(g_rt.MemcpyAsync(e->scratch, inout, (size_t)n * 8, 1 /* H2D */, stream));
+    NCCL_OK(g_nccl.AllReduce(e->scratch, e->scratch, (size_t)n, 8 /* ncclFloat64 */, 0 /* ncclSum */, e->comm, stream));
+    RT_OK(g_rt.MemcpyAsync(inout, e->scratch, (size_t)n * 8, 2 /* D2H */, stream));
+    RT_OK(g_rt.StreamSynchronize(stream));
     API_END
 }
 
 int apt_comm_finalize(apt_engine* e) {
     API_BEGIN
-    if (e && e->gather_buf) {
+    if (e && (e->gather_buf || e->scratch || e->copy_stream || !e->events.empty())) {
         g_rt.SetDevice(e->device);
-        g_rt.Free(e->gather_buf);
-        e->gather_buf = nullptr; e->gather_cap = 0;
+        if (e->gather_buf) g_rt.Free(e->gather_buf);
+        if (e->scratch) g_rt.Free(e->scratch);
+        for (void* ev : e->events) g_rt.EventDestroy(ev);
+        if (e->copy_stream) g_rt.StreamDestroy(e->copy_stream);
+        e->gather_buf = nullptr; e->gather_cap = 0; e->scratch = nullptr; e->scratch_cap = 0; e->copy_stream = nullptr;
+        e->events.clear();
     }
     if (e && e->comm) {
         g_nccl.CommDestroy(e->comm);

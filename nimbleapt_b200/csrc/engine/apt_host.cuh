@@ -107,12 +107,35 @@ struct Engine {
     double* so_ptr = nullptr;
     long long so_nr = 0, so_off = 0;
     int so_thin = 1;
+    // device-side hand-off of the same rows (aptmod_run_args.chunk_cb: the NCCL gather lives in the front library)
+    int (*chunk_cb)(void*, const double*, int64_t, int64_t, int64_t, void*) = nullptr;
+    void* chunk_arg = nullptr;
+    DevBuf<double> pack;
+    // trace rows [r0, r1) of all L ladders between two [L][pitch rows][cols] layouts; cudaMemcpy2D rejects pitches of 2 GiB
+    // and more (cudaDevAttrMaxPitch), so very long traces go ladder by ladder
+    static void copy_rows_2d(double* dst, size_t dpitch_d, const double* src, size_t spitch_d, size_t width_d, int nl,
+                             cudaMemcpyKind kind, cudaStream_t s) {
+        if (width_d == 0 || nl <= 0) return;
+        const size_t lim = (size_t)1 << 31;
+        if (nl > 1 && dpitch_d * 8 < lim && spitch_d * 8 < lim)
+            APT_CUDA(cudaMemcpy2DAsync(dst, dpitch_d * 8, src, spitch_d * 8, width_d * 8, (size_t)nl, kind, s));
+        else
+            for (int l = 0; l < nl; l++) APT_CUDA(cudaMemcpyAsync(dst + (size_t)l * dpitch_d, src + (size_t)l * spitch_d, width_d * 8, kind, s));
+    }
     void copy_rows_async(long long it0, long long it1) {
-        if (!so_ptr) return;
+        if (!so_ptr && !chunk_cb) return;
         const long long r0 = it0 / so_thin, r1 = it1 / so_thin;  // rows of this run written by iterations [it0, it1)
         if (r1 <= r0) return;
-        APT_CUDA(cudaMemcpy2DAsync(so_ptr + (size_t)r0 * G::NMON, (size_t)so_nr * G::NMON * 8, samples.p + (size_t)(so_off + r0) * G::NMON,
-                                   (size_t)cap * G::NMON * 8, (size_t)(r1 - r0) * G::NMON * 8, L, cudaMemcpyDeviceToHost, copy_stream));
+        if (chunk_cb) {
+            double* dst = pack.p + (size_t)L * r0 * G::NMON;
+            copy_rows_2d(dst, (size_t)(r1 - r0) * G::NMON, samples.p + (size_t)(so_off + r0) * G::NMON, (size_t)cap * G::NMON,
+                         (size_t)(r1 - r0) * G::NMON, L, cudaMemcpyDeviceToDevice, stream);
+            if (chunk_cb(chunk_arg, dst, (int64_t)L * (r1 - r0) * G::NMON, r0, r1, (void*)stream))
+                throw ApiError{"the device-side hand-off of the thinned output failed (see the caller's error)"};
+            return;
+        }
+        copy_rows_2d(so_ptr + (size_t)r0 * G::NMON, (size_t)so_nr * G::NMON, samples.p + (size_t)(so_off + r0) * G::NMON,
+                     (size_t)cap * G::NMON, (size_t)(r1 - r0) * G::NMON, L, cudaMemcpyDeviceToHost, copy_stream);
     }
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::vector<DevBuf<double>> arrays;
@@ -270,8 +293,7 @@ struct Engine {
         DevBuf<double> nb;
         nb.alloc((size_t)L * newcap * cols);
         if (b.p && keep_rows > 0)
-            APT_CUDA(cudaMemcpy2DAsync(nb.p, (size_t)newcap * cols * 8, b.p, (size_t)oldcap * cols * 8, (size_t)keep_rows * cols * 8,
-                                       L, cudaMemcpyDeviceToDevice, s));
+            copy_rows_2d(nb.p, (size_t)newcap * cols, b.p, (size_t)oldcap * cols, (size_t)keep_rows * cols, L, cudaMemcpyDeviceToDevice, s);
         APT_CUDA(cudaStreamSynchronize(s));
         std::swap(b.p, nb.p);
         std::swap(b.n, nb.n);
@@ -329,29 +351,41 @@ struct Engine {
             if (ra->resetMV) { off = 0; off2 = 0; }
         }
         const long long nr = ra->niter / thin, nr2 = ra->niter / thin2;
+        // a continuation (reset = FALSE, APT:378-385) grows the capacity geometrically, so that a sequence of appending
+        // runs does not copy the whole trace every time; the Tmax traces exist only with monitorTmax (APT:314-317)
         if (off + nr > cap) {
             long long nc = off + nr;
+            if (off > 0) nc = std::max(nc, cap + cap / 2);
             grow_trace(samples, L, cap, nc, off, G::NMON, stream);
-            grow_trace(samplesT, L, cap, nc, off, G::NMON, stream);
+            if (monitor_tmax) grow_trace(samplesT, L, cap, nc, off, G::NMON, stream);
             grow_trace(logprobs, L, cap, nc, off, 1, stream);
             cap = nc;
         }
         if (off2 + nr2 > cap2) {
             long long nc = off2 + nr2;
+            if (off2 > 0) nc = std::max(nc, cap2 + cap2 / 2);
             grow_trace(samples2, L, cap2, nc, off2, G::NMON2, stream);
-            grow_trace(samples2T, L, cap2, nc, off2, G::NMON2, stream);
+            if (monitor_tmax) grow_trace(samples2T, L, cap2, nc, off2, G::NMON2, stream);
             cap2 = nc;
         }
         if (nr > ttcap) { temptraj.alloc((size_t)L * nr * K); ttcap = nr; }
-        rows = off + nr; rows2 = off2 + nr2; ttrows = nr;
-        so_ptr = (ra->samples_out && nr > 0 && G::NMON > 0) ? ra->samples_out : nullptr;
+        // the row counts follow the iterations that have actually run: an interrupted run (should_abort) or a failed
+        // launch must not report rows that were never written
+        rows = off; rows2 = off2; ttrows = 0;
+        auto rows_after = [&](long long it_done) { rows = off + it_done / thin; rows2 = off2 + it_done / thin2; ttrows = it_done / thin; };
+        chunk_cb = (ra->chunk_cb && nr > 0 && G::NMON > 0) ? ra->chunk_cb : nullptr;
+        chunk_arg = ra->chunk_arg;
+        so_ptr = (!chunk_cb && ra->samples_out && nr > 0 && G::NMON > 0) ? ra->samples_out : nullptr;
         if (so_ptr) {
             if ((long long)L * nr * G::NMON > ra->samples_out_cap) throw ApiError{"samples_out: buffer too small for n_ladders x (niter / thin) x n_monitors doubles"};
             if (!copy_stream) APT_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
-            so_nr = nr; so_off = off; so_thin = thin;
         }
-        // with a host destination the run is split into at least 4 launches, so that copying a piece overlaps the next
-        const long long so_chunk = so_ptr ? std::max<long long>(thin, ((ra->niter + 3) / 4 + thin - 1) / thin * thin) : 0;
+        if (so_ptr || chunk_cb) { so_nr = nr; so_off = off; so_thin = thin; }
+        if (chunk_cb && pack.n < (size_t)L * nr * G::NMON) pack.alloc((size_t)L * nr * G::NMON);
+        // with a destination the run is split into at least 4 launches (8 for long runs), so that moving a piece overlaps
+        // the sampling of the next one and only the last piece is left when the run ends
+        const long long so_pieces = ra->niter >= 8 * 64 * (long long)thin ? 8 : 4;
+        const long long so_chunk = (so_ptr || chunk_cb) ? std::max<long long>(thin, ((ra->niter + so_pieces - 1) / so_pieces + thin - 1) / thin * thin) : 0;
         refresh_lpd();
         // test hooks
         const size_t nz = (size_t)ra->niter * L * K * G::NU;
@@ -376,7 +410,9 @@ struct Engine {
         a.rec = record ? rec.p : nullptr; a.recswap = record ? recswap.p : nullptr;
         bool aborted = false;
         if constexpr (G::ENGINE == 2) {
-            aborted = run_grid(a, ra);
+            long long done = 0;
+            try { aborted = run_grid(a, ra, done); } catch (...) { rows_after(done); throw; }
+            rows_after(done);
         } else {
             long long chunk = ra->iters_per_launch > 0 ? ra->iters_per_launch : 4096;
             if (so_chunk > 0 && ra->iters_per_launch <= 0) chunk = std::min(chunk, so_chunk);
@@ -405,6 +441,7 @@ struct Engine {
                 timing.kernel_ms += ms; timing.main_kernel_ms += ms; timing.launches++; timing.main_launches++;
                 rngIter += (uint64_t)(a.it1 - a.it0);
                 totalIters += (a.it1 - a.it0);
+                rows_after(a.it1);
                 copy_rows_async(a.it0, a.it1);
             }
         }
@@ -414,6 +451,7 @@ struct Engine {
         timing.launches++;
         APT_CUDA(cudaStreamSynchronize(stream));
         if (so_ptr) { so_ptr = nullptr; APT_CUDA(cudaStreamSynchronize(copy_stream)); }
+        chunk_cb = nullptr;
         launches_total += timing.launches;
         if (aborted) throw ApiError{"run interrupted by the caller"};
     }
@@ -421,7 +459,7 @@ struct Engine {
     // grid engine: one launch per (iteration, stage, pass); chunks of iterations are self-contained (prologue
     // launch proposes, the last launch of the chunk does not propose ahead) so that a run can be interrupted
     // between chunks with the state consistent.  Returns true when interrupted.
-    bool run_grid(KArgs& a, const aptmod_run_args* ra) {
+    bool run_grid(KArgs& a, const aptmod_run_args* ra, long long& it_done) {
         if constexpr (G::ENGINE == 2) {
             GArgs g{};
             const int nchain = L * K;
@@ -472,6 +510,7 @@ struct Engine {
                 timing.kernel_ms += ms; timing.main_kernel_ms += ms; timing.launches += nl; timing.main_launches += nl - 1;
                 rngIter += (uint64_t)(it1 - it0);
                 totalIters += (it1 - it0);
+                it_done = it1;
                 copy_rows_async(it0, it1);
                 if (g.dbg) {
                     auto v = d2h(g_dbg.p, 80);
@@ -584,10 +623,8 @@ struct Engine {
         *n = (int64_t)L * nrows * cols;
         *strm = (void*)stream;
         if (capr == nrows) { *ptr = b->p; return; }
-        compact.alloc((size_t)std::max<int64_t>(*n, 1));
-        if (*n)
-            APT_CUDA(cudaMemcpy2DAsync(compact.p, (size_t)nrows * cols * 8, b->p, (size_t)capr * cols * 8, (size_t)nrows * cols * 8, L,
-                                       cudaMemcpyDeviceToDevice, stream));
+        if (compact.n < (size_t)std::max<int64_t>(*n, 1)) compact.alloc((size_t)std::max<int64_t>(*n, 1));
+        if (*n) copy_rows_2d(compact.p, (size_t)nrows * cols, b->p, (size_t)capr * cols, (size_t)nrows * cols, L, cudaMemcpyDeviceToDevice, stream);
         *ptr = compact.p;
     }
 
@@ -630,8 +667,8 @@ struct Engine {
         if (n > capn) throw ApiError{"output buffer too small"};
         if (n == 0) return;
         const double* src = b.p + (size_t)(ladder < 0 ? 0 : ladder) * capr * cols;
-        APT_CUDA(cudaMemcpy2DAsync(out, (size_t)nrows * cols * 8, src, (size_t)capr * cols * 8, (size_t)nrows * cols * 8, nl,
-                                   cudaMemcpyDeviceToHost, stream));
+        if (!b.p) throw ApiError{"this trace is not kept (monitorTmax = FALSE)"};
+        copy_rows_2d(out, (size_t)nrows * cols, src, (size_t)capr * cols, (size_t)nrows * cols, nl, cudaMemcpyDeviceToHost, stream);
         APT_CUDA(cudaStreamSynchronize(stream));
     }
 
@@ -783,6 +820,7 @@ inline void set_err(char* err, int errlen, const std::string& m) {
     }                                                                                                               \
     APT_EXPORT double aptmod_waic_ms(void* h) { return static_cast<apt::Engine<G>*>(h)->waic_ms; }                             \
     APT_EXPORT void aptmod_timing_get(void* h, aptmod_timing* t) { *t = static_cast<apt::Engine<G>*>(h)->timing; }             \
+    APT_EXPORT void* aptmod_stream(void* h) { return (void*)static_cast<apt::Engine<G>*>(h)->stream; }                          \
     APT_EXPORT int aptmod_device_ptr(void* h, int what, void** ptr, int64_t* n, void** strm) {                                 \
         try { static_cast<apt::Engine<G>*>(h)->device_ptr(what, ptr, n, strm); return 0; } catch (...) { return 1; }            \
     }                                                                                                               \

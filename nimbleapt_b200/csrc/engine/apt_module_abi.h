@@ -6,7 +6,7 @@
 #define APT_MODULE_ABI_H
 #include <stdint.h>
 
-#define APTMOD_ABI_VERSION 5
+#define APTMOD_ABI_VERSION 6
 
 #ifdef __cplusplus
 extern "C" {
@@ -46,6 +46,13 @@ typedef struct {
     int iters_per_launch;          /* 0 = default */
     double* samples_out;           /* host destination of this run's mvSamples rows [L][niter/thin][NMON], or null */
     int64_t samples_out_cap;       /* doubles */
+    /* Hand-off of this run's mvSamples rows to the caller ON THE DEVICE, piece by piece (the NCCL gather of
+     * include/aptb200.h: apt_run_args.gather): after the launch that wrote rows [row0, row1) of this run the module packs
+     * them into a contiguous device buffer [L][row1 - row0][NMON] and calls chunk_cb with the engine's stream, on which
+     * the packed rows are complete in stream order; whatever the callback enqueues there runs before the next launch.
+     * The packed buffer stays valid until the next run.  Non-zero return = error (the run stops with it). */
+    int (*chunk_cb)(void* arg, const double* d_packed, int64_t n_doubles, int64_t row0, int64_t row1, void* stream);
+    void* chunk_arg;
 } aptmod_run_args;
 
 enum {

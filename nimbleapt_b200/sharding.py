@@ -1,9 +1,9 @@
 """Host-side logic of the multi-GPU path: independent ladders are sharded across ranks, nothing is
 exchanged while sampling, and only traces / pooled statistics are gathered afterwards.
 
-On GPUs the gather and the pooled sums go through NCCL inside libaptb200.so (apt_comm_*).  The functions here are
-the rank arithmetic and the statistics pooling, written against a generic `torch.distributed`-like all_reduce so
-that they are testable with the gloo backend on CPU (tests/test_sharding_gloo.py)."""
+On GPUs the gather and the pooled sums go through NCCL inside libaptb200.so (apt_comm_*, apt_run_args.gather).  The
+functions here are the rank arithmetic and the statistics pooling (numpy only); tests/test_sharding_gloo.py drives them
+over 2 CPU ranks with the gloo backend."""
 import numpy as np
 
 
@@ -45,14 +45,3 @@ def ess_batch_means(x):
     v = x.var(ddof=1)
     vb = bm.var(ddof=1) * m
     return float(n * v / vb) if vb > 0 else float(n)
-
-
-def all_reduce_sum(vec, dist=None):
-    """Sum a small host vector over ranks with torch.distributed (gloo on CPU, nccl on GPU); identity without dist."""
-    if dist is None or not dist.is_initialized():
-        return np.asarray(vec, dtype=np.float64)
-    import torch
-    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
-    t = torch.as_tensor(np.asarray(vec, dtype=np.float64), device=dev)
-    dist.all_reduce(t, op=dist.ReduceOp.SUM)
-    return t.cpu().numpy()

@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 import models
-from nimbleapt_b200.sharding import all_reduce_sum, local_moments, pooled_mean_var, shard_ladders
+from nimbleapt_b200.sharding import local_moments, pooled_mean_var, shard_ladders
 
 
 def _free_port():
@@ -25,7 +25,7 @@ def _worker(rank, world, port, total, niter, out):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     sys.path[:0] = [root, os.path.join(root, "tests")]
     import torch.distributed as dist
-    from helpers import build_oracle
+    from helpers import all_reduce_sum, build_oracle
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
