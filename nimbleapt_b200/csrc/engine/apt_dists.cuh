@@ -400,69 +400,78 @@ __device__ __forceinline__ void bern_logit_acc(double y, const double (&eta)[N],
     }
 }
 
-// Thread tile of the grid engine: NR rows (each with its own y) x NC chains; rows are taken in groups so that 8
-// terms advance in lock step.  Same arithmetic and fix-ups as bern_logit_acc.
+// Thread tile of the grid engine: NR rows (each with its own y) x NC chains.  A batch is CPB chains x all NR rows (8 terms in
+// lock step); per chain the rows are accumulated in ascending order.  Same arithmetic and fix-ups as bern_logit_acc.
+// The literal branch (y = 0, eta > 8) is taken per CHAIN, i.e. per column of the tile: whether it is needed depends almost
+// only on how hot the chain is (a chain at T ~ 1e5 roams the prior and has |eta| > 8 on most rows, a cold chain never), and
+// the grid kernel deals the rungs to the threads with a stride (apt_grid.cuh), so that every thread of a warp holds exactly one
+// of the hottest rungs in the same column: the branch is warp-uniform in the steady state and its 1/w and log run on all
+// lanes for that one column, instead of on a quarter of the lanes for every column as with consecutive rungs per thread.
 template <int NR, int NC>
 __device__ __forceinline__ void bern_logit_tile(const double (&y)[NR], const double (&eta)[NR][NC], double (&acc)[NC]) {
 #ifndef APT_TILE_BATCH
 #define APT_TILE_BATCH 8
 #endif
-    constexpr int RPB = (NC >= APT_TILE_BATCH) ? 1 : ((APT_TILE_BATCH / NC) < NR ? (APT_TILE_BATCH / NC) : NR);  // rows per batch
-    constexpr int M = RPB * NC;
-    static_assert(NR % RPB == 0, "rows per thread must be a multiple of the batch");
+    constexpr int CPB = (NR >= APT_TILE_BATCH) ? 1 : ((APT_TILE_BATCH / NR) < NC ? (APT_TILE_BATCH / NR) : NC);  // chains per batch
+    constexpr int M = CPB * NR;
+    static_assert(NC % CPB == 0, "chains per thread must be a multiple of the batch");
+    bool valid = true, y0[NR];
+    double sgn[NR];
 #pragma unroll
-    for (int r0 = 0; r0 < NR; r0 += RPB) {
+    for (int r = 0; r < NR; r++) {
+        y0[r] = (y[r] == 0.0);
+        valid = valid && (y0[r] || y[r] == 1.0);
+        sgn[r] = 1.0 - 2.0 * y[r];
+    }
+#pragma unroll
+    for (int c0 = 0; c0 < NC; c0 += CPB) {
         double a[M], v[M];
-        int amax = 0, smax = (int)0x80000000;  // largest |eta|; largest eta among the y = 0 rows (high words)
-        bool valid = true;
+        int amax = 0, smax[CPB];  // largest |eta|; per chain the largest eta among the y = 0 rows (high words)
 #pragma unroll
-        for (int rr = 0; rr < RPB; rr++) {
-            const bool y0 = (y[r0 + rr] == 0.0);
-            valid = valid && (y0 || y[r0 + rr] == 1.0);
+        for (int cc = 0; cc < CPB; cc++) {
+            smax[cc] = (int)0x80000000;
 #pragma unroll
-            for (int j = 0; j < NC; j++) {
-                const double e = eta[r0 + rr][j];
+            for (int r = 0; r < NR; r++) {
+                const double e = eta[r][c0 + cc];
                 const int hi = __double2hiint(e);
                 amax = max(amax, hi & 0x7fffffff);
-                smax = max(smax, y0 ? hi : (int)0x80000000);
-                a[rr * NC + j] = fabs(e);
+                smax[cc] = max(smax[cc], y0[r] ? hi : (int)0x80000000);
+                a[cc * NR + r] = fabs(e);
             }
         }
         double w[M];  // 1 + exp(-|eta|)
         apt_softplus_neg_batch<M>(a, v, w);
 #pragma unroll
-        for (int rr = 0; rr < RPB; rr++) {
-            const double sgn = 1.0 - 2.0 * y[r0 + rr];
+        for (int cc = 0; cc < CPB; cc++)
 #pragma unroll
-            for (int j = 0; j < NC; j++) v[rr * NC + j] = fma(-0.5, fma(sgn, eta[r0 + rr][j], a[rr * NC + j]), -v[rr * NC + j]);
-        }
-        if (smax >= 0x40200000) {
-            // y = 0 and eta > 8: the reference's own chain p = 1/(1+exp(-eta)), q = 1-p, log(q), whose rounding the
-            // decisions of hot chains depend on (see above) -- for the whole batch in lock step, reusing 1+exp(-eta)
-            double lq[M];
+            for (int r = 0; r < NR; r++) v[cc * NR + r] = fma(-0.5, fma(sgn[r], eta[r][c0 + cc], a[cc * NR + r]), -v[cc * NR + r]);
 #pragma unroll
-            for (int j = 0; j < M; j++) lq[j] = 1.0 - 1.0 / w[j];
+        for (int cc = 0; cc < CPB; cc++)
+            if (smax[cc] >= 0x40200000) {
+                // y = 0 and eta > 8: the reference's own chain p = 1/(1+exp(-eta)), q = 1-p, log(q), whose rounding the
+                // decisions of hot chains depend on (see above) -- the rows of this chain in lock step, reusing 1+exp(-eta)
+                double lq[NR];
 #pragma unroll
-            for (int j = 0; j < M; j++) lq[j] = apt_log_pos(lq[j]);  // q == 0 -> -Inf
+                for (int r = 0; r < NR; r++) lq[r] = 1.0 - apt_rcp_1to2(w[cc * NR + r]);  // w in [1, 2]: bit for bit the quotient 1 / w
 #pragma unroll
-            for (int rr = 0; rr < RPB; rr++)
+                for (int r = 0; r < NR; r++) lq[r] = apt_log_q(lq[r]);  // q == 0 -> -Inf; q is 0 or normal (a multiple of 2^-53)
 #pragma unroll
-                for (int j = 0; j < NC; j++)
-                    if (y[r0 + rr] == 0.0 && eta[r0 + rr][j] > 8.0) v[rr * NC + j] = lq[rr * NC + j];
-        }
+                for (int r = 0; r < NR; r++)
+                    if (y0[r] && eta[r][c0 + cc] > 8.0) v[cc * NR + r] = lq[r];
+            }
         if (!valid || amax >= 0x40862800) {  // invalid response, |eta| >= 709, Inf, NaN: exact tests inside
 #pragma unroll
-            for (int rr = 0; rr < RPB; rr++)
+            for (int cc = 0; cc < CPB; cc++)
 #pragma unroll
-                for (int j = 0; j < NC; j++) {
-                    const double e = eta[r0 + rr][j];
-                    if (!valid || !(fabs(e) <= 709.0)) v[rr * NC + j] = bern_logit_fix(y[r0 + rr], e, v[rr * NC + j]);
+                for (int r = 0; r < NR; r++) {
+                    const double e = eta[r][c0 + cc];
+                    if (!valid || !(fabs(e) <= 709.0)) v[cc * NR + r] = bern_logit_fix(y[r], e, v[cc * NR + r]);
                 }
         }
 #pragma unroll
-        for (int rr = 0; rr < RPB; rr++)
+        for (int cc = 0; cc < CPB; cc++)
 #pragma unroll
-            for (int j = 0; j < NC; j++) acc[j] += v[rr * NC + j];
+            for (int r = 0; r < NR; r++) acc[c0 + cc] += v[cc * NR + r];
     }
 }
 

@@ -41,6 +41,14 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// Programmatic dependent launch: a pass kernel is launched with programmatic stream serialisation, so that its CTAs become
+// resident as the previous pass's CTAs leave (all but the one that runs the control step leave right after streaming), prime
+// their data rings -- the design matrix does not depend on the previous pass -- and then block in pdl_wait() until the previous
+// grid has completed and its writes (accepted states, ladder, next proposals) are visible.  Removes the launch gap and the
+// pipeline fill from the critical path between two passes.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 struct GArgs {
     KArgs k;
     double* partial;      // [grid][2][TB] per-CTA partial sums
@@ -199,10 +207,27 @@ __global__ void __launch_bounds__(G::GRID_THREADS, G::GRID_MINB) grid_pass_kerne
     const bool has_dcta = a.delta != nullptr && a.next_stage >= 0 && G::stage_is_block(a.next_stage) && gridDim.x > 2;
     const int nstream = (int)gridDim.x - (has_dcta ? 1 : 0);
     const bool is_dcta = has_dcta && blockIdx.x == gridDim.x - 1;
+    // the next pass may become resident as soon as every CTA of this one has started (it waits for our completion below)
+    pdl_launch_dependents();
+    // tile mode: the first blocks of this warp's first tile are on their way before anything of the previous pass is needed
+    [[maybe_unused]] long wt0 = 0;
+    if constexpr (S::TILE) {
+        wt0 = (long)warp * nstream + blockIdx.x;
+        if (!is_dcta && wt0 < S::big_n(0) / S::TROWS) S::template ring_prime<0>(a.k.D, xbuf, tid, (int)(wt0 * S::TROWS));
+    }
+    pdl_wait();
     if (is_dcta) { grid_precompute_delta<G>(a, tid); if (a.dbg && tid == 0) a.dbg[7] = clock64() - t_start; }
-    // ---- 1. proposed states of this pass's chains -> shared memory, param-major / chain-minor
+    // ---- 1. proposed states of this pass's chains -> shared memory, param-major / chain-minor.
+    //         CS threads share a row (tile mode: a row group), each owning TBT = TB / CS of the chains.  In tile mode the
+    //         chains are dealt to the CS threads with a stride: position (h, c) of the staged parameters holds chain
+    //         c * CS + h, so that a thread's c-th chain is one of rungs [c * CS, (c + 1) * CS) -- every thread of a warp holds
+    //         one of the CS hottest rungs in the same column of its tile (see bern_logit_tile: the branch that reproduces
+    //         the reference's rounding for hot chains is then warp-uniform).  Partial sums travel by position.
+    constexpr int CS = S::TILE ? S::CS : G::CSPLIT, TBT = TB / CS, RPC = THREADS / CS;
+    auto chain_of_pos = [](int pos) { return S::TILE ? (pos % TBT) * CS + pos / TBT : pos; };
+    auto pos_of_chain = [](int q) { return S::TILE ? (q % CS) * TBT + q / CS : q; };
     for (int idx = tid; idx < P * TB; idx += THREADS) {
-        const int p = idx / TB, cc = idx % TB;
+        const int p = idx / TB, cc = chain_of_pos(idx % TB);
         int q = q0 + cc;
         if (q >= nch) q = nch - 1;
         const int l = q / K, kk = q % K;
@@ -210,9 +235,7 @@ __global__ void __launch_bounds__(G::GRID_THREADS, G::GRID_MINB) grid_pass_kerne
         thT[idx] = a.k.theta[((size_t)l * K + sl) * P + p];
     }
     __syncthreads();
-    // ---- 2. one pass over the data.  CS threads share a row (tile mode: a row group), each owning TBT = TB / CS of
-    //         the chains
-    constexpr int CS = S::TILE ? S::CS : G::CSPLIT, TBT = TB / CS, RPC = THREADS / CS;
+    // ---- 2. one pass over the data
     const int half = S::TILE ? (lane % CS) : (tid % CS), coff = half * TBT;
     double acc[NB][TBT];
 #pragma unroll
@@ -225,9 +248,8 @@ __global__ void __launch_bounds__(G::GRID_THREADS, G::GRID_MINB) grid_pass_kerne
         constexpr int TR = S::TROWS;
         const long n = S::big_n(0);
         const long ntile = is_dcta ? 0 : n / TR, wstep = (long)nstream * NWARP;
-        long wt = (long)warp * nstream + blockIdx.x;
+        long wt = wt0;
         int ring_pos = 0;
-        if (wt < ntile) S::template ring_prime<0>(a.k.D, xbuf, tid, (int)(wt * TR));
         for (; wt < ntile; wt += wstep)
             S::template big_eval<0, TBT, S::RT>(a.k.D, thT + coff, (int)(wt * TR), wt + wstep < ntile ? (int)((wt + wstep) * TR) : -1, acc[0], xbuf, ring_pos, tid);
         cp_async_wait<0>();
@@ -366,7 +388,7 @@ __global__ void __launch_bounds__(G::GRID_THREADS, G::GRID_MINB) grid_pass_kerne
 #pragma unroll
             for (int g = 0; g < S::NG; g++) nw[g] = c.sum(nw[g]);
 #pragma unroll
-            for (int gi = 0; gi < NB; gi++) nw[S::big_group(gi)] = s_new[gi * TB + tile];
+            for (int gi = 0; gi < NB; gi++) nw[S::big_group(gi)] = s_new[gi * TB + pos_of_chain(tile)];
             rw_finish<G, S>(c, a.k.D, kk, 0, p, nw);
         }
     }
@@ -381,6 +403,19 @@ __global__ void __launch_bounds__(G::GRID_THREADS, G::GRID_MINB) grid_pass_kerne
     grid_propose_ahead<G>(a, tid);
     if (a.dbg) { __syncthreads(); if (tid == 0) { a.dbg[4] = clock64(); unsigned long long g_; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g_)); a.dbg[17 + 2 * ((a.it * a.npass + a.pass) & 31)] = (long long)g_; } }
     if (tid == 0) *a.ticket = 0u;
+}
+
+template <class Kern>
+inline cudaError_t launch_pass(Kern kern, int grid, int threads, size_t smem, cudaStream_t st, const GArgs& a) {
+    static const bool pdl = getenv("APTB200_NO_PDL") == nullptr;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)threads);
+    cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, a);
 }
 
 template <class G>

@@ -1979,7 +1979,7 @@ struct Lowerer {
             out << "      default: break;\n    }\n  }\n";
             out << "  static void launch_stage(int s, const apt::GArgs& a, int grid, size_t smem, cudaStream_t st) {\n    switch (s) {\n";
             for (size_t i = 0; i < units.size(); i++)
-                out << "      case " << i << ": apt::grid_pass_kernel<Model, S" << i << "><<<grid, GRID_THREADS, smem, st>>>(a); break;\n";
+                out << "      case " << i << ": apt::launch_pass(apt::grid_pass_kernel<Model, S" << i << ">, grid, GRID_THREADS, smem, st, a); break;\n";
             out << "    }\n  }\n";
             out << "  static void launch_prologue(const apt::GArgs& a, cudaStream_t st) { apt::grid_prologue_kernel<Model><<<1, GRID_THREADS, 0, st>>>(a); }\n";
             out << "  static void set_stage_smem(size_t smem) {\n";
