@@ -225,6 +225,12 @@ int apt_run(apt_engine* e, const apt_run_args* args);
 int64_t apt_info(apt_engine* e, int what);
 /* ladder >= 0: one ladder; ladder = -1: all local ladders, ladder-major.  *n_written receives the count. */
 int apt_get(apt_engine* e, int what, int ladder, double* out, int64_t capacity, int64_t* n_written);
+/* the same with the layout chosen by the caller: APT_COLUMN_MAJOR (one ladder, ladder >= 0) writes a matrix item the way R
+ * stores a matrix, i.e. straight into REAL() of the matrix the R side allocated -- rows x n_monitors for the traces, nTemps x
+ * nTemps for accCountSwap, nTemps x n_params for the rung states, ...; traces are transposed on the device.  Vector items
+ * (logProbs, Temps, ...) are the same in either layout. */
+enum { APT_ROW_MAJOR = 0, APT_COLUMN_MAJOR = 1 };
+int apt_get_layout(apt_engine* e, int what, int ladder, int layout, double* out, int64_t capacity, int64_t* n_written);
 int apt_get_timing(apt_engine* e, apt_timing* t);
 /* whole-model log probability of caller-provided parameter vectors: theta [n][n_params] ->
  * out_total [n] and (optional) out_groups [n][n_logprob_groups] */

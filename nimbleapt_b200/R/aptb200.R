@@ -66,13 +66,21 @@ buildAPT <- function(conf, Temps, monitorTmax = TRUE, ULT = 1E6, thinPrintTemps 
     self$monitorNames2 <- strsplit(.Call("aptR_model_names", m, 2L), "\n")[[1]]
     info <- function(what) .Call("aptR_info", h, as.integer(what))
     get  <- function(what, rows, cols, ladder = 0L) .Call("aptR_get", h, as.integer(what), as.integer(ladder), rows, cols)
+    ## samplesOut (extension): a numeric vector of nLadders * (niter %/% thin) * length(monitorNames) doubles that receives this
+    ## run's rows of mvSamples while the run is still sampling; ladder l is t(matrix(block l, length(monitorNames)))
     self$run <- function(niter, reset = TRUE, resetMV = FALSE, resetTempering = FALSE, simulateAll = FALSE, time = FALSE,
                          adaptTemps = TRUE, printTemps = FALSE, tuneTemper1 = 10, tuneTemper2 = 1, progressBar = TRUE,
-                         thin = -1L, thin2 = -1L) {
+                         thin = -1L, thin2 = -1L, samplesOut = NULL) {
         .Call("aptR_run", h, niter, c(reset, resetMV, resetTempering, simulateAll, time, adaptTemps, as.logical(printTemps)),
-              c(tuneTemper1, tuneTemper2), as.integer(c(thin, thin2)))
+              c(tuneTemper1, tuneTemper2), as.integer(c(thin, thin2)), samplesOut)
         invisible(NULL)
     }
+    ## extensions of the C ABI that have no counterpart in the reference's object: new initial values / data for the same
+    ## compiled model (the reference would assign into the compiled model, cModel$beta <- ...), and model$calculate() at
+    ## given states (rows of theta), evaluated on the device
+    self$setInits  <- function(theta, ladder = -1L) invisible(.Call("aptR_set_inits", h, as.numeric(theta), as.integer(ladder)))
+    self$setData   <- function(name, values) invisible(.Call("aptR_set_array", h, name, values))
+    self$calculate <- function(theta) { lp <- .Call("aptR_logprob", h, t(rbind(theta))); list(total = lp[1, ], groups = t(lp[-1, , drop = FALSE])) }
     self$calculateWAIC <- function(nburnin = 0, ladder = 0L) {                            # APT:593-635
         if (!enableWAIC) {
             print("Error: must set enableWAIC = TRUE in buildAPT to use the method calcualteWAIC. See help(buildAPT) and help(buildMCMC) for additional information.")

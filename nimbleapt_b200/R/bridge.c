@@ -115,8 +115,11 @@ SEXP aptR_build(SEXP p, SEXP temps, SEXP monitorTmax, SEXP ULT, SEXP nLadders, S
 static void probe_interrupt(void* flag) { R_CheckUserInterrupt(); *(int*)flag = 0; }
 static int should_abort(void* unused) { int interrupted = 1; R_ToplevelExec(probe_interrupt, &interrupted); return interrupted; }
 
+/* samplesOut: R_NilValue, or a numeric vector of n_ladders x (niter / thin) x n_monitors doubles that receives THIS run's
+ * rows of mvSamples while the run is still sampling (apt_run_args.samples_out): ladder-major, each ladder's block row-major
+ * (the R side reads ladder l as t(matrix(x[block l], n_monitors, rows))). */
 SEXP aptR_run(SEXP h, SEXP niter, SEXP flags /* logical(7): reset resetMV resetTempering simulateAll time adaptTemps printTemps */,
-              SEXP tune /* numeric(2) */, SEXP thins /* integer(2) */) {
+              SEXP tune /* numeric(2) */, SEXP thins /* integer(2) */, SEXP samplesOut) {
     apt_run_args a;
     apt_run_args_default(&a);
     a.niter = (int64_t)Rf_asReal(niter);
@@ -125,20 +128,58 @@ SEXP aptR_run(SEXP h, SEXP niter, SEXP flags /* logical(7): reset resetMV resetT
     a.tuneTemper1 = REAL(tune)[0]; a.tuneTemper2 = REAL(tune)[1];
     a.thin = INTEGER(thins)[0]; a.thin2 = INTEGER(thins)[1];
     a.should_abort = should_abort;
+    if (samplesOut != R_NilValue) { a.samples_out = REAL(samplesOut); a.samples_out_capacity = (int64_t)XLENGTH(samplesOut); }
     chk(apt_run(R_ExternalPtrAddr(h), &a));
     return R_NilValue;
 }
 
-/* what: APT_SAMPLES ... ; returns a numeric matrix rows x cols (R allocates, the library fills a row-major
- * scratch that is transposed here into R's column-major layout) */
+/* what: APT_SAMPLES ... ; returns a numeric matrix rows x cols.  R allocates it; the library writes it in R's own
+ * column-major layout (apt_get_layout, APT_COLUMN_MAJOR: transposed on the device), so REAL(out) is passed straight through. */
 SEXP aptR_get(SEXP h, SEXP what, SEXP ladder, SEXP rows, SEXP cols) {
     R_xlen_t r = (R_xlen_t)Rf_asReal(rows), c = (R_xlen_t)Rf_asReal(cols);
     SEXP out = PROTECT(Rf_allocMatrix(REALSXP, (int)r, (int)c));
-    double* tmp = (double*)R_alloc((size_t)(r * c > 0 ? r * c : 1), sizeof(double));
     int64_t n = 0;
-    int rc = apt_get(R_ExternalPtrAddr(h), Rf_asInteger(what), Rf_asInteger(ladder), tmp, (int64_t)(r * c), &n);
-    if (!rc) for (R_xlen_t i = 0; i < r; i++) for (R_xlen_t j = 0; j < c; j++) REAL(out)[i + j * r] = tmp[i * c + j];
+    int rc = apt_get_layout(R_ExternalPtrAddr(h), Rf_asInteger(what), Rf_asInteger(ladder), APT_COLUMN_MAJOR, REAL(out), (int64_t)(r * c), &n);
+    if (!rc && n != (int64_t)(r * c)) { UNPROTECT(1); Rf_error("aptR_get: the item has %lld elements, not %lld x %lld", (long long)n, (long long)r, (long long)c); }
     UNPROTECT(1);
+    chk(rc);
+    return out;
+}
+
+/* overwrite the model's current values (the inits of the next reset run): theta numeric(n_params); ladder -1 = all ladders */
+SEXP aptR_set_inits(SEXP h, SEXP theta, SEXP ladder) {
+    SEXP t = PROTECT(Rf_coerceVector(theta, REALSXP));
+    int rc = (int64_t)XLENGTH(t) != apt_info(R_ExternalPtrAddr(h), APT_INFO_N_PARAMS) ? -1 : apt_set_inits(R_ExternalPtrAddr(h), REAL(t), Rf_asInteger(ladder));
+    UNPROTECT(1);
+    if (rc == -1) Rf_error("aptR_set_inits: theta must have one value per parameter");
+    chk(rc);
+    return R_NilValue;
+}
+
+/* re-upload a constant / data array of the same shape (model$setData for a resident array) */
+SEXP aptR_set_array(SEXP h, SEXP name, SEXP x) {
+    SEXP xr = PROTECT(Rf_coerceVector(x, REALSXP));
+    int rc = apt_set_array(R_ExternalPtrAddr(h), CHAR(STRING_ELT(name, 0)), REAL(xr), (int64_t)XLENGTH(xr));
+    UNPROTECT(1);
+    chk(rc);
+    return R_NilValue;
+}
+
+/* model$calculate() at given states: thetaT is an n_params x n matrix (one state per COLUMN, i.e. t(theta) of the usual
+ * n x n_params layout, which makes R's column-major storage the [n][n_params] the library takes); returns an
+ * (n_groups + 1) x n matrix: row 1 the total logProb, the other rows the per-declaration sums */
+SEXP aptR_logprob(SEXP h, SEXP thetaT) {
+    SEXP dim = Rf_getAttrib(thetaT, R_DimSymbol);
+    const int64_t P = apt_info(R_ExternalPtrAddr(h), APT_INFO_N_PARAMS), ND = apt_info(R_ExternalPtrAddr(h), APT_INFO_N_LOGPROB_GROUPS);
+    if (dim == R_NilValue || LENGTH(dim) != 2 || INTEGER(dim)[0] != P) Rf_error("aptR_logprob: thetaT must be an n_params x n matrix");
+    const int n = INTEGER(dim)[1];
+    SEXP t = PROTECT(Rf_coerceVector(thetaT, REALSXP));
+    SEXP out = PROTECT(Rf_allocMatrix(REALSXP, (int)ND + 1, n));
+    double* tot = (double*)R_alloc((size_t)(n > 0 ? n : 1), sizeof(double));
+    double* grp = (double*)R_alloc((size_t)(n > 0 ? n * ND : 1), sizeof(double));
+    int rc = apt_logprob(R_ExternalPtrAddr(h), REAL(t), n, tot, grp);
+    if (!rc) for (int i = 0; i < n; i++) { REAL(out)[(size_t)i * (ND + 1)] = tot[i]; for (int d = 0; d < ND; d++) REAL(out)[(size_t)i * (ND + 1) + 1 + d] = grp[(size_t)i * ND + d]; }
+    UNPROTECT(2);
     chk(rc);
     return out;
 }

@@ -43,7 +43,7 @@ class Timing(C.Structure):
 EXPORTS = ["apt_last_error", "apt_version", "apt_abi_sizeof", "apt_sampler_control_default", "apt_build_opts_default",
            "apt_run_args_default", "apt_model_create", "apt_model_free", "apt_model_set_array",
            "apt_model_add_sampler", "apt_model_remove_samplers", "apt_model_set_monitors", "apt_model_set_thin",
-           "apt_model_names", "apt_model_lower", "apt_model_compile", "apt_build", "apt_free", "apt_run", "apt_info", "apt_get",
+           "apt_model_names", "apt_model_lower", "apt_model_compile", "apt_build", "apt_free", "apt_run", "apt_info", "apt_get", "apt_get_layout",
            "apt_get_timing", "apt_logprob", "apt_waic", "apt_set_inits", "apt_set_array", "apt_comm_unique_id", "apt_comm_init",
            "apt_comm_allgather_samples", "apt_comm_gather_samples", "apt_comm_allreduce_sum", "apt_comm_finalize"]
 
@@ -87,6 +87,7 @@ def lib():
     L.apt_info.restype = C.c_int64
     L.apt_info.argtypes = [vp, C.c_int]
     L.apt_get.argtypes = [vp, C.c_int, C.c_int, dp, C.c_int64, C.POINTER(C.c_int64)]
+    L.apt_get_layout.argtypes = [vp, C.c_int, C.c_int, C.c_int, dp, C.c_int64, C.POINTER(C.c_int64)]
     L.apt_get_timing.argtypes = [vp, C.POINTER(Timing)]
     L.apt_logprob.argtypes = [vp, dp, C.c_int, dp, dp]
     L.apt_waic.argtypes = [vp, C.c_int64, C.c_int, dp]

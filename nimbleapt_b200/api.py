@@ -139,6 +139,16 @@ class _Samples:
     def __init__(self, apt, what, names):
         self._apt, self._what, self.names = apt, what, names
 
+    def matrix_column_major(self, ladder=0):
+        """The same matrix of one ladder delivered in column-major order (what an R matrix is): transposed on the device,
+        copied as it is (apt_get_layout with APT_COLUMN_MAJOR).  Returned as a Fortran-ordered [rows, monitors] array."""
+        rows = self._apt.info(INFO_ROWS2 if self._what in (APT_SAMPLES2, APT_SAMPLES2_TMAX) else INFO_ROWS)
+        cols = len(self.names)
+        out = np.empty(max(rows * cols, 1), dtype=np.float64)
+        got = C.c_int64()
+        check(lib().apt_get_layout(self._apt._h, self._what, int(ladder), 1, _dp(out), out.size, C.byref(got)))
+        return out[:got.value].reshape((rows, cols), order="F")
+
     def matrix(self, ladder=0, out=None):
         """as.matrix(cAPT$mvSamples) of one ladder ([rows, monitors]) or of all local ladders (ladder = -1:
         [ladders, rows, monitors]).  `out`: optional caller-allocated flat float64 destination (the C ABI always

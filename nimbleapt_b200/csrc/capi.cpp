@@ -25,6 +25,7 @@ struct ModFns {
     void (*destroy)(void*);
     int (*run)(void*, const aptmod_run_args*, char*, int);
     int (*get)(void*, int, int, double*, int64_t, int64_t*, char*, int);
+    int (*get_cm)(void*, int, int, double*, int64_t, int64_t*, char*, int);
     long long (*info)(void*, int);
     int (*logprob)(void*, const double*, int, double*, char*, int);
     int (*set_model_theta)(void*, const double*, int, char*, int);
@@ -267,6 +268,7 @@ int apt_build(apt_model* m, const double* temps, int n_temps, const apt_build_op
         e->fn.destroy = (decltype(e->fn.destroy))sym("aptmod_destroy");
         e->fn.run = (decltype(e->fn.run))sym("aptmod_run");
         e->fn.get = (decltype(e->fn.get))sym("aptmod_get");
+        e->fn.get_cm = (decltype(e->fn.get_cm))sym("aptmod_get_cm");
         e->fn.info = (decltype(e->fn.info))sym("aptmod_info");
         e->fn.logprob = (decltype(e->fn.logprob))sym("aptmod_logprob");
         e->fn.set_model_theta = (decltype(e->fn.set_model_theta))sym("aptmod_set_model_theta");
@@ -377,6 +379,20 @@ int apt_get(apt_engine* e, int what, int ladder, double* out, int64_t capacity, 
     char err[2048] = {0};
     int64_t n = 0;
     if (e->fn.get(e->mod, what, ladder, out, capacity, &n, err, sizeof err)) throw Error(err);
+    if (n_written) *n_written = n;
+    API_END
+}
+
+int apt_get_layout(apt_engine* e, int what, int ladder, int layout, double* out, int64_t capacity, int64_t* n_written) {
+    API_BEGIN
+    if (!e || !out) throw Error("null argument");
+    if (layout != APT_ROW_MAJOR && layout != APT_COLUMN_MAJOR) throw Error("layout must be APT_ROW_MAJOR or APT_COLUMN_MAJOR");
+    char err[2048] = {0};
+    int64_t n = 0;
+    if (layout == APT_COLUMN_MAJOR) {
+        if (ladder < 0) throw Error("column-major output is per ladder (ladder >= 0)");
+        if (e->fn.get_cm(e->mod, what, ladder, out, capacity, &n, err, sizeof err)) throw Error(err);
+    } else if (e->fn.get(e->mod, what, ladder, out, capacity, &n, err, sizeof err)) throw Error(err);
     if (n_written) *n_written = n;
     API_END
 }

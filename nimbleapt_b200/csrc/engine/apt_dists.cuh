@@ -326,6 +326,11 @@ __device__ __forceinline__ int dyn_index(double v, int n) {
 //     1.1e-16 e^eta, and saturates to -Inf beyond eta = 36.74 (p rounds to 1).
 // To give the SAME accept/reject decisions as the reference even for hot chains that wander there, that one branch
 // is reproduced literally for eta > 8 (below 8 both agree to < 3.3e-13); everything else takes the fused form.
+// threshold of the literal branch and its high word (a power of two or 1.5 times one, so that the high-word test is exact)
+#ifndef APT_LIT_ETA
+#define APT_LIT_ETA 8.0
+#define APT_LIT_HI 0x40200000
+#endif
 __device__ __noinline__ double bern_logit_invalid(double y, double eta) {
     if (isnan(y) || isnan(eta)) return y + eta;
     return APT_NEG_INF;  // dbinom: non-integer or out-of-range x
@@ -336,6 +341,17 @@ __device__ __noinline__ double bern_logit_generic(double y, double eta) {
     const double p = 1.0 / (1.0 + exp(-eta));
     return dbinom_raw_log(y, 1.0, p, 1.0 - p);
 }
+// |eta| > 709 (exp about to overflow) with a valid response.  Hot chains live here: a rung at T ~ 1e5 under a tempered
+// N(0, 10^2) prior has |beta| in the thousands, and every row of such a chain used to take the out-of-line library chain.
+// Beyond 710 that chain has only two outcomes: exp(-eta) is 0 or Inf, p is exactly 1 or 0, and dbinom_raw(y, 1, p, q) returns
+// log(1) = 0 for the matching response and log(0) = -Inf for the other one.  (Between 709 and 710 p can still be a denormal
+// whose logarithm is finite, and Inf / NaN propagate: those stay with the verbatim chain.)
+__device__ __forceinline__ double bern_logit_far(double y, double eta) {
+    const double a = fabs(eta);
+    if (a > 710.0 && a < CUDART_INF) return ((y == 0.0) == (eta > 0.0)) ? APT_NEG_INF : 0.0;
+    return bern_logit_generic(y, eta);
+}
+
 __device__ __noinline__ double bern_logit_literal_q(double eta) {  // y = 0, eta > 8; out of line: one copy instead of one per term
     const double e = apt_exp_neg(eta);
     const double p = 1.0 / (1.0 + e);
@@ -344,10 +360,10 @@ __device__ __noinline__ double bern_logit_literal_q(double eta) {  // y = 0, eta
 }
 __device__ __forceinline__ double bern_logit_log(double y, double eta) {
     if (!(y == 0.0 || y == 1.0)) return bern_logit_invalid(y, eta);
-    if (!(fabs(eta) <= 709.0)) return bern_logit_generic(y, eta);
+    if (!(fabs(eta) <= 709.0)) return bern_logit_far(y, eta);
     const double t = (y == 1.0) ? -eta : eta;
     double r = -(fmax(t, 0.0) + apt_softplus_neg(fmin(fabs(t), 64.0)));
-    if (y == 0.0 && eta > 8.0) r = bern_logit_literal_q(eta);
+    if (y == 0.0 && eta > APT_LIT_ETA) r = bern_logit_literal_q(eta);
     return r;
 }
 
@@ -356,7 +372,7 @@ __device__ __forceinline__ double bern_logit_log(double y, double eta) {
 __device__ __noinline__ double bern_logit_fix(double y, double eta, double v) {
     if (!(y == 0.0 || y == 1.0)) return bern_logit_invalid(y, eta);
     if (!(fabs(eta) <= 709.0)) return bern_logit_generic(y, eta);
-    if (y == 0.0 && eta > 8.0) return bern_logit_literal_q(eta);
+    if (y == 0.0 && eta > APT_LIT_ETA) return bern_logit_literal_q(eta);
     return v;
 }
 
@@ -390,10 +406,11 @@ __device__ __forceinline__ void bern_logit_acc(double y, const double (&eta)[N],
         // -(max(t, 0) + softplus), t = sgn * eta:  t + |t| is exactly 2 max(t, 0), so one rounding as before
 #pragma unroll
         for (int j = 0; j < M; j++) v[j] = fma(-0.5, fma(sgn, eta[h + j], a[j]), -v[j]);
-        if ((y0 && smax >= 0x40200000) || amax >= 0x40862800) {  // conservative on the high words; exact tests inside
+        if ((y0 && smax >= APT_LIT_HI) || amax >= 0x40862800) {  // conservative on the high words; exact tests inside
 #pragma unroll
             for (int j = 0; j < M; j++)
-                if ((y0 && eta[h + j] > 8.0) || !(fabs(eta[h + j]) <= 709.0)) v[j] = bern_logit_fix(y, eta[h + j], v[j]);
+                if (!(fabs(eta[h + j]) <= 709.0)) v[j] = bern_logit_far(y, eta[h + j]);
+                else if (y0 && eta[h + j] > APT_LIT_ETA) v[j] = bern_logit_literal_q(eta[h + j]);
         }
 #pragma unroll
         for (int j = 0; j < M; j++) acc[h + j] += v[j];
@@ -415,14 +432,9 @@ __device__ __forceinline__ void bern_logit_tile(const double (&y)[NR], const dou
     constexpr int CPB = (NR >= APT_TILE_BATCH) ? 1 : ((APT_TILE_BATCH / NR) < NC ? (APT_TILE_BATCH / NR) : NC);  // chains per batch
     constexpr int M = CPB * NR;
     static_assert(NC % CPB == 0, "chains per thread must be a multiple of the batch");
-    bool valid = true, y0[NR];
-    double sgn[NR];
+    bool valid = true;
 #pragma unroll
-    for (int r = 0; r < NR; r++) {
-        y0[r] = (y[r] == 0.0);
-        valid = valid && (y0[r] || y[r] == 1.0);
-        sgn[r] = 1.0 - 2.0 * y[r];
-    }
+    for (int r = 0; r < NR; r++) valid = valid && (y[r] == 0.0 || y[r] == 1.0);
 #pragma unroll
     for (int c0 = 0; c0 < NC; c0 += CPB) {
         double a[M], v[M];
@@ -435,7 +447,7 @@ __device__ __forceinline__ void bern_logit_tile(const double (&y)[NR], const dou
                 const double e = eta[r][c0 + cc];
                 const int hi = __double2hiint(e);
                 amax = max(amax, hi & 0x7fffffff);
-                smax[cc] = max(smax[cc], y0[r] ? hi : (int)0x80000000);
+                smax[cc] = max(smax[cc], (y[r] == 0.0) ? hi : (int)0x80000000);
                 a[cc * NR + r] = fabs(e);
             }
         }
@@ -444,10 +456,10 @@ __device__ __forceinline__ void bern_logit_tile(const double (&y)[NR], const dou
 #pragma unroll
         for (int cc = 0; cc < CPB; cc++)
 #pragma unroll
-            for (int r = 0; r < NR; r++) v[cc * NR + r] = fma(-0.5, fma(sgn[r], eta[r][c0 + cc], a[cc * NR + r]), -v[cc * NR + r]);
+            for (int r = 0; r < NR; r++) v[cc * NR + r] = fma(-0.5, fma(1.0 - 2.0 * y[r], eta[r][c0 + cc], a[cc * NR + r]), -v[cc * NR + r]);
 #pragma unroll
         for (int cc = 0; cc < CPB; cc++)
-            if (smax[cc] >= 0x40200000) {
+            if (smax[cc] >= APT_LIT_HI) {
                 // y = 0 and eta > 8: the reference's own chain p = 1/(1+exp(-eta)), q = 1-p, log(q), whose rounding the
                 // decisions of hot chains depend on (see above) -- the rows of this chain in lock step, reusing 1+exp(-eta)
                 double lq[NR];
@@ -457,7 +469,7 @@ __device__ __forceinline__ void bern_logit_tile(const double (&y)[NR], const dou
                 for (int r = 0; r < NR; r++) lq[r] = apt_log_q(lq[r]);  // q == 0 -> -Inf; q is 0 or normal (a multiple of 2^-53)
 #pragma unroll
                 for (int r = 0; r < NR; r++)
-                    if (y0[r] && eta[r][c0 + cc] > 8.0) v[cc * NR + r] = lq[r];
+                    if (y[r] == 0.0 && eta[r][c0 + cc] > APT_LIT_ETA) v[cc * NR + r] = lq[r];
             }
         if (!valid || amax >= 0x40862800) {  // invalid response, |eta| >= 709, Inf, NaN: exact tests inside
 #pragma unroll
@@ -465,7 +477,8 @@ __device__ __forceinline__ void bern_logit_tile(const double (&y)[NR], const dou
 #pragma unroll
                 for (int r = 0; r < NR; r++) {
                     const double e = eta[r][c0 + cc];
-                    if (!valid || !(fabs(e) <= 709.0)) v[cc * NR + r] = bern_logit_fix(y[r], e, v[cc * NR + r]);
+                    if (!valid) v[cc * NR + r] = bern_logit_fix(y[r], e, v[cc * NR + r]);
+                    else if (!(fabs(e) <= 709.0)) v[cc * NR + r] = bern_logit_far(y[r], e);
                 }
         }
 #pragma unroll

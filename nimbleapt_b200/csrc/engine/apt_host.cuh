@@ -88,6 +88,25 @@ __global__ void __launch_bounds__(256, 2) fp64_peak_kernel(double* out, int iter
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// [rows][cols] -> [cols][rows]: the column-major getters (R matrices) transpose on the device, so that the copy lands in the
+// caller's matrix as it is
+__global__ void transpose_kernel(const double* __restrict__ src, long rows, int cols, double* __restrict__ dst) {
+    __shared__ double t[32][33];
+    const long r0 = (long)blockIdx.x * 32;
+    const int c0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const long r = r0 + i;
+        const int c = c0 + threadIdx.x;
+        if (r < rows && c < cols) t[i][threadIdx.x] = src[r * cols + c];
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int c = c0 + i;
+        const long r = r0 + threadIdx.x;
+        if (r < rows && c < cols) dst[(size_t)c * rows + r] = t[threadIdx.x][i];
+    }
+}
+
 template <class G>
 __global__ void derived_kernel(Data D, int k, long n, double* out) {
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) G::der_fill(D, k, i, out);
@@ -672,6 +691,51 @@ struct Engine {
         APT_CUDA(cudaStreamSynchronize(stream));
     }
 
+    // One ladder's matrix in COLUMN-major order (what R's REAL() of a matrix is): traces are transposed on the device and
+    // copied straight into the caller's buffer; the small per-rung matrices are transposed on the host.
+    DevBuf<double> transposed;
+    int64_t get_cm(int what, int ladder, double* out, int64_t capn) {
+        APT_CUDA(cudaSetDevice(device));
+        if (ladder < 0 || ladder >= L) throw ApiError{"column-major output is per ladder: ladder index out of range"};
+        const DevBuf<double>* b = nullptr; long long capr = 0, nrows = 0; int cols = 0;
+        switch (what) {
+            case APTMOD_SAMPLES: b = &samples; capr = cap; nrows = rows; cols = G::NMON; break;
+            case APTMOD_SAMPLES_TMAX: b = &samplesT; capr = cap; nrows = rows; cols = G::NMON; break;
+            case APTMOD_SAMPLES2: b = &samples2; capr = cap2; nrows = rows2; cols = G::NMON2; break;
+            case APTMOD_SAMPLES2_TMAX: b = &samples2T; capr = cap2; nrows = rows2; cols = G::NMON2; break;
+            case APTMOD_TEMPTRAJ: b = &temptraj; capr = ttcap; nrows = ttrows; cols = K; break;
+            default: break;
+        }
+        if (b) {
+            const int64_t n = (int64_t)nrows * cols;
+            if (n > capn) throw ApiError{"output buffer too small"};
+            if (n == 0) return 0;
+            if (!b->p) throw ApiError{"this trace is not kept (monitorTmax = FALSE)"};
+            if (transposed.n < (size_t)n) transposed.alloc((size_t)n);
+            const dim3 grid((unsigned)((nrows + 31) / 32), (unsigned)((cols + 31) / 32));
+            transpose_kernel<<<grid, dim3(32, 8), 0, stream>>>(b->p + (size_t)ladder * capr * cols, (long)nrows, cols, transposed.p);
+            APT_CUDA(cudaGetLastError());
+            APT_CUDA(cudaMemcpyAsync(out, transposed.p, (size_t)n * 8, cudaMemcpyDeviceToHost, stream));
+            APT_CUDA(cudaStreamSynchronize(stream));
+            launches_total++;
+            return n;
+        }
+        int r = 1, c = 1;
+        switch (what) {
+            case APTMOD_ACCSWAP: r = K; c = K; break;
+            case APTMOD_THETA: r = K; c = P; break;
+            case APTMOD_SCALE: r = K; c = G::NU; break;
+            case APTMOD_PROPCOV: r = K; c = G::BLKSZ; break;
+            default: return get(what, ladder, out, capn);  // vectors: the same in either order
+        }
+        std::vector<double> tmp((size_t)std::max(r * c, 1));
+        const int64_t n = get(what, ladder, tmp.data(), (int64_t)tmp.size());
+        if (n > capn) throw ApiError{"output buffer too small"};
+        for (int i = 0; i < r; i++)
+            for (int j = 0; j < c; j++) out[(size_t)j * r + i] = tmp[(size_t)i * c + j];
+        return n;
+    }
+
     // copies into caller-allocated host memory; returns the number of doubles written
     int64_t get(int what, int ladder, double* out, int64_t capn) {
         APT_CUDA(cudaSetDevice(device));
@@ -804,6 +868,9 @@ inline void set_err(char* err, int errlen, const std::string& m) {
     }                                                                                                               \
     APT_EXPORT int aptmod_get(void* h, int what, int ladder, double* out, int64_t cap, int64_t* n, char* err, int errlen) {    \
         APT_GUARD(*n = static_cast<apt::Engine<G>*>(h)->get(what, ladder, out, cap))                                \
+    }                                                                                                               \
+    APT_EXPORT int aptmod_get_cm(void* h, int what, int ladder, double* out, int64_t cap, int64_t* n, char* err, int errlen) { \
+        APT_GUARD(*n = static_cast<apt::Engine<G>*>(h)->get_cm(what, ladder, out, cap))                             \
     }                                                                                                               \
     APT_EXPORT long long aptmod_info(void* h, int what) { return static_cast<apt::Engine<G>*>(h)->info(what); }                \
     APT_EXPORT int aptmod_logprob(void* h, const double* th, int n, double* out, char* err, int errlen) {                      \

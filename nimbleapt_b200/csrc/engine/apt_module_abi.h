@@ -6,7 +6,7 @@
 #define APT_MODULE_ABI_H
 #include <stdint.h>
 
-#define APTMOD_ABI_VERSION 6
+#define APTMOD_ABI_VERSION 7
 
 #ifdef __cplusplus
 extern "C" {

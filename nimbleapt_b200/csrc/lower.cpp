@@ -2008,7 +2008,7 @@ struct Lowerer {
             if (units[ui].count > 1) {
                 out << "    if (active) for (int it_ = c.tile_id; it_ < K * " << units[ui].count << "; it_ += c.ntiles) apt::rw_update<Model, S" << ui
                     << ">(c, D, it_ / " << units[ui].count << ", it_ % " << units[ui].count << ");\n";
-                out << "    c.team_sync();\n    if (active) apt::family_commit<Model, S" << ui << ">(c);\n";
+                out << "    c.team_sync();\n    if (active) apt::family_commit<Model, S" << ui << ">(c, D);\n";
                 ui++;
             } else if (unit_is_wide(units[ui], cluster, tiles, W)) {
                 // cluster mode, a sampler whose dependants are a large declaration: the whole cluster evaluates ONE

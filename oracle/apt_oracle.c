@@ -1017,7 +1017,10 @@ int orc_ladder_run(orc_ladder* L, long niter, int reset, int resetMV, int resetT
             double gammaTSA = 1 / pow((double)L->totalIters / tuneTemper1 + 3, tuneTemper2);
             for (int i = 0; i < K; i++) L->TempsCurrent[i] = L->Temps[i];
             for (int ii = 0; ii < K - 1; ii++) {
-                double accProb = fmin(1.0, exp((L->invTemps[ii + 1] - L->invTemps[ii]) * (L->logProbTemps[ii] - L->logProbTemps[ii + 1])));
+                /* min(1, x) as R evaluates it and as nimble compiles it (pairmin: x1 < x2 ? x1 : x2) [NIMBLE-UNVERIFIED]: a
+                 * NaN -- two neighbouring rungs both at logProb -Inf -- propagates into the ladder; C's fmin() would hide it */
+                const double e_ = exp((L->invTemps[ii + 1] - L->invTemps[ii]) * (L->logProbTemps[ii] - L->logProbTemps[ii + 1]));
+                double accProb = (1.0 < e_) ? 1.0 : e_;
                 L->Temps[ii + 1] = L->Temps[ii] + (L->TempsCurrent[ii + 1] - L->TempsCurrent[ii]) * exp(gammaTSA * (accProb - 0.234));
                 if (L->Temps[ii + 1] > L->ULT) L->Temps[ii + 1] = L->ULT + (ii + 1);
             }

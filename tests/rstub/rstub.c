@@ -120,6 +120,7 @@ SEXP stub_call(SEXP (*fn)(), int nargs, SEXP* a) {
             case 3: r = fn(a[0], a[1], a[2]); break;
             case 4: r = fn(a[0], a[1], a[2], a[3]); break;
             case 5: r = fn(a[0], a[1], a[2], a[3], a[4]); break;
+            case 6: r = fn(a[0], a[1], a[2], a[3], a[4], a[5]); break;
             case 8: r = fn(a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7]); break;
             default: snprintf(errmsg, sizeof errmsg, "stub_call: unsupported arity %d", nargs);
         }

@@ -344,3 +344,64 @@ def test_grid_engine_mid_size_against_oracle():
     for k in (0, 7, 15):
         ref, _ = orc.logprob(th[k])
         assert abs(tot[k] - ref) <= 1e-12 * abs(ref)
+
+
+@pytest.mark.parametrize("kind", ["scalar", "family"])
+def test_start_outside_the_support_recovers_like_per_node_logprobs(kind):
+    """An initial value outside a prior's support makes ONE node's logProb -Inf.  nimble stores logProbs per node, so
+    the first accepted move into the support (logMHR = +Inf) leaves finite sums behind (APT:711,720-722); the engine
+    stores one sum per declaration and must not turn -Inf + Inf into a NaN that poisons logProbTemps, the swap phase and
+    the ladder adaptation (APT:460-462, 494-499).  Scalar samplers on single elements of a prior declaration (PARTIAL
+    groups) and a family of 12 of them; compared with the oracle decision by decision."""
+    rng = np.random.default_rng(models.DATA_SEED + 77)
+    if kind == "scalar":
+        n = 15
+        y = np.stack([rng.standard_normal(n) + 1.0, rng.standard_normal(n)], axis=1)
+        code = """{
+        for (i in 1:n) {
+            y[i,1] ~ dnorm(theta[1], sd=1)
+            y[i,2] ~ dnorm(theta[2], sd=1)
+        }
+        for (j in 1:2) {
+            theta[j] ~ dunif(-4, 4)
+        }
+        }"""
+        spec = dict(code=code, constants=dict(n=n), data=dict(y=y), inits=dict(theta=np.array([4.5, -4.6])),  # both outside
+                    samplers=[dict(target="theta[1]", type="sampler_RW_tempered", control=dict(temperPriors=True, scale=2.0)),
+                              dict(target="theta[2]", type="sampler_RW_tempered", control=dict(temperPriors=True, scale=2.0))],
+                    monitors=["theta"], Temps=np.exp(np.linspace(0.0, np.log(30.0), 6)), ULT=1e6)
+    else:
+        G, per = 12, 4
+        g = np.repeat(np.arange(1, G + 1), per).astype(float)
+        y = rng.standard_normal(G * per) * 0.7
+        code = """{
+        for (i in 1:N) {
+            y[i] ~ dnorm(u[g[i]], sd=1)
+        }
+        for (k in 1:G) {
+            u[k] ~ dunif(-3, 3)
+        }
+        }"""
+        u0 = np.zeros(G); u0[[0, 5, 11]] = [3.4, -3.5, 4.0]  # three members start outside
+        spec = dict(code=code, constants=dict(N=G * per, G=G, g=g), data=dict(y=y), inits=dict(u=u0),
+                    samplers=[dict(target="u[%d]" % (k + 1), type="sampler_RW_tempered", control=dict(temperPriors=True, scale=1.5)) for k in range(G)],
+                    monitors=["u"], Temps=np.exp(np.linspace(0.0, np.log(20.0), 5)), ULT=1e6)
+    eng, orc = _both(spec, L=2)
+    tot0, _ = eng.calculate(np.concatenate([np.ravel(spec["inits"][k]) for k in spec["inits"]]))
+    assert tot0[0] == -np.inf
+    # While two neighbouring rungs both sit at logProb -Inf the reference's own ladder adaptation produces NaN
+    # temperatures (APT:494-496: exp((-Inf) - (-Inf))), so the ladder is held fixed until every rung has recovered
+    _run_both(eng, orc, 150, 9, adaptTemps=False)
+    for l in range(2):
+        assert eng.logProbsLadder(l)[0] == -np.inf and np.isfinite(eng.logProbsLadder(l)[-1])
+        assert np.all(np.isfinite(eng._get(nb.api.APT_LOGPROBTEMPS, l, eng.nTemps)))
+    _run_both(eng, orc, 110, 10, reset=False)
+    for l in range(2):
+        lp = eng.logProbsLadder(l)
+        assert lp.shape == (260,) and np.all(np.isfinite(lp[150:])) and np.all(np.isfinite(eng.TempsLadder(l)))
+        np.testing.assert_allclose(lp, orc.logProbs(l), rtol=1e-9)
+        np.testing.assert_allclose(eng.mvSamples.matrix(l), orc.samples(l), rtol=1e-8, atol=1e-10)
+        np.testing.assert_allclose(eng.TempsLadder(l), orc.Temps(l), rtol=1e-9)
+        st = eng.rungStates(l)
+        tot, _ = eng.calculate(st)
+        np.testing.assert_allclose(eng._get(nb.api.APT_LOGPROBTEMPS, l, eng.nTemps), tot, rtol=1e-10)

@@ -3,8 +3,8 @@
 This image has no R, so the bridge is built against tests/rstub/ — a stand-in for the few entry points of
 R's C API it uses (SEXP vectors with names/dim attributes, external pointers with finalizers, Rf_error unwinding by
 longjmp, R_ToplevelExec / R_CheckUserInterrupt) — and driven from Python the way aptb200.R drives it through .Call.
-What this checks is the marshalling: argument conversion, control-list keys, the row-major -> column-major transpose,
-caller-allocated outputs, that a non-zero status becomes an R error only AFTER the library call returned with the
+What this checks is the marshalling: argument conversion, control-list keys, matrices arriving in R's column-major layout
+(written by the library itself, apt_get_layout), caller-allocated outputs, samplesOut / setInits / setData / calculate, that a non-zero status becomes an R error only AFTER the library call returned with the
 protection stack balanced, and that finalizers release the handles.  It does not check aptb200.R itself."""
 import ctypes as C
 import os
@@ -148,7 +148,9 @@ def test_bridge_builds_runs_and_returns_column_major_matrices():
     m = _configure(r, spec)
     h = r.call("aptR_build", m, r.num(spec["Temps"]), r.lgl(True), r.num(spec["ULT"]), r.int(2), r.int(11), r.int(0), r.lgl(False))
     flags = [True, False, False, False, False, True, False]  # reset resetMV resetTempering simulateAll time adaptTemps printTemps
-    r.call("aptR_run", h, r.num(300), r.lgl(flags), r.num([10, 1]), r.int([3, -1]))
+    nil = C.cast(r.L.stub_nil(), SEXP)
+    so = r.num(np.full(2 * 100 * 2, np.nan))  # numeric(nLadders * rows * monitors): this run's rows, while it samples
+    r.call("aptR_run", h, r.num(300), r.lgl(flags), r.num([10, 1]), r.int([3, -1]), so)
     ref = build_engine(spec, nLadders=2)
     ref.run(300, thin=3)
     rows = int(r.matrix(r.call("aptR_info", h, r.int(nb.api.INFO_ROWS)))[0])
@@ -159,14 +161,40 @@ def test_bridge_builds_runs_and_returns_column_major_matrices():
         np.testing.assert_array_equal(got, ref.mvSamples.matrix(ladder))  # same seed, same ladder ids: bit-identical
         tt = r.matrix(r.call("aptR_get", h, r.int(nb.api.APT_TEMPTRAJ), r.int(ladder), r.num(rows), r.num(5)))
         np.testing.assert_array_equal(tt, ref.tempTrajLadder(ladder))
+        acc = r.matrix(r.call("aptR_get", h, r.int(nb.api.APT_ACCSWAP), r.int(ladder), r.num(5), r.num(5)))
+        np.testing.assert_array_equal(acc, ref.accCountSwapLadder(ladder))
+        np.testing.assert_array_equal(r.matrix(so).reshape(2, 100, 2)[ladder], ref.mvSamples.matrix(ladder))
+        np.testing.assert_array_equal(ref.mvSamples.matrix_column_major(ladder), ref.mvSamples.matrix(ladder))
+    with pytest.raises(RuntimeError, match="output buffer too small"):  # a matrix of the wrong shape is an R error, ...
+        r.call("aptR_get", h, r.int(nb.api.APT_SAMPLES), r.int(0), r.num(7), r.num(2))
+    with pytest.raises(RuntimeError, match="not 300 x 2"):                 # ... not a silent short copy
+        r.call("aptR_get", h, r.int(nb.api.APT_SAMPLES), r.int(0), r.num(300), r.num(2))
+    # model$calculate() at two states, new inits and new data for the compiled model
+    th = np.array([[3.0, 3.0], [-2.5, 0.4]])
+    lp = r.matrix(r.call("aptR_logprob", h, r.num(th.T.copy())))
+    tot, grp = ref.calculate(th)
+    np.testing.assert_array_equal(lp[0], tot)
+    np.testing.assert_array_equal(lp[1:].T, grp)
+    y2 = spec["data"]["y"] + 0.25
+    r.call("aptR_set_array", h, r.str("y"), r.num(y2))
+    r.call("aptR_set_inits", h, r.num([1.0, -1.0]), r.int(-1))
+    ref.setData("y", y2)
+    ref.setInits(np.array([1.0, -1.0]))
+    with pytest.raises(RuntimeError, match="one value per parameter"):
+        r.call("aptR_set_inits", h, r.num([1.0, -1.0, 0.0]), r.int(-1))
+    r.call("aptR_run", h, r.num(90), r.lgl(flags), r.num([10, 1]), r.int([3, -1]), nil)
+    ref.run(90, thin=3)
+    for ladder in (0, 1):
+        got = r.matrix(r.call("aptR_get", h, r.int(nb.api.APT_SAMPLES), r.int(ladder), r.num(30), r.num(2)))
+        np.testing.assert_array_equal(got, ref.mvSamples.matrix(ladder))
     # continue without reset (APT:378-380), interrupted by the user at the first poll: an R error, handle still usable
     flags[0] = False
     r.L.stub_set_interrupt(1)
     with pytest.raises(RuntimeError, match="interrupt"):
-        r.call("aptR_run", h, r.num(200000), r.lgl(flags), r.num([10, 1]), r.int([3, -1]))
-    r.call("aptR_run", h, r.num(30), r.lgl(flags), r.num([10, 1]), r.int([3, -1]))
+        r.call("aptR_run", h, r.num(200000), r.lgl(flags), r.num([10, 1]), r.int([3, -1]), nil)
+    r.call("aptR_run", h, r.num(30), r.lgl(flags), r.num([10, 1]), r.int([3, -1]), nil)
     with pytest.raises(RuntimeError, match="niter < 0"):  # APT:350
-        r.call("aptR_run", h, r.num(-5), r.lgl(flags), r.num([10, 1]), r.int([3, -1]))
+        r.call("aptR_run", h, r.num(-5), r.lgl(flags), r.num([10, 1]), r.int([3, -1]), nil)
     with pytest.raises(RuntimeError, match="enableWAIC"):
         r.call("aptR_waic", h, r.num(0), r.int(0))
     r.L.stub_reset()  # finalizers: apt_free, apt_model_free
