@@ -41,6 +41,12 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// FP64 tensor-core step D (8 x 8) += A (8 x 4, row) * B (4 x 8, col): lane holds A[lane / 4][lane % 4], B[lane % 4][lane / 4] and
+// D[lane / 4][2 (lane % 4) + {0, 1}].  Same pipe as DFMA on sm_100a, one issue slot per 256 FMAs.
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
 // Programmatic dependent launch: a pass kernel is launched with programmatic stream serialisation, so that its CTAs become
 // resident as the previous pass's CTAs leave (all but the one that runs the control step leave right after streaming), prime
 // their data rings -- the design matrix does not depend on the previous pass -- and then block in pdl_wait() until the previous

@@ -1229,8 +1229,8 @@ struct Lowerer {
     // a parameter slice with a data row are interchanged so that each data element is loaded once and reused by
     // all chains (the loop over the TB chains is innermost and fully unrolled into registers).
     // tile mode of the grid engine (see emit_big_eval_fn): lanes of a warp = (row group, chain group)
-    bool tile_want = false, unit_tile = false;
-    int tile_cs = 1, tile_rt = 2, tile_rows = 64;
+    bool tile_want = false, unit_tile = false, tile_mma = false;
+    int tile_cs = 1, tile_rt = 2, tile_rows = 64, tile_tb = 1;
     void emit_big_eval(Unit& u) {
         std::vector<size_t> bigs;
         for (size_t g = 0; g < u.groups.size(); g++)
@@ -1296,6 +1296,70 @@ struct Lowerer {
                 std::string nm = "ip" + std::to_string(nh++) + "_";
                 const int BW = 5, RD = 5, RS = 6;
                 const bool ring = allow_ring && vec && !any_ring && bigs.size() == 1 && lp_ % BW == 0 && lp_ / BW >= RD && ring_ok;
+                if (allow_ring && vec && !any_ring && bigs.size() == 1 && lp_ >= 12 && ring_ok && tile_want && tile_mma && ips.size() == 1) {
+                    // MMA tile mode (8 or 16 rungs per pass).  A warp owns 32 consecutive rows; the product of its 32 x lp_ block of
+                    // the design matrix with the lp_ x TBS parameter block runs on the FP64 tensor-core path (mma.sync.m8n8k4.f64):
+                    // per block of 4 columns, 4 row blocks x TBS/8 chain blocks, A fragments (one data value per lane and row
+                    // block) from the warp's cp.async ring, B fragments (one parameter per lane and chain block) from the staged
+                    // parameters.  DMMA shares the FP64 pipe with DFMA on sm_100a (tools/ub_dmma.cu), so the arithmetic floor is
+                    // unchanged; the product costs 104 issue slots + 78 LDS.64 per tile instead of 800 DFMA + 200 LDS.128
+                    // (tools/ub_dmma_stream.cu: streaming 127 -> 107 us per pass).  The accumulator fragment gives lane (rq, kq)
+                    // rows rq + 8 r and chain positions kq * TBT + {0 .. TBT-1}: the same 4 x TBT thread tile as before, so the
+                    // Bernoulli-logit terms and the reductions are unchanged.  Columns beyond lp_ (last block) enter as zeros.
+                    any_ring = true;
+                    unit_tile = true;
+                    const int KB = 4, XS = 36;  // columns per block; padded column stride (doubles): LDS.64 of a fragment hits 16 distinct bank pairs
+                    const int NBR = (lp_ + KB - 1) / KB, NT = tile_tb / 8;
+                    int TRD = 3;
+                    if (const char* e = getenv("APTB200_TILE_DEPTH")) TRD = std::max(1, std::min(NBR, atoi(e)));
+                    const int TRS = TRD + 1, BLK = KB * XS;
+                    auto xaddr = [&](const std::string& row, const std::string& col) {
+                        Env e2 = env;
+                        e2[d.loops[0].var] = "(" + std::to_string(d.loops[0].lo) + " + " + row + ")";
+                        int tmp;
+                        return gen_slice_elem(ds, col, e2, tmp);
+                    };
+                    auto fill = [&](std::ostream& o, const std::string& ind, const std::string& slot, const std::string& row0, const std::string& blk) {
+                        o << ind << "_Pragma(\"unroll\") for (int j_ = 0; j_ < 2; ++j_) { const int col_ = (lane_ >> 4) + 2 * j_; if (" << blk << " * " << KB << " + col_ < " << lp_
+                          << ") apt::cp_async16(&xw_[" << slot << " * " << BLK << " + col_ * " << XS << " + 2 * (lane_ & 15)], &" << xaddr(row0 + " + 2 * (lane_ & 15)", "(" + blk + " * " + std::to_string(KB) + " + col_)") << "); }\n";
+                    };
+                    out << "        static_assert(R == 4 && TB == " << 2 * NT << ", \"MMA tile: 4 rows x TBS/4 chains per thread\");\n";
+                    out << "        const int lane_ = tid_ & 31, kq_ = lane_ & 3, rq_ = lane_ >> 2;\n";
+                    out << "        double* xw_ = xbuf + (tid_ >> 5) * " << TRS * BLK << ";\n";
+                    out << "        const int bpos_ = (rq_ >> 1) * TB + (rq_ & 1);  // chain position of column rq_ of chain block 0 (block t: + 2 t)\n";
+                    out << "        double " << nm << "[R][TB];\n";
+                    out << "        _Pragma(\"unroll\") for (int r_ = 0; r_ < R; ++r_) { _Pragma(\"unroll\") for (int c_ = 0; c_ < TB; ++c_) " << nm << "[r_][c_] = 0.0; }\n";
+                    out << "        _Pragma(\"unroll\") for (int b_ = 0; b_ < " << NBR << "; ++b_) {\n";
+                    out << "          apt::cp_async_wait<" << TRD - 1 << ">();\n          __syncwarp();\n";
+                    out << "          { const int nb_ = b_ + " << TRD << "; int slot_ = ring_pos + " << TRD << "; if (slot_ >= " << TRS << ") slot_ -= " << TRS << ";\n";
+                    out << "            if (nb_ < " << NBR << ") {\n"; fill(out, "              ", "slot_", "i0", "nb_"); out << "            }\n";
+                    out << "            else if (i_next >= 0) {\n"; fill(out, "              ", "slot_", "i_next", "(nb_ - " + std::to_string(NBR) + ")"); out << "            }\n";
+                    out << "            apt::cp_async_commit(); }\n";
+                    {
+                        Env e3 = env;
+                        int tmp;
+                        cv_mode = true;
+                        std::string pe2 = gen_slice_elem(ps, "(b_ * " + std::to_string(KB) + " + kq_)", e3, tmp);
+                        out << "          const bool live_ = b_ * " << KB << " + kq_ < " << lp_ << ";\n";
+                        out << "          double bf_[" << NT << "];\n";
+                        out << "          { const double* thB_ = thT - kq_ * TB;  // the caller passes this thread's chain group; fragments address all TBS positions\n";
+                        out << "            _Pragma(\"unroll\") for (int t_ = 0; t_ < " << NT << "; ++t_) { const int c_ = bpos_ + 2 * t_; const double* thT = thB_; bf_[t_] = live_ ? " << pe2 << " : 0.0; } }\n";
+                        out << "          const double* xs_ = xw_ + ring_pos * " << BLK << " + kq_ * " << XS << " + rq_;\n";
+                        out << "          _Pragma(\"unroll\") for (int r_ = 0; r_ < R; ++r_) {\n";
+                        out << "            double a_ = xs_[8 * r_];\n";
+                        if (lp_ % KB != 0) out << "            if (b_ == " << NBR - 1 << ") a_ = live_ ? a_ : 0.0;  // never multiply stale shared memory\n";
+                        out << "            _Pragma(\"unroll\") for (int t_ = 0; t_ < " << NT << "; ++t_) apt::dmma884(" << nm << "[r_][2 * t_], " << nm << "[r_][2 * t_ + 1], a_, bf_[t_]);\n          }\n";
+                    }
+                    out << "          ring_pos = (ring_pos + 1 == " << TRS << ") ? 0 : ring_pos + 1;\n        }\n";
+                    prime << "      if constexpr (GI == " << bi << ") {\n        const int lane_ = tid_ & 31;\n        double* xw_ = xbuf + (tid_ >> 5) * " << TRS * BLK << ";\n"
+                          << "        _Pragma(\"unroll\") for (int b_ = 0; b_ < " << TRD << "; ++b_) {\n";
+                    fill(prime, "          ", "b_", "i0", "b_");
+                    prime << "          apt::cp_async_commit();\n        }\n      }\n";
+                    ring_slots = std::max(ring_slots, (TRS * BLK + 31) / 32);
+                    hoisted[ip.get()] = nm + "[r_][c_]";
+                    env[d.loops[0].var] = "(" + std::to_string(d.loops[0].lo) + " + i0 + r_ * 8 + rq_)";
+                    continue;
+                }
                 if (allow_ring && vec && !any_ring && bigs.size() == 1 && lp_ % BW == 0 && lp_ / BW >= 3 && ring_ok && tile_want && ips.size() == 1) {
                     // Tile mode.  A warp owns TR consecutive rows; lane = (row group rg, chain group cg): the thread
                     // multiplies RT rows (RT/2 adjacent pairs, one LDS.128 each) by TBT chains, so that one broadcast
@@ -1922,6 +1986,9 @@ struct Lowerer {
                     tile_rt = std::min(4, 2 * tile_cs);  // 4 rows x 4 chains measured best at 16 rungs (8 x 4 spills at 128 registers)
                     if (const char* e = getenv("APTB200_TILE_RT")) tile_rt = std::max(2, atoi(e) & ~1);
                     tile_rows = (32 / tile_cs) * tile_rt;
+                    // the X beta product of a tile on the FP64 tensor-core path: 8 or 16 rungs per pass (1 or 2 chain blocks of 8)
+                    tile_mma = (TB == 8 || TB == 16) && !getenv("APTB200_NO_MMA") && !getenv("APTB200_TILE_TBT") && !getenv("APTB200_TILE_RT");
+                    if (tile_mma) { tile_cs = 4; tile_rt = 4; tile_rows = 32; tile_tb = TB; }
                 }
                 }
             }
