@@ -166,6 +166,8 @@ struct Engine {
     DevBuf<double> g_partial, g_pend, g_scratch;  // grid engine
     DevBuf<unsigned int> g_ticket;
     DevBuf<long long> g_dbg, g_delta_tag;
+    DevBuf<unsigned long long> g_flags;  // hand-over between pass kernels (apt_grid.cuh)
+    unsigned long long launch_seq = 0;
     DevBuf<double> g_delta;
     int num_sms = 148, grid_occ = 1;
     DevBuf<double> samples, samples2, samplesT, samples2T, logprobs, temptraj;
@@ -261,6 +263,7 @@ struct Engine {
             g_partial.alloc((size_t)num_sms * 8 * 2 * G::TB);
             g_ticket.alloc(1); g_ticket.zero(stream);
             g_dbg.alloc(80); g_dbg.zero(stream);
+            g_flags.alloc(2); g_flags.zero(stream);
             g_delta.alloc(nch * 2 * G::DMAX); g_delta.zero(stream);
             g_delta_tag.alloc(nch * 2);
             APT_CUDA(cudaMemsetAsync(g_delta_tag.p, 0xff, nch * 2 * sizeof(long long), stream));
@@ -506,36 +509,25 @@ struct Engine {
                 g.dbg = getenv("APTB200_DEBUG_TIMING") ? g_dbg.p : nullptr;
                 g.delta = getenv("APTB200_NO_DELTA_CTA") ? nullptr : g_delta.p; g.delta_tag = g_delta_tag.p;
                 APT_CUDA(cudaEventRecord(ev0, stream));
-                g.next_stage = 0; g.next_pass = 0; g.next_it = it0;
-                G::launch_prologue(g, stream);
-                long long nl = 1;
-                for (long long it = it0; it < it1; ++it)
-                    for (int st = 0; st < G::NSTAGE; ++st)
-                        for (int ps = 0; ps < npass; ++ps) {
-                            g.it = it; g.stage = st; g.pass = ps;
-                            g.last_of_iter = (st == G::NSTAGE - 1 && ps == npass - 1) ? 1 : 0;
-                            if (ps + 1 < npass) { g.next_stage = st; g.next_pass = ps + 1; g.next_it = it; }
-                            else if (st + 1 < G::NSTAGE) { g.next_stage = st + 1; g.next_pass = 0; g.next_it = it; }
-                            else if (it + 1 < it1) { g.next_stage = 0; g.next_pass = 0; g.next_it = it + 1; }
-                            else { g.next_stage = -1; g.next_pass = 0; g.next_it = 0; }
-                            G::launch_stage(st, g, grid, smem, stream);
-                            nl++;
-                        }
+                g.flags = g_flags.p; g.seq0 = launch_seq;
+                const long long nl = (it1 - it0) * G::NSTAGE * npass;  // steps (passes over the data) of this launch
+                launch_seq += (unsigned long long)nl + 1;  // the proposals of the first step are published as seq0 + 1, step n as seq0 + n + 2
+                if (grid < 2) throw ApiError{"grid engine: the device must hold at least 2 resident CTAs (a control CTA and a streaming CTA)"};
+                APT_CUDA(G::launch_run(g, grid, smem, stream));
                 APT_CUDA(cudaGetLastError());
                 APT_CUDA(cudaEventRecord(ev1, stream));
                 APT_CUDA(cudaEventSynchronize(ev1));
                 float ms = 0;
                 APT_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
-                timing.kernel_ms += ms; timing.main_kernel_ms += ms; timing.launches += nl; timing.main_launches += nl - 1;
+                timing.kernel_ms += ms; timing.main_kernel_ms += ms; timing.launches += 1; timing.main_launches += nl;  // main_launches: passes over the data inside the persistent launch
                 rngIter += (uint64_t)(it1 - it0);
                 totalIters += (it1 - it0);
                 it_done = it1;
                 copy_rows_async(it0, it1);
-                if (g.dbg) {
+                if (getenv("APTB200_DEBUG_TIMING")) {
                     auto v = d2h(g_dbg.p, 80);
-                    fprintf(stderr, "[aptb200] finishing CTA cycles: stream %lld cta-reduce+ticket %lld reduce %lld finish %lld ladder %lld propose %lld total %lld (delta CTA %lld)\n", v[6] - v[5], v[0] - v[6], v[1] - v[0], v[2] - v[1], v[3] - v[2], v[4] - v[3], v[4] - v[5], v[7]);
-                    fprintf(stderr, "   ladder step: load %lld | lp+philox+log %lld | K^2 exp %lld | rowsum %lld | normalise+log %lld | chain %lld | adapt %lld | traces+writeback %lld\n", v[8] - v[2], v[9] - v[8], v[10] - v[9], v[11] - v[10], v[12] - v[11], v[13] - v[12], v[14] - v[13], v[3] - v[15]);
-                    for (int i = 0; i + 1 < 8 && i + 1 < (int)(it1 - it0) * npass; i++) { const int i0_ = (int)((it0 * npass + i) & 31), i1_ = (int)((it0 * npass + i + 1) & 31); fprintf(stderr, "   launch %d: in-kernel %lld ns, gap to next %lld ns\n", i, v[17 + 2 * i0_] - v[16 + 2 * i0_], v[16 + 2 * i1_] - v[17 + 2 * i0_]); }
+                    fprintf(stderr, "[aptb200] control CTA cycles (last step of the launch): delta %lld | preload %lld | wait for the streaming CTAs %lld | reduce %lld | finish %lld | ladder (to the swaps) %lld | propose+publish %lld | deferred %lld\n", v[7], v[6] - v[5] - v[7], v[0] - v[6], v[1] - v[0], v[2] - v[1], v[3] - v[2], v[4] - v[3], v[15] - v[4]);
+                    fprintf(stderr, "   ladder step: load %lld | lp+philox+log %lld | K^2 exp %lld | rowsum %lld | normalise+log %lld | chain %lld\n", v[8] - v[2], v[9] - v[8], v[10] - v[9], v[11] - v[10], v[12] - v[11], v[13] - v[12]);
                 }
             }
         }

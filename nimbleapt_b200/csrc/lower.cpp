@@ -1230,6 +1230,8 @@ struct Lowerer {
     // all chains (the loop over the TB chains is innermost and fully unrolled into registers).
     // tile mode of the grid engine (see emit_big_eval_fn): lanes of a warp = (row group, chain group)
     bool tile_want = false, unit_tile = false, tile_mma = false;
+    std::string mma_stage_fn, mma_y_hoisted;
+    int frag_doubles = 0;
     int tile_cs = 1, tile_rt = 2, tile_rows = 64, tile_tb = 1;
     void emit_big_eval(Unit& u) {
         std::vector<size_t> bigs;
@@ -1237,11 +1239,14 @@ struct Lowerer {
             if (u.groups[g].big) bigs.push_back(g);
         out << "    static constexpr int NBIG = " << bigs.size() << ";\n";
         unit_tile = false;
+        mma_stage_fn.clear(); mma_y_hoisted.clear();
         if (!bigs.empty()) {
             emit_big_eval_fn(u, bigs, "big_eval", true);
             if (unit_tile) emit_big_eval_fn(u, bigs, "big_eval_rem", false);
         } else emit_big_eval_fn(u, bigs, "big_eval", true);
-        out << "    static constexpr bool TILE = " << (unit_tile ? "true" : "false") << ";\n";
+        out << "    static constexpr bool TILE = " << (unit_tile ? "true" : "false") << ", MMA = " << (mma_stage_fn.empty() ? "false" : "true") << ";\n";
+        if (mma_stage_fn.empty()) out << "    __device__ static __forceinline__ void mma_stage(const double*, double*, int) {}\n";
+        else out << mma_stage_fn;
         out << "    static constexpr int CS = " << (unit_tile ? tile_cs : 1) << ", RT = " << (unit_tile ? tile_rt : 1) << ", TROWS = " << (unit_tile ? tile_rows : 1) << ";\n";
     }
     void emit_big_eval_fn(Unit& u, const std::vector<size_t>& bigs, const std::string& fname, bool allow_ring) {
@@ -1326,7 +1331,13 @@ struct Lowerer {
                     out << "        static_assert(R == 4 && TB == " << 2 * NT << ", \"MMA tile: 4 rows x TBS/4 chains per thread\");\n";
                     out << "        const int lane_ = tid_ & 31, kq_ = lane_ & 3, rq_ = lane_ >> 2;\n";
                     out << "        double* xw_ = xbuf + (tid_ >> 5) * " << TRS * BLK << ";\n";
-                    out << "        const int bpos_ = (rq_ >> 1) * TB + (rq_ & 1);  // chain position of column rq_ of chain block 0 (block t: + 2 t)\n";
+                    out << "        const double* thF_ = xbuf - Model::FRAG_DOUBLES + lane_ * " << NT << ";  // B fragments of this lane, see mma_stage\n";
+                    {   // the responses of the thread's rows are on their way while the product runs
+                        Env ey = env;
+                        ey[d.loops[0].var] = "(" + std::to_string(d.loops[0].lo) + " + i0 + r_ * 8 + rq_)";
+                        out << "        double yh_[R];\n        _Pragma(\"unroll\") for (int r_ = 0; r_ < R; ++r_) yh_[r_] = " << gen_dbl(d.lhs, ey) << ";\n";
+                        mma_y_hoisted = gen_dbl(d.lhs, ey);
+                    }
                     out << "        double " << nm << "[R][TB];\n";
                     out << "        _Pragma(\"unroll\") for (int r_ = 0; r_ < R; ++r_) { _Pragma(\"unroll\") for (int c_ = 0; c_ < TB; ++c_) " << nm << "[r_][c_] = 0.0; }\n";
                     out << "        _Pragma(\"unroll\") for (int b_ = 0; b_ < " << NBR << "; ++b_) {\n";
@@ -1342,8 +1353,20 @@ struct Lowerer {
                         std::string pe2 = gen_slice_elem(ps, "(b_ * " + std::to_string(KB) + " + kq_)", e3, tmp);
                         out << "          const bool live_ = b_ * " << KB << " + kq_ < " << lp_ << ";\n";
                         out << "          double bf_[" << NT << "];\n";
-                        out << "          { const double* thB_ = thT - kq_ * TB;  // the caller passes this thread's chain group; fragments address all TBS positions\n";
-                        out << "            _Pragma(\"unroll\") for (int t_ = 0; t_ < " << NT << "; ++t_) { const int c_ = bpos_ + 2 * t_; const double* thT = thB_; bf_[t_] = live_ ? " << pe2 << " : 0.0; } }\n";
+                        if (NT == 2) out << "          { const double2 f2_ = *reinterpret_cast<const double2*>(thF_ + b_ * 64); bf_[0] = f2_.x; bf_[1] = f2_.y; }\n";
+                        else out << "          bf_[0] = thF_[b_ * 32];\n";
+                        // the staged parameters in fragment order: [block][lane][chain block], zeros beyond the last column (one
+                        // conflict-free LDS per block; read straight from the [parameter][position] staging, the four lanes of a
+                        // row group collide on the same banks)
+                        std::ostringstream st;
+                        st << "    __device__ static __forceinline__ void mma_stage(const double* thT, double* thF, int tid_) {\n";
+                        st << "      constexpr int TBS = Model::TB, TB = " << 2 * NT << ";\n";
+                        st << "      for (int i_ = tid_; i_ < " << NBR * 32 * NT << "; i_ += Model::GRID_THREADS) {\n";
+                        st << "        const int t_ = i_ % " << NT << ", lane_ = (i_ / " << NT << ") % 32, b_ = i_ / " << 32 * NT << ", kq_ = lane_ & 3, rq_ = lane_ >> 2;\n";
+                        st << "        const int c_ = (rq_ >> 1) * TB + (rq_ & 1) + 2 * t_;\n";
+                        st << "        thF[i_] = (b_ * " << KB << " + kq_ < " << lp_ << ") ? " << pe2 << " : 0.0;\n      }\n    }\n";
+                        mma_stage_fn = st.str();
+                        frag_doubles = std::max(frag_doubles, NBR * 32 * NT);
                         out << "          const double* xs_ = xw_ + ring_pos * " << BLK << " + kq_ * " << XS << " + rq_;\n";
                         out << "          _Pragma(\"unroll\") for (int r_ = 0; r_ < R; ++r_) {\n";
                         out << "            double a_ = xs_[8 * r_];\n";
@@ -1489,7 +1512,7 @@ struct Lowerer {
             if (unit_tile && primary && d.dist == "dbinom" && opts.fuse_links && (is_call(d.iargs[0], "ilogit") || is_call(d.iargs[0], "expit")) && try_ceval(d.iargs[1], {}, sz_) && sz_ == 1.0) {
                 // fused Bernoulli-logit terms of the whole thread tile (pairs of rows in lock step)
                 out << "        double y_[R], eta_[R][TB];\n";
-                out << "        _Pragma(\"unroll\") for (int r_ = 0; r_ < R; ++r_) { y_[r_] = " << gen_dbl(d.lhs, env) << "; _Pragma(\"unroll\") for (int c_ = 0; c_ < TB; ++c_) eta_[r_][c_] = "
+                out << "        _Pragma(\"unroll\") for (int r_ = 0; r_ < R; ++r_) { y_[r_] = " << ((!mma_y_hoisted.empty() && mma_y_hoisted == gen_dbl(d.lhs, env)) ? std::string("yh_[r_]") : gen_dbl(d.lhs, env)) << "; _Pragma(\"unroll\") for (int c_ = 0; c_ < TB; ++c_) eta_[r_][c_] = "
                     << gen_dbl(d.iargs[0]->a[0], env) << "; }\n";
                 out << "        apt::bern_logit_tile<R, TB>(y_, eta_, acc);\n      }\n";
                 cv_mode = false;
@@ -2044,27 +2067,23 @@ struct Lowerer {
             for (size_t i = 0; i < units.size(); i++)
                 if (units[i].kind == 1) out << "      case " << i << ": apt::block_increment<Model, S" << i << ">(c, k, 0, z, outp); break;\n";
             out << "      default: break;\n    }\n  }\n";
-            out << "  static void launch_stage(int s, const apt::GArgs& a, int grid, size_t smem, cudaStream_t st) {\n    switch (s) {\n";
-            for (size_t i = 0; i < units.size(); i++)
-                out << "      case " << i << ": apt::launch_pass(apt::grid_pass_kernel<Model, S" << i << ">, grid, GRID_THREADS, smem, st, a); break;\n";
+            out << "  template <class F> __device__ static __forceinline__ void with_stage(int s, F&& f) {\n    switch (s) {\n";
+            for (size_t i = 0; i < units.size(); i++) out << "      case " << i << ": f(apt::StageTag<S" << i << ">{}); break;\n";
             out << "    }\n  }\n";
-            out << "  static void launch_prologue(const apt::GArgs& a, cudaStream_t st) { apt::grid_prologue_kernel<Model><<<1, GRID_THREADS, 0, st>>>(a); }\n";
-            out << "  static void set_stage_smem(size_t smem) {\n";
-            for (size_t i = 0; i < units.size(); i++)
-                out << "    cudaFuncSetAttribute(apt::grid_pass_kernel<Model, S" << i << ">, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);\n";
-            out << "  }\n";
-            out << "  static int stage_occupancy(int s, size_t smem) {\n    int n = 1;\n    switch (s) {\n";
-            for (size_t i = 0; i < units.size(); i++)
-                out << "      case " << i << ": cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, apt::grid_pass_kernel<Model, S" << i << ">, GRID_THREADS, smem); break;\n";
-            out << "    }\n    return n;\n  }\n";
+            // one cooperative launch per chunk of iterations: every CTA must be resident (they wait for each other)
+            out << "  static cudaError_t launch_run(const apt::GArgs& a, int grid, size_t smem, cudaStream_t st) {\n";
+            out << "    void* args_[] = {(void*)&a};\n";
+            out << "    return cudaLaunchCooperativeKernel((void*)apt::grid_run_kernel<Model>, dim3((unsigned)grid), dim3(GRID_THREADS), args_, smem, st);\n  }\n";
+            out << "  static void set_stage_smem(size_t smem) { cudaFuncSetAttribute(apt::grid_run_kernel<Model>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); }\n";
+            out << "  static int stage_occupancy(int, size_t smem) { int n = 1; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, apt::grid_run_kernel<Model>, GRID_THREADS, smem); return n; }\n";
         }
         // sweep: stages
         if (engine != 2) {
             out << "  template <class C> __device__ static __forceinline__ void propose_stage(int, C&, const Data&, int, double*, const double*) {}\n";
             out << "  __host__ __device__ static constexpr bool stage_is_block(int) { return false; }\n  __host__ __device__ static constexpr int stage_unit0(int) { return 0; }\n";
             out << "  template <class C> __device__ static __forceinline__ void delta_stage(int, C&, int, double*, double*) {}\n";
-            out << "  static void launch_stage(int, const apt::GArgs&, int, size_t, cudaStream_t) {}\n";
-            out << "  static void launch_prologue(const apt::GArgs&, cudaStream_t) {}\n  static int stage_occupancy(int, size_t) { return 1; }\n  static void set_stage_smem(size_t) {}\n";
+            out << "  static cudaError_t launch_run(const apt::GArgs&, int, size_t, cudaStream_t) { return cudaSuccess; }\n";
+            out << "  static int stage_occupancy(int, size_t) { return 1; }\n  static void set_stage_smem(size_t) {}\n";
         }
         out << "  template <class C> __device__ static __forceinline__ void sweep(C& c, const Data& D, bool active) {\n";
         size_t ui = 0;
@@ -2140,7 +2159,7 @@ struct Lowerer {
             out << "  static constexpr int LADDER_MINB = " << minb << ";\n";
         }
         out << "  static constexpr bool STATE_IN_SMEM = " << (smem_state && engine == 1 ? "true" : "false") << ", HAS_FAMILY = " << (has_family ? "true" : "false") << ";\n";
-        out << "  static constexpr int ENGINE = " << engine << ", TB = " << TB << ", R = " << R << ", GRID_THREADS = 256, RING_SLOTS = " << ring_slots << ", CSPLIT = " << csplit << ", GRID_MINB = " << (getenv("APTB200_GRID_MINB") ? std::max(1, atoi(getenv("APTB200_GRID_MINB"))) : (csplit == 2 ? 3 : 2)) << ", NSTAGE = " << units.size() << ";\n";
+        out << "  static constexpr int ENGINE = " << engine << ", TB = " << TB << ", R = " << R << ", GRID_THREADS = 256, RING_SLOTS = " << ring_slots << ", FRAG_DOUBLES = " << frag_doubles << ", CSPLIT = " << csplit << ", GRID_MINB = " << (getenv("APTB200_GRID_MINB") ? std::max(1, atoi(getenv("APTB200_GRID_MINB"))) : (csplit == 2 ? 3 : 2)) << ", NSTAGE = " << units.size() << ";\n";
         // derived arrays (data-only terms, filled by derived_kernel when data is uploaded)
         out << "  static constexpr int NDER = " << derived.size() << ";\n";
         out << "  static long der_inst(int k) { return ";
