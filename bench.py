@@ -262,7 +262,9 @@ def c3_roofline(device, passes=400):
     r = res[16]
     return {"bound": "hbm", "achieved": r["achieved"], "peak": peak, "unit": "GB/s", "frac": r["frac"],
             "traffic": 413.7e6, "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture (profiles/)",
-            "peak_source": how, "kernel": "apt::grid_pass_kernel", "ms_per_launch": r["ms_per_launch"], "launches": r["launches"],
+            "peak_source": how, "kernel": "apt::grid_run_kernel", "ms_per_launch": r["ms_per_launch"], "launches": r["launches"],
+            "launch_unit": "one pass over the data (X and y read once for all rungs of the pass); the kernel is persistent -- one cooperative "
+                           "launch runs 256 iterations -- so device time of the launches / passes inside them is the per-pass duration",
             "algorithmic_bytes_per_launch": by, "rungs_per_pass": 16, "updates_per_s": r["updates_per_s"],
             "timed": "400 passes after 1620 iterations (adapted ladder); first_400_iterations = iterations 21..420",
             "first_400_iterations": r["first_400_iterations"],

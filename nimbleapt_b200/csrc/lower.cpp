@@ -1315,7 +1315,7 @@ struct Lowerer {
                     unit_tile = true;
                     const int KB = 4, XS = 36;  // columns per block; padded column stride (doubles): LDS.64 of a fragment hits 16 distinct bank pairs
                     const int NBR = (lp_ + KB - 1) / KB, NT = tile_tb / 8;
-                    int TRD = 3;
+                    int TRD = std::min(NBR, 6);  // blocks in flight per warp (measured at 16 rungs, ms per pass: 3: 0.1331, 4: 0.1309, 5: 0.1301, 6: 0.1299, 7: 0.1297)
                     if (const char* e = getenv("APTB200_TILE_DEPTH")) TRD = std::max(1, std::min(NBR, atoi(e)));
                     const int TRS = TRD + 1, BLK = KB * XS;
                     auto xaddr = [&](const std::string& row, const std::string& col) {
