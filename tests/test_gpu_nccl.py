@@ -111,14 +111,20 @@ def test_two_gpus_reproduce_one_and_nccl_gathers(tmp_path):
     from nimbleapt_b200.sharding import local_moments
     world, total, niter = 2, 5, 400
     mp.spawn(_worker, args=(world, _free_port(), total, niter, str(tmp_path)), nprocs=world, join=True)
+    # one process, all 5 ladders, the same four runs as the workers (every run continues the random slots of the one before
+    # and starts from the state the one before left in the model, APT:548; the workers' third run samples too before the
+    # root reports its short buffer)
     eng = build_engine(_spec(), nLadders=total)
-    eng.run(niter, thin=2)
-    ref = eng.mvSamples.matrix(-1)
+    refs = []
+    for _ in range(4):
+        eng.run(niter, thin=2)
+        refs.append(eng.mvSamples.matrix(-1).copy())
+    ref = refs[3]
     loc = [np.load(tmp_path / ("local%d.npy" % r)) for r in range(world)]
     assert [a.shape[0] for a in loc] == [3, 2]
     assert np.array_equal(np.concatenate(loc), ref)  # sharding does not change any ladder's chain
-    for name in ("run_root0", "run_root1", "g_root0", "g_root1", "allg0", "allg1"):
-        assert np.array_equal(np.load(tmp_path / (name + ".npy")).reshape(ref.shape), ref), name
+    for name, want in (("run_root0", refs[0]), ("run_root1", refs[1]), ("g_root0", ref), ("g_root1", ref), ("allg0", ref), ("allg1", ref)):
+        assert np.array_equal(np.load(tmp_path / (name + ".npy")).reshape(want.shape), want), name
     m0, m1 = np.load(tmp_path / "mom0.npy"), np.load(tmp_path / "mom1.npy")
     assert np.array_equal(m0, m1)
     np.testing.assert_allclose(m0, local_moments(ref), rtol=1e-13)
