@@ -203,6 +203,12 @@ int apt_model_create(const char* bugs_code, apt_model** out);
 void apt_model_free(apt_model* m);
 int apt_model_set_array(apt_model* m, const char* name, int role, const double* values, const int64_t* dims, int ndim);
 int apt_model_add_sampler(apt_model* m, const char* target, const char* type, const apt_sampler_control* control);
+/* A user-supplied deterministic function the model code calls (a nimbleFunction with a `run` function: demo/APT_demo.R:42-71
+ * k2theta / k2sigma).  r_source is the R text of the function -- `function(k = double(), v = double(1), ...) { ... }`, or the
+ * whole `nimbleFunction(run = function(...) {...})` -- with scalar / vector double arguments, assignments, if / else,
+ * return(), arithmetic, comparisons, | & !, ceiling floor round trunc abs exp log sqrt ..., and indexed loads of the vector
+ * arguments; it is inlined into the lowered model.  Replaces nimble's compilation of the nimbleFunction. */
+int apt_model_add_function(apt_model* m, const char* name, const char* r_source);
 int apt_model_remove_samplers(apt_model* m);
 int apt_model_set_monitors(apt_model* m, int which /* 1 | 2 */, const char* const* names, int n);
 int apt_model_set_thin(apt_model* m, int thin, int thin2);

@@ -21,7 +21,7 @@ sampler_RW_multinomial_tempered <- structure(list(name = "sampler_RW_multinomial
 
 ## Works with a nimble MCMCconf (conf$samplerConfs[[i]]$target / $name / $control, conf$monitors, conf$thin, conf$model)
 ## or with a plain list(model = list(code =, constants =, data =, inits =), samplers = list(...), monitors =, thin =).
-buildAPT <- function(conf, Temps, monitorTmax = TRUE, ULT = 1E6, thinPrintTemps = 1, nLadders = 1, seed = 11L, device = 0L, ...) {
+buildAPT <- function(conf, Temps, monitorTmax = TRUE, ULT = 1E6, thinPrintTemps = 1, nLadders = 1, seed = 11L, device = 0L, functions = list(), ...) {
     if (missing(ULT)) message(paste("ULT set to", ULT))                                   # APT:254-257
     if (inherits(conf, "modelBaseClass")) conf <- nimble::configureMCMC(conf, ...)        # APT:249-250
     is_nimble <- inherits(conf, "MCMCconf")
@@ -44,6 +44,13 @@ buildAPT <- function(conf, Temps, monitorTmax = TRUE, ULT = 1E6, thinPrintTemps 
         thin <- if (is.null(conf$thin)) 1L else conf$thin; thin2 <- if (is.null(conf$thin2)) 1L else conf$thin2
     }
     m <- .Call("aptR_model_create", code)
+    ## user-supplied nimbleFunctions the model code calls (demo/APT_demo.R:42-71): `functions = list(k2theta = k2theta, ...)`;
+    ## the text of their run functions is inlined by the library instead of being compiled by nimble
+    for (nm in names(functions)) {
+        f <- functions[[nm]]
+        run <- if (is.function(f)) environment(f)$nfMethodRCobject$run else f   # [NIMBLE-UNVERIFIED] where nimble keeps `run`
+        .Call("aptR_model_add_function", m, nm, if (is.character(run)) run else paste(deparse(run), collapse = "\n"))
+    }
     for (nm in names(constants)) .Call("aptR_model_set_array", m, nm, 0L, constants[[nm]])
     for (nm in names(data))      .Call("aptR_model_set_array", m, nm, 1L, data[[nm]])
     for (nm in names(inits))     .Call("aptR_model_set_array", m, nm, 2L, inits[[nm]])

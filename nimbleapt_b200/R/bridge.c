@@ -28,6 +28,12 @@ SEXP aptR_model_create(SEXP code) {
     return p;
 }
 
+/* a user-supplied deterministic function the model code calls: name, deparse()d text of the nimbleFunction's run function */
+SEXP aptR_model_add_function(SEXP p, SEXP name, SEXP src) {
+    chk(apt_model_add_function(R_ExternalPtrAddr(p), CHAR(STRING_ELT(name, 0)), CHAR(STRING_ELT(src, 0))));
+    return R_NilValue;
+}
+
 /* role: 0 constants, 1 data, 2 inits; x is a numeric vector/matrix (column-major, as R stores it) */
 SEXP aptR_model_set_array(SEXP p, SEXP name, SEXP role, SEXP x) {
     SEXP dim = Rf_getAttrib(x, R_DimSymbol);

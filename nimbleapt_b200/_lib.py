@@ -42,7 +42,7 @@ class Timing(C.Structure):
 # every symbol include/aptb200.h declares
 EXPORTS = ["apt_last_error", "apt_version", "apt_abi_sizeof", "apt_sampler_control_default", "apt_build_opts_default",
            "apt_run_args_default", "apt_model_create", "apt_model_free", "apt_model_set_array",
-           "apt_model_add_sampler", "apt_model_remove_samplers", "apt_model_set_monitors", "apt_model_set_thin",
+           "apt_model_add_sampler", "apt_model_add_function", "apt_model_remove_samplers", "apt_model_set_monitors", "apt_model_set_thin",
            "apt_model_names", "apt_model_lower", "apt_model_compile", "apt_build", "apt_free", "apt_run", "apt_info", "apt_get", "apt_get_layout",
            "apt_get_timing", "apt_logprob", "apt_waic", "apt_set_inits", "apt_set_array", "apt_comm_unique_id", "apt_comm_init",
            "apt_comm_allgather_samples", "apt_comm_gather_samples", "apt_comm_allreduce_sum", "apt_comm_finalize"]
@@ -75,6 +75,7 @@ def lib():
     L.apt_model_free.argtypes = [vp]
     L.apt_model_set_array.argtypes = [vp, C.c_char_p, C.c_int, dp, C.POINTER(C.c_int64), C.c_int]
     L.apt_model_add_sampler.argtypes = [vp, C.c_char_p, C.c_char_p, C.POINTER(SamplerControl)]
+    L.apt_model_add_function.argtypes = [vp, C.c_char_p, C.c_char_p]
     L.apt_model_remove_samplers.argtypes = [vp]
     L.apt_model_set_monitors.argtypes = [vp, C.c_int, C.POINTER(C.c_char_p), C.c_int]
     L.apt_model_set_thin.argtypes = [vp, C.c_int, C.c_int]

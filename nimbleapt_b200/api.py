@@ -51,22 +51,46 @@ def _dp(a):
     return a.ctypes.data_as(C.POINTER(C.c_double))
 
 
+_FUNCTIONS = {}  # user-supplied functions by name: R finds them in the calling environment, here they register themselves
+
+
+class NimbleFunction:
+    """nimbleFunction(run = function(...) {...}): a deterministic function the model code calls (demo/APT_demo.R:42-71).
+    `run` is the R text of the function; the library inlines it into the lowered model (apt_model_add_function)."""
+
+    def __init__(self, run, name=None):
+        self.run, self.name = str(run), name
+        if name:
+            _FUNCTIONS[name] = self
+
+
+def nimbleFunction(run, name=None, **_ignored):
+    return NimbleFunction(run, name)
+
+
 class NimbleModel:
     """nimbleModel(code, constants, data, inits) for the supported BUGS subset."""
 
-    def __init__(self, code, constants=None, data=None, inits=None):
+    def __init__(self, code, constants=None, data=None, inits=None, functions=None):
         self.code = code
         self.constants = {k: np.asarray(v, dtype=np.float64) for k, v in (constants or {}).items()}
         self.data = {k: np.asarray(v, dtype=np.float64) for k, v in (data or {}).items()}
         self.inits = {k: np.asarray(v, dtype=np.float64) for k, v in (inits or {}).items()}
+        fns = {k: v for k, v in _FUNCTIONS.items() if (k + "(") in code.replace(" ", "")}
+        fns.update(functions or {})
+        self.functions = {k: (v.run if isinstance(v, NimbleFunction) else str(v)) for k, v in fns.items()}
         # parse now so that syntax errors surface where nimbleModel() would raise them
         h = C.c_void_p()
         check(lib().apt_model_create(code.encode(), C.byref(h)))
-        lib().apt_model_free(h)
+        try:
+            for k, v in self.functions.items():
+                check(lib().apt_model_add_function(h, k.encode(), v.encode()))
+        finally:
+            lib().apt_model_free(h)
 
 
-def nimbleModel(code, constants=None, data=None, inits=None, **_ignored):
-    return NimbleModel(code, constants, data, inits)
+def nimbleModel(code, constants=None, data=None, inits=None, functions=None, **_ignored):
+    return NimbleModel(code, constants, data, inits, functions)
 
 
 class MCMCconf:
@@ -183,6 +207,8 @@ class APT:
         self.conf = conf
         model = conf.model
         check(L.apt_model_create(model.code.encode(), C.byref(self._m)))
+        for k, v in model.functions.items():
+            check(L.apt_model_add_function(self._m, k.encode(), v.encode()))
         for role, d in ((0, model.constants), (1, model.data), (2, model.inits)):
             for name, arr in d.items():
                 a = np.asfortranarray(arr, dtype=np.float64)

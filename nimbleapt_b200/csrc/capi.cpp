@@ -151,6 +151,13 @@ int apt_model_add_sampler(apt_model* m, const char* target, const char* type, co
     m->spec.samplers.push_back(std::move(sc));
     API_END
 }
+int apt_model_add_function(apt_model* m, const char* name, const char* r_source) {
+    API_BEGIN
+    if (!m || !name || !r_source) throw Error("null argument");
+    (void)parse_user_function(name, r_source);  // syntax errors are reported here, not at buildAPT time
+    m->spec.functions[name] = r_source;
+    API_END
+}
 int apt_model_remove_samplers(apt_model* m) {
     API_BEGIN
     m->spec.samplers.clear();

@@ -4,6 +4,7 @@
 // (APT_functions.R:157-162 documents that the reference must be compiled by nimble at this point).
 #pragma once
 #include <cstdint>
+#include <functional>
 #include <map>
 #include <memory>
 #include <stdexcept>
@@ -47,6 +48,17 @@ struct RawDecl {
     int line = 0;
 };
 std::vector<RawDecl> parse_bugs(const std::string& code);
+// A user-supplied deterministic function (nimbleFunction with a `run` function of scalar / vector double arguments:
+// assignments, if / else, return, arithmetic, comparisons, ceiling / floor / abs ..., indexed loads; demo/APT_demo.R:42-71).
+// It is inlined where the model calls it: `call` executes the body symbolically on the argument expressions.
+struct UserFunction {
+    struct Param { std::string name; int ndim = 0; };
+    std::string name;
+    std::vector<Param> params;
+    std::function<EP(const std::vector<EP>&, const std::vector<std::string>&)> call;
+};
+UserFunction parse_user_function(const std::string& name, const std::string& r_source);
+EP expand_user_calls(const EP& e, const std::map<std::string, UserFunction>& fns, int depth = 0);
 EP parse_expr_text(const std::string& s);  // e.g. a sampler target "beta[1:50]"
 
 struct Array {
@@ -66,7 +78,8 @@ struct SamplerConf {
 
 struct ModelSpec {
     std::string code;
-    std::vector<RawDecl> decls;
+    std::vector<RawDecl> decls;  // user-supplied functions already inlined
+    std::map<std::string, std::string> functions;  // name -> R source, as given to apt_model_add_function
     std::map<std::string, Array> constants, data, inits;
     std::vector<SamplerConf> samplers;
     std::vector<std::string> monitors, monitors2;

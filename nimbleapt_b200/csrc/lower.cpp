@@ -173,7 +173,24 @@ struct Lowerer {
                     if (e->name == "log") return std::log(x);
                     if (e->name == "sqrt") return std::sqrt(x);
                     if (e->name == "abs") return std::fabs(x);
+                    if (e->name == "ceiling") return std::ceil(x);
+                    if (e->name == "floor") return std::floor(x);
+                    if (e->name == "round") return std::nearbyint(x);
+                    if (e->name == "trunc") return std::trunc(x);
+                    if (e->name == "__not") return x == 0.0 ? 1.0 : 0.0;
                 }
+                if (e->a.size() == 2 && e->name.rfind("__", 0) == 0) {
+                    double x = ceval(e->a[0], env), y = ceval(e->a[1], env);
+                    if (e->name == "__lt") return x < y;
+                    if (e->name == "__gt") return x > y;
+                    if (e->name == "__le") return x <= y;
+                    if (e->name == "__ge") return x >= y;
+                    if (e->name == "__eq") return x == y;
+                    if (e->name == "__ne") return x != y;
+                    if (e->name == "__or") return (x != 0.0) || (y != 0.0);
+                    if (e->name == "__and") return (x != 0.0) && (y != 0.0);
+                }
+                if (e->name == "__if" && e->a.size() == 3) return ceval(e->a[0], env) != 0.0 ? ceval(e->a[1], env) : ceval(e->a[2], env);
                 break;
             }
             default: break;
@@ -214,9 +231,20 @@ struct Lowerer {
         return r;
     }
 
+    // user-supplied deterministic functions (apt_model_add_function) are inlined where the model calls them
+    std::vector<RawDecl> expanded_decls;
+    void expand_functions() {
+        expanded_decls = spec.decls;
+        if (spec.functions.empty()) return;
+        std::map<std::string, UserFunction> fns;
+        for (auto& kv : spec.functions) fns[kv.first] = parse_user_function(kv.first, kv.second);
+        for (auto& rd : expanded_decls) rd.rhs = expand_user_calls(rd.rhs, fns);
+    }
+
     void canonicalise() {
         int idx = 0;
-        for (const RawDecl& rd : spec.decls) {
+        expand_functions();
+        for (const RawDecl& rd : expanded_decls) {
             CDecl d;
             d.line = rd.line;
             for (auto& l : rd.loops) {
@@ -995,6 +1023,16 @@ struct Lowerer {
                     return "(" + gen_int(e->a[0], env) + " " + e->op + " " + gen_int(e->a[1], env) + ")";
                 break;
             case Expr::NEG: return "(-" + gen_int(e->a[0], env) + ")";
+            case Expr::CALL:
+                // ceiling(k) etc. of a sampled node as an index (demo/APT_demo.R:49-53): evaluated in double, clamped into the
+                // array like a bare sampled-node index (the function's own range check decides what the value is used for)
+                if ((e->name == "ceiling" || e->name == "floor" || e->name == "round" || e->name == "trunc") && e->a.size() == 1 && dyn_dim > 0 && !cv_mode) {
+                    const int64_t dd = dyn_dim;
+                    const std::string v = gen_dbl(e, env);
+                    dyn_dim = dd;
+                    return "apt::dyn_index(" + v + ", " + std::to_string(dd) + ")";
+                }
+                break;
             default: break;
         }
         throw Error("unsupported index expression: " + to_string(e));
@@ -1071,6 +1109,18 @@ struct Lowerer {
         return gen_load(v, ref, e2);
     }
     int tmp_id = 0;
+    // a condition as a C boolean expression
+    std::string gen_cond(const EP& e, const Env& env) {
+        if (e->k == Expr::CALL && e->name.rfind("__", 0) == 0) {
+            static const std::map<std::string, std::string> c2 = {{"__lt", "<"}, {"__gt", ">"}, {"__le", "<="}, {"__ge", ">="}, {"__eq", "=="}, {"__ne", "!="}};
+            auto it = c2.find(e->name);
+            if (it != c2.end() && e->a.size() == 2) return "(" + gen_dbl(e->a[0], env) + " " + it->second + " " + gen_dbl(e->a[1], env) + ")";
+            if (e->name == "__or" && e->a.size() == 2) return "(" + gen_cond(e->a[0], env) + " || " + gen_cond(e->a[1], env) + ")";
+            if (e->name == "__and" && e->a.size() == 2) return "(" + gen_cond(e->a[0], env) + " && " + gen_cond(e->a[1], env) + ")";
+            if (e->name == "__not" && e->a.size() == 1) return "(!" + gen_cond(e->a[0], env) + ")";
+        }
+        return "(" + gen_dbl(e, env) + " != 0.0)";
+    }
     std::string gen_dbl(const EP& e, const Env& env) {
         double cv;
         if (try_ceval(e, {}, cv)) return fmt_d(cv);
@@ -1105,6 +1155,14 @@ struct Lowerer {
                     if (e->a.size() != 1) throw Error(e->name + "() takes one argument");
                     return it->second + "(" + gen_dbl(e->a[0], env) + ")";
                 }
+                {
+                    static const std::map<std::string, std::string> r1 = {{"ceiling", "ceil"}, {"floor", "floor"}, {"round", "nearbyint"}, {"trunc", "trunc"}};
+                    auto ir = r1.find(e->name);
+                    if (ir != r1.end() && e->a.size() == 1) return ir->second + "(" + gen_dbl(e->a[0], env) + ")";
+                }
+                if (e->name == "__if" && e->a.size() == 3)  // lazily evaluated, like the `if (...) return(...)` it came from
+                    return "(" + gen_cond(e->a[0], env) + " ? " + gen_dbl(e->a[1], env) + " : " + gen_dbl(e->a[2], env) + ")";
+                if (e->name.rfind("__", 0) == 0) return "(" + gen_cond(e, env) + " ? 1.0 : 0.0)";
                 if (e->name == "pow" && e->a.size() == 2) return "pow(" + gen_dbl(e->a[0], env) + ", " + gen_dbl(e->a[1], env) + ")";
                 if ((e->name == "min" || e->name == "max") && e->a.size() == 2)
                     return "f" + e->name + "(" + gen_dbl(e->a[0], env) + ", " + gen_dbl(e->a[1], env) + ")";

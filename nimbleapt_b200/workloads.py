@@ -182,6 +182,48 @@ def demo_wrong(N=50, K=10, nTemps=7):
                 Temps=np.arange(1, nTemps + 1, dtype=float), ULT=1e6)
 
 
+# the demo's two user-supplied functions and its 'wrong' model, verbatim (demo/APT_demo.R:42-71, 83-92)
+K2THETA_R = """function(k = double(),              ## A categorical random variable in continuous form.
+                   K = double(),              ## Upper limit of k.
+                   randomEffects = double(1), ## A set of "randomEffects" which will be fixed during MCMC in order to generate poor mixing
+                   theta0=double()            ## An intercept term
+                   ) {
+        ## Uses a categorical rv to apply a shift in the value of a parameter theta
+        k <- ceiling(k)
+        if (k < 1 | k > K)
+            return(-Inf)
+        theta <- theta0 + randomEffects[k]
+        return(theta)
+        returnType(double())
+    }"""
+K2SIGMA_R = """function(k = double(), K = double(), randomEffects = double(1), sigma0=double()) {
+        ## Uses a categorical rv to determine a change in a standard deviation parameter theta
+        k <- ceiling(k)
+        if (k < 1 | k > K)
+            return(-Inf)
+        sigma <- abs(sigma0 + randomEffects[k])
+        return(sigma)
+        returnType(double())
+    }"""
+WRONG_CODE_R = """{
+    k      ~ dcat(pk[1:K])
+    theta0 ~ dnorm(0, sd=1E6)
+    theta <- k2theta(k, K, rfx_theta[1:K], theta0)
+    sigma0 ~ dexp(1)
+    sigma <- abs(k2sigma(k, K, rfx_sigma[1:K], sigma0))
+    for (i in 1:N)
+        y[i] ~ dnorm(mean=theta, sd=sigma)
+}"""
+
+
+def demo_wrong_verbatim(N=50, K=10, nTemps=7):
+    """demo_wrong() with the demo's own text: `wrongCode` and the nimbleFunctions k2theta / k2sigma as the demo has them."""
+    spec = demo_wrong(N, K, nTemps)
+    spec["code"] = WRONG_CODE_R
+    spec["functions"] = dict(k2theta=K2THETA_R, k2sigma=K2SIGMA_R)
+    return spec
+
+
 def demo_wrong_k_posterior(spec):
     """Exact marginal posterior of k in demo_wrong(): theta0 has an (effectively) flat prior and integrates out
     analytically, sigma0 ~ dexp(1) is integrated on a grid."""
@@ -250,7 +292,8 @@ def multinomial_latent_posterior(spec):
 def build_engine(spec, nLadders=1, **kw):
     """A workload spec (one of the functions above) through the drop-in interface; returns the built APT object."""
     from . import api as nb
-    m = nb.nimbleModel(nb.nimbleCode(spec["code"]), constants=spec["constants"], data=spec["data"], inits=spec["inits"])
+    m = nb.nimbleModel(nb.nimbleCode(spec["code"]), constants=spec["constants"], data=spec["data"], inits=spec["inits"],
+                       functions=spec.get("functions"))
     conf = nb.configureMCMC(m, monitors=spec["monitors"], monitors2=spec.get("monitors2"))
     conf.removeSamplers()
     for s in spec["samplers"]:

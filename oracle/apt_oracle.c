@@ -45,7 +45,9 @@
 
 enum { OP_END = 0, OP_CONST, OP_LOOP, OP_LOAD0, OP_LOAD1, OP_LOAD2, OP_ADD, OP_SUB, OP_MUL, OP_DIV, OP_POW, OP_NEG,
        OP_EXP, OP_LOG, OP_ABS, OP_SQRT, OP_ILOGIT, OP_LOGIT, OP_PHI, OP_ICLOGLOG, OP_CLOGLOG, OP_LOG1P, OP_STEP,
-       OP_MIN, OP_MAX, OP_INPROD, OP_SUM, OP_LGAMMA };
+       OP_MIN, OP_MAX, OP_INPROD, OP_SUM, OP_LGAMMA,
+       /* bodies of user-supplied deterministic functions (demo/APT_demo.R:42-71) */
+       OP_CEIL, OP_FLOOR, OP_ROUND, OP_TRUNC, OP_LT, OP_GT, OP_LE, OP_GE, OP_EQ, OP_NE, OP_OR, OP_AND, OP_NOT, OP_SEL };
 enum { D_NORM = 0, D_UNIF, D_GAMMA, D_BETA, D_BINOM, D_POIS, D_MNORM_CHOL, D_EXP, D_CAT, D_MULTI };
 
 /* declaration record layout (ints) */
@@ -185,6 +187,20 @@ static double eval(orc_ctx* c, int pc) {
             case OP_LOG1P: st[sp - 1] = log1p(st[sp - 1]); break;
             case OP_LGAMMA: st[sp - 1] = lgamma(st[sp - 1]); break;
             case OP_STEP: st[sp - 1] = st[sp - 1] >= 0 ? 1.0 : 0.0; break;
+            case OP_CEIL: st[sp - 1] = ceil(st[sp - 1]); break;
+            case OP_FLOOR: st[sp - 1] = floor(st[sp - 1]); break;
+            case OP_ROUND: st[sp - 1] = nearbyint(st[sp - 1]); break;
+            case OP_TRUNC: st[sp - 1] = trunc(st[sp - 1]); break;
+            case OP_LT: st[sp - 2] = st[sp - 2] < st[sp - 1]; sp--; break;
+            case OP_GT: st[sp - 2] = st[sp - 2] > st[sp - 1]; sp--; break;
+            case OP_LE: st[sp - 2] = st[sp - 2] <= st[sp - 1]; sp--; break;
+            case OP_GE: st[sp - 2] = st[sp - 2] >= st[sp - 1]; sp--; break;
+            case OP_EQ: st[sp - 2] = st[sp - 2] == st[sp - 1]; sp--; break;
+            case OP_NE: st[sp - 2] = st[sp - 2] != st[sp - 1]; sp--; break;
+            case OP_OR: st[sp - 2] = (st[sp - 2] != 0.0) || (st[sp - 1] != 0.0); sp--; break;
+            case OP_AND: st[sp - 2] = (st[sp - 2] != 0.0) && (st[sp - 1] != 0.0); sp--; break;
+            case OP_NOT: st[sp - 1] = st[sp - 1] == 0.0; break;
+            case OP_SEL: st[sp - 3] = st[sp - 3] != 0.0 ? st[sp - 2] : st[sp - 1]; sp -= 2; break;  /* cond, then, else */
             case OP_INPROD: {
                 /* a = offset (in code[]) of two arg records (kind 1); other-dim indices were pushed A then B */
                 const int* A = &code[a];

@@ -20,7 +20,8 @@ import numpy as np
 
 OPS = dict(END=0, CONST=1, LOOP=2, LOAD0=3, LOAD1=4, LOAD2=5, ADD=6, SUB=7, MUL=8, DIV=9, POW=10, NEG=11,
            EXP=12, LOG=13, ABS=14, SQRT=15, ILOGIT=16, LOGIT=17, PHI=18, ICLOGLOG=19, CLOGLOG=20, LOG1P=21,
-           STEP=22, MIN=23, MAX=24, INPROD=25, SUM=26, LGAMMA=27)
+           STEP=22, MIN=23, MAX=24, INPROD=25, SUM=26, LGAMMA=27,
+           CEIL=28, FLOOR=29, ROUND=30, TRUNC=31, LT=32, GT=33, LE=34, GE=35, EQ=36, NE=37, OR=38, AND=39, NOT=40, SEL=41)
 DISTS = dict(dnorm=0, dunif=1, dgamma=2, dbeta=3, dbinom=4, dpois=5, dmnorm=6, dexp=7, dcat=8, dmulti=9)
 DISCRETE_DISTS = ("dcat", "dbinom", "dpois", "dmulti")  # model$isDiscrete(target), APT_functions.R:926
 DREC, MAXARGS, ARGREC = 80, 6, 8
@@ -30,6 +31,9 @@ FUNC1 = dict(exp="EXP", log="LOG", abs="ABS", sqrt="SQRT", ilogit="ILOGIT", expi
              phi="PHI", iprobit="PHI", icloglog="ICLOGLOG", cloglog="CLOGLOG", log1p="LOG1P", step="STEP",
              lgamma="LGAMMA", loggam="LGAMMA")
 INVLINK = dict(log="exp", logit="ilogit", probit="iprobit", cloglog="icloglog")
+# what the bodies of user-supplied deterministic functions add (demo/APT_demo.R:42-71)
+FUNC1.update(ceiling="CEIL", floor="FLOOR", round="ROUND", trunc="TRUNC", __not="NOT")
+FUNC2 = dict(__lt="LT", __gt="GT", __le="LE", __ge="GE", __eq="EQ", __ne="NE", __or="OR", __and="AND")
 
 
 # --------------------------------------------------------------------------- parsing
@@ -56,7 +60,14 @@ def _split_statements(text):
             header = text[i + m.end():j - 1]
             while text[j] in " \t\r\n":
                 j += 1
-            assert text[j] == "{", "for(...) must be followed by {"
+            if text[j] != "{":  # a body of one statement (demo/APT_demo.R:90-91): up to the end of that statement
+                k, depth = j, 0
+                while k < n and not (text[k] in "\n;" and depth == 0 and not re.search(r"(<-|~|[-+*/^,])\s*$", text[j:k])):
+                    depth += {"(": 1, "[": 1, ")": -1, "]": -1}.get(text[k], 0)
+                    k += 1
+                yield ("for", header, text[j:k])
+                i = k
+                continue
             k = j + 1
             depth = 1
             while depth:
@@ -91,12 +102,25 @@ def _to_tree(node):
     if isinstance(node, ast.Constant):
         return ("num", float(node.value))
     if isinstance(node, ast.Name):
+        if node.id == "Inf":
+            return ("num", float("inf"))
         return ("var", node.id, [])
     if isinstance(node, ast.UnaryOp):
         if isinstance(node.op, ast.USub):
             return ("neg", _to_tree(node.operand))
         if isinstance(node.op, ast.UAdd):
             return _to_tree(node.operand)
+        if isinstance(node.op, ast.Not):
+            return ("call", "__not", [_to_tree(node.operand)], {})
+    if isinstance(node, ast.BoolOp):
+        f = "__or" if isinstance(node.op, ast.Or) else "__and"
+        t = _to_tree(node.values[0])
+        for v in node.values[1:]:
+            t = ("call", f, [t, _to_tree(v)], {})
+        return t
+    if isinstance(node, ast.Compare) and len(node.ops) == 1:
+        f = {ast.Lt: "__lt", ast.Gt: "__gt", ast.LtE: "__le", ast.GtE: "__ge", ast.Eq: "__eq", ast.NotEq: "__ne"}[type(node.ops[0])]
+        return ("call", f, [_to_tree(node.left), _to_tree(node.comparators[0])], {})
     if isinstance(node, ast.BinOp):
         op = {ast.Add: "+", ast.Sub: "-", ast.Mult: "*", ast.Div: "/", ast.Pow: "^"}[type(node.op)]
         return ("bin", op, _to_tree(node.left), _to_tree(node.right))
@@ -121,6 +145,10 @@ def _parse_expr(s):
     s = s.strip().replace("^", "**")
     s = re.sub(r"\bTRUE\b", "1", s)
     s = re.sub(r"\bFALSE\b", "0", s)
+    # R's logical operators bind looser than comparisons (Python's | and & bind tighter): spell them as or / and / not
+    s = re.sub(r"\|\|?", " or ", s)
+    s = re.sub(r"&&?", " and ", s)
+    s = re.sub(r"!(?!=)", " not ", s)
     s = re.sub(r"\bin\b", " in_ ", s) if False else s
     return _to_tree(ast.parse(s, mode="eval"))
 
@@ -166,6 +194,173 @@ def parse_bugs(code):
     return decls
 
 
+# --------------------------------------------------------------------------- user-supplied deterministic functions
+def _balanced(text, i, open_, close):
+    """index just behind the bracket that closes text[i] == open_."""
+    depth, j = 0, i
+    while True:
+        depth += {open_: 1, close: -1}.get(text[j], 0)
+        j += 1
+        if depth == 0:
+            return j
+
+
+def _fn_block(text, i):
+    """statements of the block (or single statement) that starts at text[i:]; returns (list, index behind it)."""
+    while text[i] in " \t\r\n;":
+        i += 1
+    if text[i] == "{":
+        j = _balanced(text, i, "{", "}")
+        return _fn_statements(text[i + 1:j - 1]), j
+    st, j = _fn_one(text, i)
+    return ([st] if st else []), j
+
+
+def _fn_one(text, i):
+    n = len(text)
+    m = re.match(r"if\s*\(", text[i:])
+    if m:
+        j = _balanced(text, i + m.end() - 1, "(", ")")
+        cond = _parse_expr(text[i + m.end():j - 1])
+        then, j = _fn_block(text, j)
+        k = j
+        while k < n and text[k] in " \t\r\n":
+            k += 1
+        els = []
+        if text[k:k + 4] == "else" and not (text[k + 4:k + 5].isalnum() or text[k + 4:k + 5] == "_"):
+            els, j = _fn_block(text, k + 4)
+        return ("if", cond, then, els), j
+    j, depth = i, 0
+    while j < n and not (text[j] in "\n;" and depth == 0):
+        depth += {"(": 1, "[": 1, ")": -1, "]": -1}.get(text[j], 0)
+        j += 1
+    st = text[i:j].strip()
+    if not st or st.startswith("returnType"):
+        return None, j
+    m = re.match(r"return\s*\((.*)\)$", st, re.S)
+    if m:
+        return ("return", _parse_expr(m.group(1))), j
+    m = re.match(r"(\w+)\s*(<-|=)(?!=)(.*)$", st, re.S)
+    assert m, "unsupported statement in a user-supplied function: " + st
+    return ("assign", m.group(1), _parse_expr(m.group(3))), j
+
+
+def _fn_statements(text):
+    out, i, n = [], 0, len(text)
+    while True:
+        while i < n and text[i] in " \t\r\n;":
+            i += 1
+        if i >= n:
+            return out
+        st, i = _fn_one(text, i)
+        if st:
+            out.append(st)
+
+
+class UserFunction:
+    """nimbleFunction(run = function(a = double(), v = double(1), ...) {...}) as a tree transformer: call(args) executes
+    the body symbolically on the argument trees and returns ONE expression tree (conditionals become ("call", "__if", ..))."""
+
+    def __init__(self, name, src):
+        src = re.sub(r"#[^\n]*", "", src)
+        i = src.index("function")
+        i = src.index("(", i)
+        j = _balanced(src, i, "(", ")")
+        self.name, self.params = name, []
+        depth, cur = 0, ""
+        for ch in src[i + 1:j - 1] + ",":
+            depth += {"(": 1, ")": -1}.get(ch, 0)
+            if ch == "," and depth == 0:
+                if cur.strip():
+                    self.params.append(cur.split("=")[0].strip())
+                cur = ""
+            else:
+                cur += ch
+        k = src.index("{", j)
+        self.body = _fn_statements(src[k + 1:_balanced(src, k, "{", "}") - 1])
+
+    @staticmethod
+    def _index(arg, idx):
+        assert arg[0] == "var", "vector argument must be a variable or a slice of one"
+        if not arg[2]:
+            return ("var", arg[1], [idx])
+        out, nr = [], 0
+        for i in arg[2]:
+            if i[0] == "range":
+                nr += 1
+                out.append(idx if i[1] == ("num", 1.0) else ("bin", "-", ("bin", "+", i[1], idx), ("num", 1.0)))
+            else:
+                out.append(i)
+        assert nr == 1
+        return ("var", arg[1], out)
+
+    def _subst(self, t, env):
+        k = t[0]
+        if k == "var":
+            if t[1] in env:
+                if not t[2]:
+                    return env[t[1]]
+                assert len(t[2]) == 1 and t[2][0][0] != "range"
+                return self._index(env[t[1]], self._subst(t[2][0], env))
+            return ("var", t[1], [("range", self._subst(i[1], env), self._subst(i[2], env)) if i[0] == "range" else self._subst(i, env) for i in t[2]])
+        if k == "neg":
+            return ("neg", self._subst(t[1], env))
+        if k == "bin":
+            return ("bin", t[1], self._subst(t[2], env), self._subst(t[3], env))
+        if k == "call":
+            return ("call", t[1], [self._subst(a, env) for a in t[2]], {kk: self._subst(v, env) for kk, v in t[3].items()})
+        return t
+
+    def _exec(self, st, env):
+        for i, s in enumerate(st):
+            if s[0] == "assign":
+                env[s[1]] = self._subst(s[2], env)
+            elif s[0] == "return":
+                return self._subst(s[1], env)
+            else:
+                c = self._subst(s[1], env)
+                ea, eb = dict(env), dict(env)
+                ra, rb = self._exec(s[2], ea), self._exec(s[3], eb)
+                if ra is not None and rb is not None:
+                    return ("call", "__if", [c, ra, rb], {})
+                if ra is not None:
+                    return ("call", "__if", [c, ra, self._exec(st[i + 1:], eb)], {})
+                if rb is not None:
+                    return ("call", "__if", [c, self._exec(st[i + 1:], ea), rb], {})
+                for name in set(ea) | set(eb):
+                    va, vb = ea.get(name), eb.get(name)
+                    env[name] = va if vb is None or va == vb else vb if va is None else ("call", "__if", [c, va, vb], {})
+        return None
+
+    def call(self, args, kw):
+        vals = list(args) + [None] * (len(self.params) - len(args))
+        for k, v in kw.items():
+            vals[self.params.index(k)] = v
+        assert all(v is not None for v in vals), "missing argument of " + self.name
+        r = self._exec(self.body, dict(zip(self.params, vals)))
+        assert r is not None, self.name + "() does not return a value"
+        return r
+
+
+def expand_user_calls(t, fns, depth=0):
+    assert depth < 16, "user-supplied functions nest too deeply"
+    k = t[0]
+    if k == "var":
+        return ("var", t[1], [("range", expand_user_calls(i[1], fns, depth), expand_user_calls(i[2], fns, depth)) if i[0] == "range"
+                              else expand_user_calls(i, fns, depth) for i in t[2]])
+    if k == "neg":
+        return ("neg", expand_user_calls(t[1], fns, depth))
+    if k == "bin":
+        return ("bin", t[1], expand_user_calls(t[2], fns, depth), expand_user_calls(t[3], fns, depth))
+    if k == "call":
+        args = [expand_user_calls(a, fns, depth) for a in t[2]]
+        kw = {kk: expand_user_calls(v, fns, depth) for kk, v in t[3].items()}
+        if t[1] in fns:
+            return expand_user_calls(fns[t[1]].call(args, kw), fns, depth + 1)
+        return ("call", t[1], args, kw)
+    return t
+
+
 # --------------------------------------------------------------------------- model
 class Var:
     def __init__(self, name, role, dims):
@@ -184,11 +379,15 @@ class Var:
 class OracleModel:
     """Concrete model: variables, canonical declarations in topological order, bytecode."""
 
-    def __init__(self, code, constants=None, data=None, inits=None):
+    def __init__(self, code, constants=None, data=None, inits=None, functions=None):
         self.constants = {k: np.asarray(v, dtype=float) for k, v in (constants or {}).items()}
         self.data = {k: np.asarray(v, dtype=float) for k, v in (data or {}).items()}
         self.inits = {k: np.asarray(v, dtype=float) for k, v in (inits or {}).items()}
         self.decls = parse_bugs(code)
+        if functions:
+            fns = {k: UserFunction(k, v) for k, v in functions.items()}
+            for d in self.decls:
+                d.rhs = expand_user_calls(d.rhs, fns)
         self.code, self.consts = [], []
         self._canonicalise()
         self._build_vars()
@@ -461,6 +660,12 @@ class OracleModel:
             f = t[1]
             if f in FUNC1:
                 self._compile_expr(t[2][0], loopnames, subst); self._emit(FUNC1[f])
+            elif f in FUNC2:
+                self._compile_expr(t[2][0], loopnames, subst); self._compile_expr(t[2][1], loopnames, subst); self._emit(FUNC2[f])
+            elif f == "__if":  # evaluated eagerly on both sides (indices from sampled nodes are clamped), then selected
+                for a in t[2]:
+                    self._compile_expr(a, loopnames, subst)
+                self._emit("SEL")
             elif f in ("pow",):
                 self._compile_expr(t[2][0], loopnames, subst); self._compile_expr(t[2][1], loopnames, subst); self._emit("POW")
             elif f in ("min", "max"):

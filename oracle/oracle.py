@@ -107,9 +107,9 @@ class OracleAPT:
     """CPU oracle with the shape of the reference's buildAPT object (APT_functions.R:242-639)."""
 
     def __init__(self, code, constants=None, data=None, inits=None, samplers=(), monitors=(), monitors2=(),
-                 Temps=(1.0,), ULT=1e6, monitorTmax=True, nLadders=1, seed=11, ladder0=0):
+                 Temps=(1.0,), ULT=1e6, monitorTmax=True, nLadders=1, seed=11, ladder0=0, functions=None):
         L = lib()
-        self.om = om = OracleModel(code, constants, data, inits)
+        self.om = om = OracleModel(code, constants, data, inits, functions)
         self.K = len(Temps)
         self.nLadders = nLadders
         specs = []

@@ -11,7 +11,7 @@ from oracle.oracle import OracleAPT
 
 def build_oracle(spec, nLadders=1, seed=11, ladder0=0):
     return OracleAPT(spec["code"], spec["constants"], spec["data"], spec["inits"], spec["samplers"], spec["monitors"],
-                     spec.get("monitors2", ()), spec["Temps"], spec["ULT"], True, nLadders, seed, ladder0)
+                     spec.get("monitors2", ()), spec["Temps"], spec["ULT"], True, nLadders, seed, ladder0, functions=spec.get("functions"))
 
 
 def make_tables(niter, L, K, NU, DMAX, seed=1):

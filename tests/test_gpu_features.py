@@ -221,7 +221,7 @@ def test_posterior_matches_oracle_within_4_mcse_c1():
 def test_posterior_demo_model_slice_sampler_within_4_mcse():
     """The reference's demo model (demo/APT_demo.R): the discrete node k is sampled by sampler_slice_tempered; its
     exact marginal posterior is known (tests/models.py).  64 independent ladders give the Monte-Carlo error."""
-    spec = models.demo_wrong()
+    spec = models.demo_wrong_verbatim()
     exact = models.demo_wrong_k_posterior(spec)
     L, niter, burn = 64, 6000, 1000
     eng = build_engine(spec, nLadders=L)

@@ -30,7 +30,7 @@ SMALL = {
     "c4cluster": lambda: models.c4_glmm(G=20, per=10, K=4),
     # the reference's demo model (demo/APT_demo.R:83-92,173-177): dcat + dexp, a discrete node sampled by
     # sampler_slice_tempered, elements of constant arrays selected by that node, scalar + block RW samplers
-    "demo": lambda: models.demo_wrong(),
+    "demo": lambda: models.demo_wrong_verbatim(),  # the demo's own text: wrongCode + the nimbleFunctions k2theta / k2sigma
     # sampler_RW_multinomial_tempered (APT:1005-1145) on a latent dmulti node + a log-scale scalar sampler
     "multinom": lambda: models.multinomial_latent(),
     "mixed": lambda: models.mixed_dists(),  # dbinom(size>1) dpois dgamma dbeta dexp dunif dnorm(tau) + all sampler options

@@ -106,6 +106,8 @@ class R:
 def _configure(r, spec):
     """What buildAPT in aptb200.R does before aptR_build."""
     m = r.call("aptR_model_create", r.str(spec["code"]))
+    for name, src in (spec.get("functions") or {}).items():
+        r.call("aptR_model_add_function", m, r.str(name), r.str(src))
     for role, d in ((0, spec["constants"]), (1, spec["data"]), (2, spec["inits"])):
         for name, arr in d.items():
             r.call("aptR_model_set_array", m, r.str(name), r.int(role), r.num(arr))
@@ -136,6 +138,10 @@ def test_bridge_marshals_model_and_errors_without_a_gpu():
         r.call("aptR_model_names", m1, r.int(1))
     m2 = _configure(r, models.multinomial_latent())  # useTempering reaches the library through the control list
     assert r.string(r.call("aptR_model_names", m2, r.int(1))).split("\n") == ["x[1]", "x[2]", "x[3]", "x[4]", "a"]
+    m3 = _configure(r, models.demo_wrong_verbatim())  # the demo's nimbleFunctions travel as text (aptR_model_add_function)
+    assert r.string(r.call("aptR_model_names", m3, r.int(1))).split("\n") == ["k", "theta0", "sigma0"]
+    with pytest.raises(RuntimeError, match="expected 'function'"):
+        r.call("aptR_model_add_function", m3, r.str("f"), r.str("42"))
     r.L.stub_reset()  # finalizers free both models
 
 
