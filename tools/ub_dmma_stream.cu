@@ -19,13 +19,21 @@ __device__ __forceinline__ void cpa16(void* smem, const void* gmem) {
 }
 __device__ __forceinline__ void cpa_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cpa_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void mbar_init(uint64_t* b, unsigned n) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(b)), "r"(n) : "memory"); }
+__device__ __forceinline__ void mbar_expect(uint64_t* b, unsigned bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(b)), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* b) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* b, unsigned parity) {
+    asm volatile("{\n.reg .pred p;\nWAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}" ::"r"((unsigned)__cvta_generic_to_shared(b)), "r"(parity) : "memory");
+}
 __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
 // BREG: B fragments (26 doubles) live in registers for the whole kernel; else re-read from shared memory per block.
 // DEPTH: blocks in flight (ring slots = DEPTH + 1).  MODE 0: dot only, 2: dot + Bernoulli-logit terms.
-template <int THREADS, int MINB, bool BREG, int DEPTH, int MODE, int UNR = 1>
+template <int THREADS, int MINB, bool BREG, int DEPTH, int MODE, int UNR = 1, bool BULK = false>
 __global__ void __launch_bounds__(THREADS, MINB) pass_kernel(const double* __restrict__ X, const double* __restrict__ y, const double* __restrict__ th, long n, double* partial) {
     constexpr int NW = THREADS / 32, SLOTS = DEPTH + 1, BLK = KB * XS;
     extern __shared__ __align__(16) double sm[];
@@ -40,7 +48,22 @@ __global__ void __launch_bounds__(THREADS, MINB) pass_kernel(const double* __res
     // B fragment of block b, n-tile t: B[k = lane % 4][col = lane / 4]; column col of n-tile t is position (col/2)*4 + t*2 + col%2
     const int kq = lane & 3, rq = lane >> 2;
     const int bpos0 = (rq >> 1) * 4 + (rq & 1);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(xbuf + NW * SLOTS * BLK) + warp * SLOTS;
+    if (BULK) {
+        if (lane == 0) for (int i = 0; i < SLOTS; i++) mbar_init(&bars[i], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        __syncwarp();
+    }
+    unsigned phases = 0;  // parity of each slot's barrier
     auto issue = [&](long tile, int b, int slot) {
+        if (BULK) {
+            if (lane == 0) {
+                const int nc = (b * KB + KB <= P) ? KB : P - b * KB;
+                mbar_expect(&bars[slot], (unsigned)nc * 256u);
+                for (int col = 0; col < nc; col++) bulk_g2s(&xw[slot * BLK + col * XS], X + tile * 32 + (long)(b * KB + col) * n, 256u, &bars[slot]);
+            }
+            return;
+        }
         // block b = columns 4b .. 4b+3 of rows tile*32 .. +31: 4 x 16 chunks of 16 bytes, 2 per lane
         const double* src = X + tile * 32;
 #pragma unroll
@@ -51,7 +74,7 @@ __global__ void __launch_bounds__(THREADS, MINB) pass_kernel(const double* __res
     };
     if (wt < ntile) {
 #pragma unroll
-        for (int b = 0; b < DEPTH; b++) { issue(wt, b, b); cpa_commit(); }
+        for (int b = 0; b < DEPTH; b++) { issue(wt, b, b); if (!BULK) cpa_commit(); }
     }
     __syncthreads();
     double breg[BREG ? NBR : 1][2];
@@ -70,14 +93,15 @@ __global__ void __launch_bounds__(THREADS, MINB) pass_kernel(const double* __res
         const long nxt = wt + wstep;
 #pragma unroll (BREG ? NBR : UNR)
         for (int b = 0; b < NBR; b++) {
-            cpa_wait<DEPTH - 1>();
+            if (BULK) { mbar_wait(&bars[ring], (phases >> ring) & 1u); phases ^= 1u << ring; }
+            else cpa_wait<DEPTH - 1>();
             __syncwarp();
             {
                 const int nb = b + DEPTH;
                 int slot = ring + DEPTH; if (slot >= SLOTS) slot -= SLOTS;
                 if (nb < NBR) issue(wt, nb, slot);
                 else if (nxt < ntile) issue(nxt, nb - NBR, slot);
-                cpa_commit();
+                if (!BULK) cpa_commit();
             }
             double b0, b1;
             if (BREG) { b0 = breg[b][0]; b1 = breg[b][1]; }
@@ -107,7 +131,7 @@ __global__ void __launch_bounds__(THREADS, MINB) pass_kernel(const double* __res
             for (int i = 0; i < 4; i++) { acc[0] += c[i][0][0]; acc[1] += c[i][0][1]; acc[2] += c[i][1][0]; acc[3] += c[i][1][1]; }
         }
     }
-    cpa_wait<0>();
+    if (!BULK) cpa_wait<0>();
 #pragma unroll
     for (int cc = 0; cc < 4; cc++) {
         double v = acc[cc];
@@ -140,12 +164,12 @@ __global__ void ref_kernel(const double* __restrict__ X, const double* __restric
     }
 }
 
-template <int THREADS, int MINB, bool BREG, int DEPTH, int MODE, int UNR = 1>
+template <int THREADS, int MINB, bool BREG, int DEPTH, int MODE, int UNR = 1, bool BULK = false>
 void run(const char* name, const double* X, const double* y, const double* th, long n, double* partial, const double* ref) {
     const int grid = 148 * MINB;
     constexpr int NW = THREADS / 32;
-    size_t smem = (size_t)(NBR * KB * TB + NW * TB + NW * (DEPTH + 1) * KB * XS) * 8;
-    auto fn = pass_kernel<THREADS, MINB, BREG, DEPTH, MODE, UNR>;
+    size_t smem = (size_t)(NBR * KB * TB + NW * TB + NW * (DEPTH + 1) * KB * XS + NW * (DEPTH + 1)) * 8;
+    auto fn = pass_kernel<THREADS, MINB, BREG, DEPTH, MODE, UNR, BULK>;
     cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int occ = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, THREADS, smem);
     cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, fn);
@@ -196,5 +220,10 @@ int main() {
     run<128, 4, true, 3, 2>("both breg d3 4x128", X, y, th, n, partial, ref[1]);
     run<256, 2, false, 3, 2, 13>("both blds d3 unr13", X, y, th, n, partial, ref[1]);
     run<256, 2, false, 3, 2, 2>("both blds d3 unr2", X, y, th, n, partial, ref[1]);
+    run<256, 2, false, 6, 2, 13>("both blds d6 unr13", X, y, th, n, partial, ref[1]);
+    run<256, 2, false, 3, 2, 13, true>("both blds d3 unr13 BULK", X, y, th, n, partial, ref[1]);
+    run<256, 2, false, 6, 2, 13, true>("both blds d6 unr13 BULK", X, y, th, n, partial, ref[1]);
+    run<256, 2, false, 6, 0, 13, true>("dot blds d6 unr13 BULK", X, y, th, n, partial, ref[0]);
+    run<256, 2, false, 6, 0, 13>("dot blds d6 unr13", X, y, th, n, partial, ref[0]);
     return 0;
 }
