@@ -49,6 +49,32 @@ static std::string slurp(const std::string& path) {
     return o.str();
 }
 
+// single-quoted for the shell: paths with spaces or metacharacters neither break nor inject
+static std::string shq(const std::string& s) {
+    std::string o = "'";
+    for (char c : s) {
+        if (c == '\'') o += "'\\''";
+        else o += c;
+    }
+    return o + "'";
+}
+
+// `nvcc --version`, recorded in the module's build log (the cache key stays the hash of source + headers + flags, so that a
+// module cross-compiled on a machine without a GPU and shipped is found); asked once per process
+static const std::string& nvcc_version(const std::string& nvcc) {
+    static std::string v;
+    static bool done = false;
+    if (!done) {
+        done = true;
+        if (FILE* p = popen((shq(nvcc) + " --version 2>/dev/null").c_str(), "r")) {
+            char buf[256];
+            while (fgets(buf, sizeof buf, p)) v += buf;
+            pclose(p);
+        }
+    }
+    return v;
+}
+
 std::string jit_compile(const std::string& source, bool verbose) {
     const std::string inc = engine_include_dir();
     const std::string nvcc = getenv("APTB200_NVCC") ? getenv("APTB200_NVCC") : "/usr/local/cuda/bin/nvcc";
@@ -68,23 +94,32 @@ std::string jit_compile(const std::string& source, bool verbose) {
     const std::string so = base + ".so", cu = base + ".cu", log = base + ".log";
     struct stat st;
     if (stat(so.c_str(), &st) == 0 && st.st_size > 0) return so;
+    if (access(nvcc.c_str(), X_OK) != 0) throw Error("nvcc not found at " + nvcc + " (set APTB200_NVCC); the model cannot be compiled");
+    // Several processes may build the same model at once (8 ranks calling buildAPT): everything is written under names unique
+    // to this process and renamed into place, so nobody ever reads a half-written source, log or module.
+    const std::string uniq = ".tmp." + std::to_string((long)getpid());
+    const std::string cu_tmp = base + uniq + ".cu", log_tmp = base + uniq + ".log", so_tmp = base + uniq + ".so";
     {
-        std::ofstream f(cu);
-        if (!f) throw Error("cannot write " + cu);
+        std::ofstream f(cu_tmp);
+        if (!f) throw Error("cannot write " + cu_tmp);
         f << source;
     }
-    if (access(nvcc.c_str(), X_OK) != 0) throw Error("nvcc not found at " + nvcc + " (set APTB200_NVCC); the model cannot be compiled");
-    const std::string tmp = base + ".tmp." + std::to_string((long)getpid()) + ".so";
-    const std::string cmd = nvcc + " " + flags + " -I" + inc + " " + cu + " -o " + tmp + " > " + log + " 2>&1";
+    const std::string cmd = shq(nvcc) + " " + flags + " -I" + shq(inc) + " " + shq(cu_tmp) + " -o " + shq(so_tmp) + " > " + shq(log_tmp) + " 2>&1";
     if (verbose) fprintf(stderr, "[aptb200] %s\n", cmd.c_str());
     int rc = system(cmd.c_str());
+    rename(cu_tmp.c_str(), cu.c_str());
+    {
+        std::ofstream f(log_tmp, std::ios::app);
+        f << "\n# " << cmd << "\n# " << nvcc_version(nvcc);
+    }
+    rename(log_tmp.c_str(), log.c_str());
     if (rc != 0) {
         std::string l = slurp(log);
         if (l.size() > 4000) l = l.substr(0, 4000) + "\n...";
-        unlink(tmp.c_str());
+        unlink(so_tmp.c_str());
         throw Error("nvcc failed for the lowered model (source kept at " + cu + "):\n" + l);
     }
-    if (rename(tmp.c_str(), so.c_str()) != 0) throw Error("cannot move the compiled module into the cache");
+    if (rename(so_tmp.c_str(), so.c_str()) != 0) throw Error("cannot move the compiled module into the cache");
     return so;
 }
 

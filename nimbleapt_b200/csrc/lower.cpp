@@ -2217,7 +2217,7 @@ struct Lowerer {
             out << "  static constexpr int LADDER_MINB = " << minb << ";\n";
         }
         out << "  static constexpr bool STATE_IN_SMEM = " << (smem_state && engine == 1 ? "true" : "false") << ", HAS_FAMILY = " << (has_family ? "true" : "false") << ";\n";
-        out << "  static constexpr int ENGINE = " << engine << ", TB = " << TB << ", R = " << R << ", GRID_THREADS = 256, RING_SLOTS = " << ring_slots << ", FRAG_DOUBLES = " << frag_doubles << ", CSPLIT = " << csplit << ", GRID_MINB = " << (getenv("APTB200_GRID_MINB") ? std::max(1, atoi(getenv("APTB200_GRID_MINB"))) : (csplit == 2 ? 3 : 2)) << ", NSTAGE = " << units.size() << ";\n";
+        out << "  static constexpr int ENGINE = " << engine << ", TB = " << TB << ", R = " << R << ", GRID_THREADS = " << (getenv("APTB200_GRID_THREADS") ? atoi(getenv("APTB200_GRID_THREADS")) : 256) << ", RING_SLOTS = " << ring_slots << ", FRAG_DOUBLES = " << frag_doubles << ", CSPLIT = " << csplit << ", GRID_MINB = " << (getenv("APTB200_GRID_MINB") ? std::max(1, atoi(getenv("APTB200_GRID_MINB"))) : (csplit == 2 ? 3 : 2)) << ", NSTAGE = " << units.size() << ";\n";
         // derived arrays (data-only terms, filled by derived_kernel when data is uploaded)
         out << "  static constexpr int NDER = " << derived.size() << ";\n";
         out << "  static long der_inst(int k) { return ";
