@@ -87,7 +87,9 @@ __device__ __forceinline__ double dbinom_raw_log(double x, double n, double p, d
 
 __device__ __forceinline__ bool nonint(double x) { return fabs(x - nearbyint(x)) > 1e-7 * fmax(1.0, fabs(x)); }
 
-__device__ __forceinline__ double dnorm_log(double x, double mu, double sigma) {
+// dnorm4(x, mu, sigma, log = TRUE) with all of Rmath's special cases; out of line: the callers below take it only when the
+// standardised value is not an ordinary number (the checks were 8 % of the small-model kernel's instructions)
+__device__ __noinline__ double dnorm_log_slow(double x, double mu, double sigma) {
     if (isnan(x) || isnan(mu) || isnan(sigma)) return x + mu + sigma;
     if (!isfinite(sigma)) return APT_NEG_INF;
     if (!isfinite(x) && mu == x) return CUDART_NAN;
@@ -101,10 +103,19 @@ __device__ __forceinline__ double dnorm_log(double x, double mu, double sigma) {
     if (x >= 2.6815615859885194e154) return APT_NEG_INF;  // 2*sqrt(DBL_MAX)
     return -(APT_LN_SQRT_2PI + 0.5 * x * x + apt_log_pos(sigma));
 }
+// One test on the high word of z = (x - mu) / sigma covers every special case of the function above: NaN or Inf in any
+// argument, sigma == 0 (z is Inf or NaN), |z| >= 2^510 (the -Inf cut-off lies above).  sigma < 0 or denormal is caught on
+// sigma's own high word.  On the ordinary path the arithmetic is that of dnorm4, operation for operation.
+__device__ __forceinline__ double dnorm_log(double x, double mu, double sigma) {
+    const double z = (x - mu) / sigma;
+    const unsigned hs = (unsigned)__double2hiint(sigma) - 0x00100000u;  // positive normal finite <=> hs < 0x7fe00000
+    if ((__double2hiint(z) & 0x7fffffff) >= 0x5fd00000 || hs >= 0x7fe00000u) return dnorm_log_slow(x, mu, sigma);
+    return -(APT_LN_SQRT_2PI + 0.5 * z * z + apt_log_pos(sigma));
+}
 
 // dnorm with a compile-time constant, positive, finite sd: log(sd) is supplied by the lowering as a literal
 // (the library log() is not constant-folded by nvcc and dominated the small-model kernel, profiles/)
-__device__ __forceinline__ double dnorm_log_csd(double x, double mu, double sigma, double log_sigma) {
+__device__ __noinline__ double dnorm_log_csd_slow(double x, double mu, double sigma, double log_sigma) {
     if (isnan(x) || isnan(mu)) return x + mu;
     if (!isfinite(x) && mu == x) return CUDART_NAN;
     x = (x - mu) / sigma;
@@ -112,6 +123,11 @@ __device__ __forceinline__ double dnorm_log_csd(double x, double mu, double sigm
     x = fabs(x);
     if (x >= 2.6815615859885194e154) return APT_NEG_INF;
     return -(APT_LN_SQRT_2PI + 0.5 * x * x + log_sigma);
+}
+__device__ __forceinline__ double dnorm_log_csd(double x, double mu, double sigma, double log_sigma) {
+    const double z = (x - mu) / sigma;
+    if ((__double2hiint(z) & 0x7fffffff) >= 0x5fd00000) return dnorm_log_csd_slow(x, mu, sigma, log_sigma);
+    return -(APT_LN_SQRT_2PI + 0.5 * z * z + log_sigma);
 }
 
 __device__ __forceinline__ double dunif_log(double x, double a, double b) {
