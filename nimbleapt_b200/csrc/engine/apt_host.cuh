@@ -163,7 +163,7 @@ struct Engine {
     DevBuf<double> theta, lpd, temps, lp, scale, blk, empir, famdelta, wpart, model_theta, scale0, blk0;
     bool blk_initialised = false;  // sampler$reset() leaves some entries alone (Model::blk_keep) once they exist
     DevBuf<int> slot, cnt, accswap;
-    DevBuf<double> g_partial, g_pend, g_scratch;  // grid engine
+    DevBuf<double> g_partial, g_pend, g_scratch, g_stage;  // grid engine
     DevBuf<unsigned int> g_ticket;
     DevBuf<long long> g_dbg, g_delta_tag;
     DevBuf<unsigned long long> g_flags;  // hand-over between pass kernels (apt_grid.cuh)
@@ -264,6 +264,7 @@ struct Engine {
             g_ticket.alloc(1); g_ticket.zero(stream);
             g_dbg.alloc(80); g_dbg.zero(stream);
             g_flags.alloc(2); g_flags.zero(stream);
+            g_stage.alloc((size_t)G::P * G::TB + G::FRAG_DOUBLES + 2); g_stage.zero(stream);
             g_delta.alloc(nch * 2 * G::DMAX); g_delta.zero(stream);
             g_delta_tag.alloc(nch * 2);
             APT_CUDA(cudaMemsetAsync(g_delta_tag.p, 0xff, nch * 2 * sizeof(long long), stream));
@@ -509,7 +510,7 @@ struct Engine {
                 g.dbg = getenv("APTB200_DEBUG_TIMING") ? g_dbg.p : nullptr;
                 g.delta = getenv("APTB200_NO_DELTA_CTA") ? nullptr : g_delta.p; g.delta_tag = g_delta_tag.p;
                 APT_CUDA(cudaEventRecord(ev0, stream));
-                g.flags = g_flags.p; g.seq0 = launch_seq;
+                g.flags = g_flags.p; g.seq0 = launch_seq; g.stage_img = g_stage.p;
                 const long long nl = (it1 - it0) * G::NSTAGE * npass;  // steps (passes over the data) of this launch
                 launch_seq += (unsigned long long)nl + 1;  // the proposals of the first step are published as seq0 + 1, step n as seq0 + n + 2
                 if (grid < 2) throw ApiError{"grid engine: the device must hold at least 2 resident CTAs (a control CTA and a streaming CTA)"};
@@ -527,6 +528,10 @@ struct Engine {
                 if (getenv("APTB200_DEBUG_TIMING")) {
                     auto v = d2h(g_dbg.p, 80);
                     fprintf(stderr, "[aptb200] control CTA cycles (last step of the launch): delta %lld | preload %lld | wait for the streaming CTAs %lld | reduce %lld | finish %lld | ladder (to the swaps) %lld | propose+publish %lld | deferred %lld\n", v[7], v[6] - v[5] - v[7], v[0] - v[6], v[1] - v[0], v[2] - v[1], v[3] - v[2], v[4] - v[3], v[15] - v[4]);
+                    {   // hand-over of the last step: its proposals were published by the step before (same parity slot)
+                        const int par = (int)((launch_seq - 1) & 1);  // seq of the last step = seq0 + nl = launch_seq - 1
+                        fprintf(stderr, "   hand-over (CTA 0, ns): published -> seen %lld | seen -> parameters staged %lld\n", v[22 + par] - v[20 + par], v[24 + par] - v[22 + par]);
+                    }
                     fprintf(stderr, "   ladder step: load %lld | lp+philox+log %lld | K^2 exp %lld | rowsum %lld | normalise+log %lld | chain %lld\n", v[8] - v[2], v[9] - v[8], v[10] - v[9], v[11] - v[10], v[12] - v[11], v[13] - v[12]);
                 }
             }
