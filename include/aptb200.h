@@ -197,7 +197,7 @@ void apt_build_opts_default(apt_build_opts* o);
 void apt_run_args_default(apt_run_args* a);
 
 /* ---- model + configuration (replaces nimbleCode/nimbleModel/configureMCMC for the supported BUGS subset:
- *      dnorm dunif dgamma dbeta dbinom dbern dpois dexp dcat dmulti dmnorm(cholesky=), deterministic links,
+ *      dnorm dunif dgamma dbeta dbinom dbern dpois dexp dcat dmulti dmnorm(cholesky= | prec= | cov= constant), deterministic links,
  *      elements of constant arrays selected by a sampled node, e.g. rfx[k]) */
 int apt_model_create(const char* bugs_code, apt_model** out);
 void apt_model_free(apt_model* m);

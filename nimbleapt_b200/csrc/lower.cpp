@@ -50,6 +50,7 @@ struct CDecl {
     std::vector<EP> mean_elems;    // dmnorm
     std::vector<EP> chol_elems;    // dmnorm, column-major n*n
     int mvn_n = 0;
+    bool mvn_factor = false;       // dmnorm(prec = / cov = constant matrix): chol_elems are computed at build time
     int lpidx = -1;
     bool lhs_param = false;
     long ninst = 1;
@@ -309,10 +310,18 @@ struct Lowerer {
                     d.args = {need(kwarg(c, "prob", 0), "prob"), need(kwarg(c, "size", 1), "size")};
                 } else if (dist == "dmnorm") {
                     d.dist = dist;
-                    if (!has_kw(c, "cholesky"))
-                        throw Error("line " + std::to_string(rd.line) + ": dmnorm is supported as dmnorm(mean, cholesky = , prec_param = )");
-                    d.args = {need(kwarg(c, "mean", 0), "mean"), kwarg(c, "cholesky", 99),
-                              has_kw(c, "prec_param") ? kwarg(c, "prec_param", 99) : one};
+                    if (has_kw(c, "cholesky")) {
+                        d.args = {need(kwarg(c, "mean", 0), "mean"), kwarg(c, "cholesky", 99),
+                                  has_kw(c, "prec_param") ? kwarg(c, "prec_param", 99) : one};
+                    } else {
+                        // dmnorm(mean, prec) / dmnorm(mean, prec = ) / dmnorm(mean, cov = ) with a CONSTANT matrix: nimble takes
+                        // chol() of it once and calls dmnorm_chol; so does the lowering (inline_all), at build time
+                        const bool cov = has_kw(c, "cov");
+                        EP m = cov ? kwarg(c, "cov", 99) : has_kw(c, "prec") ? kwarg(c, "prec", 99) : (c->a.size() > 1 ? c->a[1] : nullptr);
+                        if (!m) throw Error("line " + std::to_string(rd.line) + ": dmnorm needs cholesky = , prec = or cov =");
+                        d.args = {need(kwarg(c, "mean", 0), "mean"), m, cov ? mk_num(0) : one};
+                        d.mvn_factor = true;
+                    }
                 } else {
                     throw Error("line " + std::to_string(rd.line) + ": unsupported distribution '" + dist +
                                 "' (supported: dnorm dunif dgamma dbeta dbinom dbern dpois dexp dcat dmulti dmnorm)");
@@ -540,9 +549,9 @@ struct Lowerer {
             if (d.dist == "dmnorm") {
                 for (auto& el : vector_elements(d.args[0])) d.mean_elems.push_back(inline_det(el));
                 d.mvn_n = (int)d.mean_elems.size();
-                if (d.mvn_n < 1 || d.mvn_n > 8) throw Error("dmnorm dimension must be between 1 and 8");
+                if (d.mvn_n < 1 || d.mvn_n > 16) throw Error("dmnorm dimension must be between 1 and 16");
                 const EP& ch = d.args[1];
-                if (ch->k != Expr::VAR) throw Error("cholesky= must be a matrix variable");
+                if (ch->k != Expr::VAR) throw Error("cholesky= / prec= / cov= must be a matrix variable");
                 long r0 = 1, c0 = 1;
                 if (!ch->a.empty()) {
                     if (ch->a.size() != 2 || ch->a[0]->k != Expr::RANGE || ch->a[1]->k != Expr::RANGE)
@@ -554,6 +563,27 @@ struct Lowerer {
                     for (int i = 0; i < d.mvn_n; i++)
                         d.chol_elems.push_back(inline_det(mk_var(ch->name, {mk_num((double)(r0 + i)), mk_num((double)(c0 + j))})));
                 // reorder: chol_elems is filled column by column -> index i + j*n
+                if (d.mvn_factor) {
+                    // upper factor U of the constant matrix M (U'U = M, R's chol()), column-major like the elements above
+                    const int n = d.mvn_n;
+                    std::vector<double> M((size_t)n * n), U((size_t)n * n, 0.0);
+                    for (int e = 0; e < n * n; e++)
+                        if (!try_ceval(d.chol_elems[e], {}, M[e]))
+                            throw Error("dmnorm(prec = / cov = ) needs a constant matrix (pass cholesky = for one that depends on parameters): " + to_string(ch));
+                    for (int j = 0; j < n; j++) {
+                        double sjj = M[j + j * n];
+                        for (int k = 0; k < j; k++) sjj -= U[k + j * n] * U[k + j * n];
+                        if (!(sjj > 0.0)) throw Error("dmnorm: the matrix is not positive definite: " + to_string(ch));
+                        const double dj = std::sqrt(sjj);
+                        U[j + j * n] = dj;
+                        for (int i = j + 1; i < n; i++) {
+                            double t = M[j + i * n];
+                            for (int k = 0; k < j; k++) t -= U[k + j * n] * U[k + i * n];
+                            U[j + i * n] = t / dj;
+                        }
+                    }
+                    for (int e = 0; e < n * n; e++) d.chol_elems[e] = mk_num(U[e]);
+                }
                 d.iargs = {inline_det(d.args[2])};
                 int ln = 0;
                 for (auto& ix : d.lhs->a)

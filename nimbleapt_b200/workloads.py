@@ -27,6 +27,29 @@ def c1_vignette(nObs=100, K=8):
                 monitors=["centroids"], Temps=np.arange(1, K + 1, dtype=float), ULT=1000.0)
 
 
+def mvn_prior(n=12, nObs=15, K=6):
+    """A 12-dimensional parameter with a dmnorm(mean, prec = constant matrix) prior, observed through dmnorm(mean, cov = ) rows
+    (the parameterisations other than the vignette's cholesky = ; nimble takes chol() of a constant matrix once)."""
+    rng = np.random.default_rng(DATA_SEED + 41)
+    A = rng.standard_normal((n, n)) * 0.3
+    prec = A @ A.T + np.eye(n) * 0.5
+    B = rng.standard_normal((n, n)) * 0.2
+    cov = B @ B.T + np.eye(n)
+    truth = rng.standard_normal(n)
+    y = truth + rng.multivariate_normal(np.zeros(n), cov, size=nObs)
+    code = """{
+    mu[1:n] ~ dmnorm(mean = m0[1:n], prec = Q[1:n, 1:n])
+    for (i in 1:nObs) {
+        y[i, 1:n] ~ dmnorm(mu[1:n], cov = S[1:n, 1:n])
+    }
+    }"""
+    return dict(code=code, constants=dict(n=n, nObs=nObs, m0=np.zeros(n), Q=prec, S=cov), data=dict(y=y),
+                inits=dict(mu=np.zeros(n)),
+                samplers=[dict(target="mu[1:%d]" % n, type="sampler_RW_block_tempered", control=dict(temperPriors=True, scale=0.3)),
+                          dict(target="mu[1]", type="sampler_RW_tempered", control=dict(temperPriors=True))],
+                monitors=["mu"], Temps=np.exp(np.linspace(0.0, np.log(30.0), K)), ULT=1e6)
+
+
 def c2_mixture(n=20, K=32, tmax=1000.0):
     """2-D bimodal posterior through an abs() link; exact posterior is a 2-component Gaussian mixture."""
     rng = np.random.default_rng(DATA_SEED + 2)

@@ -469,8 +469,22 @@ class OracleModel:
                     cargs = [kw.get("prob", args[0] if args else None), kw.get("size", args[1] if len(args) > 1 else None)]
                 elif dist == "dmnorm":
                     mean = kw.get("mean", args[0] if args else None)
-                    assert "cholesky" in kw, "oracle front end supports dmnorm(mean, cholesky=, prec_param=) only"
-                    cargs = [mean, kw["cholesky"], kw.get("prec_param", one)]
+                    if "cholesky" in kw:
+                        cargs = [mean, kw["cholesky"], kw.get("prec_param", one)]
+                    else:
+                        # dmnorm(mean, prec) / prec = / cov = with a constant matrix: chol() once, like nimble; the factor becomes
+                        # a constant array of its own
+                        cov = "cov" in kw
+                        mt = kw["cov"] if cov else kw.get("prec", args[1] if len(args) > 1 else None)
+                        assert mt is not None and mt[0] == "var", "dmnorm needs cholesky=, prec= or cov= (a constant matrix)"
+                        M = np.asarray(self.constants[mt[1]], dtype=float)
+                        if mt[2]:
+                            r0, r1 = int(self.const_eval(mt[2][0][1])), int(self.const_eval(mt[2][0][2]))
+                            c0, c1 = int(self.const_eval(mt[2][1][1])), int(self.const_eval(mt[2][1][2]))
+                            M = M[r0 - 1:r1, c0 - 1:c1]
+                        name = "chol__%d" % len(out)
+                        self.constants[name] = np.linalg.cholesky(M).T.copy()  # upper factor, U'U = M
+                        cargs = [mean, ("var", name, []), ("num", 0.0) if cov else one]
                 else:
                     raise ValueError("unsupported distribution " + dist)
                 out.append(dict(loops=loops, lhs=lhs, stoch=True, dist=dist, args=cargs))

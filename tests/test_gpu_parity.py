@@ -30,6 +30,7 @@ SMALL = {
     "c4cluster": lambda: models.c4_glmm(G=20, per=10, K=4),
     # the reference's demo model (demo/APT_demo.R:83-92,173-177): dcat + dexp, a discrete node sampled by
     # sampler_slice_tempered, elements of constant arrays selected by that node, scalar + block RW samplers
+    "mvn": lambda: models.mvn_prior(),  # dmnorm(mean, prec = ) and dmnorm(mean, cov = ) with constant matrices, n = 12
     "demo": lambda: models.demo_wrong_verbatim(),  # the demo's own text: wrongCode + the nimbleFunctions k2theta / k2sigma
     # sampler_RW_multinomial_tempered (APT:1005-1145) on a latent dmulti node + a log-scale scalar sampler
     "multinom": lambda: models.multinomial_latent(),

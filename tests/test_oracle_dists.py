@@ -159,3 +159,22 @@ def test_dmulti_and_rbinom_inversion():
             near_edge = (np.abs(u - cdf_lo) < 1e-9) | (np.abs(u - cdf_hi) < 1e-9)
             assert np.all((got == ref) | near_edge), (n, pr)
     assert L.apt_rbinom_inv(0.0, 0.3, 0.5) == 0.0 and L.apt_rbinom_inv(9.0, 1.0, 0.5) == 9.0 and L.apt_rbinom_inv(9.0, 0.0, 0.5) == 0.0
+
+
+def test_dmnorm_prec_and_cov_forms_against_scipy():
+    """dmnorm(mean, prec = ) / dmnorm(mean, cov = ) with constant matrices (the factor is taken once, like nimble does), n = 12:
+    the oracle's whole-model log-probability against scipy.stats.multivariate_normal, and the lowering accepts the model."""
+    from scipy.stats import multivariate_normal as mvn
+    import models
+    from helpers import build_engine, build_oracle
+    spec = models.mvn_prior()
+    orc = build_oracle(spec)
+    c = spec["constants"]
+    rng = np.random.default_rng(5)
+    for _ in range(3):
+        mu = rng.standard_normal(c["n"])
+        want = mvn.logpdf(mu, c["m0"], np.linalg.inv(c["Q"])) + mvn.logpdf(spec["data"]["y"], mu, c["S"]).sum()
+        got = orc.logprob(mu)[0]
+        assert abs(got - want) <= 1e-11 * abs(want)
+    src = build_engine(spec, compileOnly=True).lowered_source()
+    assert "apt::dmnorm_chol_log<12>" in src
