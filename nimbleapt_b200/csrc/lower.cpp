@@ -2205,6 +2205,7 @@ struct Lowerer {
         std::swap(out, body);  // `body` now holds the model body; `out` is the file
 
         out << "// Generated by the aptb200 lowering step (nimbleapt_b200/csrc/lower.cpp). Do not edit.\n";
+        if (engine == 2) out << "#define APT_SP_EXP_POLY 1  // see apt_softplus.cuh::apt_softplus_neg_batch\n";
         out << "#include \"apt_grid.cuh\"\n#include \"apt_host.cuh\"\n";
         out << "__device__ __forceinline__ double apt_sq(double x) { return x * x; }\n";
         out << "// unnamed namespace: every lowered model defines a type called aptgen::Model; internal linkage keeps the\n// template instantiations of different modules loaded into one process apart.\nnamespace {\nnamespace aptgen {\nusing apt::Data;\n";
