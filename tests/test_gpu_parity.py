@@ -89,3 +89,18 @@ def test_decisions_bit_identical(name, inject):
             bs = eng.blockState(l)
             for k in range(eng.nTemps):
                 np.testing.assert_allclose(bs[k, :1 + 8 * 16], orc.multinomialState(l, k, 0, 4), rtol=1e-9, atol=0)
+
+
+@pytest.mark.parametrize("L,rpp", [(5, 0), (3, 2)])
+def test_grid_engine_several_ladders_and_passes(L, rpp):
+    """The persistent grid kernel when a pass holds several whole ladders and the last pass is short (5 ladders x 4 rungs, 16
+    chains per pass: ladders 0-3, then ladder 4), and when a ladder spans two passes (3 ladders x 4 rungs, 2 chains per pass):
+    control state mirrored per pass / read from global memory, swap phase of every ladder after the last pass, proposals for a
+    different set of chains than the ones just finished.  Decisions bit for bit against the oracle, through an adaptation."""
+    spec = models.logistic(600, 4, 4, seed_off=9)
+    kw = dict(engine=2)
+    if rpp:
+        kw["rungsPerPass"] = rpp
+    niter = 230
+    eng, orc, recs = run_pair(spec, niter, L=L, inject=True, build_kw=kw)
+    assert_run_parity(eng, orc, recs, spec, "grid L=%d" % L, niter, L)
