@@ -11,7 +11,11 @@
 #include <math_constants.h>
 #include "../nimbleapt_b200/csrc/engine/apt_dists.cuh"
 using namespace apt;
-constexpr int P = 50, TB = 16, KB = 4, NBR = (P + KB - 1) / KB, XS = 36;  // XS: padded column stride of a ring block (doubles)
+constexpr int P = 50, TB = 16, KB = 4, NBR = (P + KB - 1) / KB;
+#ifndef RB
+#define RB 4  // row blocks of 8 rows per warp tile
+#endif
+constexpr int TRW = 8 * RB, XS = TRW + 4;  // XS: padded column stride of a ring block (doubles): LDS.64 of a fragment hits 16 distinct bank pairs
 
 __device__ __forceinline__ void cpa16(void* smem, const void* gmem) {
     const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -43,7 +47,7 @@ __global__ void __launch_bounds__(THREADS, MINB) pass_kernel(const double* __res
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < NBR * KB * TB; i += THREADS) thT[i] = (i < P * TB) ? th[i] : 0.0;
     double* xw = xbuf + warp * SLOTS * BLK;
-    const long ntile = n / 32, wstep = (long)gridDim.x * NW;
+    const long ntile = n / TRW, wstep = (long)gridDim.x * NW;
     long wt = (long)warp * gridDim.x + blockIdx.x;
     // B fragment of block b, n-tile t: B[k = lane % 4][col = lane / 4]; column col of n-tile t is position (col/2)*4 + t*2 + col%2
     const int kq = lane & 3, rq = lane >> 2;
@@ -59,17 +63,18 @@ __global__ void __launch_bounds__(THREADS, MINB) pass_kernel(const double* __res
         if (BULK) {
             if (lane == 0) {
                 const int nc = (b * KB + KB <= P) ? KB : P - b * KB;
-                mbar_expect(&bars[slot], (unsigned)nc * 256u);
-                for (int col = 0; col < nc; col++) bulk_g2s(&xw[slot * BLK + col * XS], X + tile * 32 + (long)(b * KB + col) * n, 256u, &bars[slot]);
+                mbar_expect(&bars[slot], (unsigned)nc * (unsigned)TRW * 8u);
+                for (int col = 0; col < nc; col++) bulk_g2s(&xw[slot * BLK + col * XS], X + tile * TRW + (long)(b * KB + col) * n, (unsigned)TRW * 8u, &bars[slot]);
             }
             return;
         }
         // block b = columns 4b .. 4b+3 of rows tile*32 .. +31: 4 x 16 chunks of 16 bytes, 2 per lane
-        const double* src = X + tile * 32;
+        const double* src = X + tile * TRW;
+        constexpr int CPC = TRW / 2;  // 16-byte chunks per column
 #pragma unroll
-        for (int j = 0; j < 2; j++) {
-            const int col = (lane >> 4) + 2 * j, q = lane & 15;
-            if (b * KB + col < P) cpa16(&xw[slot * BLK + col * XS + 2 * q], src + (long)(b * KB + col) * n + 2 * q);
+        for (int j = 0; j < (KB * CPC + 31) / 32; j++) {
+            const int c = lane + 32 * j, col = c / CPC, q = c % CPC;
+            if (c < KB * CPC && b * KB + col < P) cpa16(&xw[slot * BLK + col * XS + 2 * q], src + (long)(b * KB + col) * n + 2 * q);
         }
     };
     if (wt < ntile) {
@@ -87,9 +92,9 @@ __global__ void __launch_bounds__(THREADS, MINB) pass_kernel(const double* __res
     for (int c = 0; c < 4; c++) acc[c] = 0.0;
     int ring = 0;
     for (; wt < ntile; wt += wstep) {
-        double c[4][2][2];  // [row block][n-tile][2]
+        double c[RB][2][2];  // [row block][n-tile][2]
 #pragma unroll
-        for (int i = 0; i < 4; i++) { c[i][0][0] = c[i][0][1] = c[i][1][0] = c[i][1][1] = 0.0; }
+        for (int i = 0; i < RB; i++) { c[i][0][0] = c[i][0][1] = c[i][1][0] = c[i][1][1] = 0.0; }
         const long nxt = wt + wstep;
 #pragma unroll (BREG ? NBR : UNR)
         for (int b = 0; b < NBR; b++) {
@@ -109,7 +114,7 @@ __global__ void __launch_bounds__(THREADS, MINB) pass_kernel(const double* __res
             const double* xs = xw + ring * BLK + kq * XS + rq;
             const bool live = b * KB + kq < P;
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
+            for (int i = 0; i < RB; i++) {
                 double a = xs[8 * i];
                 if (b == NBR - 1) a = live ? a : 0.0;
                 dmma(c[i][0][0], c[i][0][1], a, b0);
@@ -119,16 +124,16 @@ __global__ void __launch_bounds__(THREADS, MINB) pass_kernel(const double* __res
         }
         // thread tile: rows rq + 8 i, chains (positions) 4 kq + {0, 1, 2, 3} = n-tile 0 cols 2kq, 2kq+1, n-tile 1 cols 2kq, 2kq+1
         if (MODE == 2) {
-            double yy[4], eta[4][4];
+            double yy[RB], eta[RB][4];
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
-                yy[i] = y[wt * 32 + rq + 8 * i];
+            for (int i = 0; i < RB; i++) {
+                yy[i] = y[wt * TRW + rq + 8 * i];
                 eta[i][0] = c[i][0][0]; eta[i][1] = c[i][0][1]; eta[i][2] = c[i][1][0]; eta[i][3] = c[i][1][1];
             }
-            bern_logit_tile<4, 4>(yy, eta, acc);
+            bern_logit_tile<RB, 4>(yy, eta, acc);
         } else {
 #pragma unroll
-            for (int i = 0; i < 4; i++) { acc[0] += c[i][0][0]; acc[1] += c[i][0][1]; acc[2] += c[i][1][0]; acc[3] += c[i][1][1]; }
+            for (int i = 0; i < RB; i++) { acc[0] += c[i][0][0]; acc[1] += c[i][0][1]; acc[2] += c[i][1][0]; acc[3] += c[i][1][1]; }
         }
     }
     if (!BULK) cpa_wait<0>();
@@ -206,6 +211,7 @@ int main() {
         cudaMemcpy(ref[mode / 2], refd, TB * 8, cudaMemcpyDeviceToHost);
     }
     // the reference sums positions as chains directly; pass_kernel's positions are the same columns of th
+#if RB == 4
     run<256, 2, true, 3, 0>("dot breg d3", X, y, th, n, partial, ref[0]);
     run<256, 2, false, 3, 0>("dot blds d3", X, y, th, n, partial, ref[0]);
     run<256, 2, true, 3, 2>("both breg d3", X, y, th, n, partial, ref[1]);
@@ -225,5 +231,18 @@ int main() {
     run<256, 2, false, 6, 2, 13, true>("both blds d6 unr13 BULK", X, y, th, n, partial, ref[1]);
     run<256, 2, false, 6, 0, 13, true>("dot blds d6 unr13 BULK", X, y, th, n, partial, ref[0]);
     run<256, 2, false, 6, 0, 13>("dot blds d6 unr13", X, y, th, n, partial, ref[0]);
+#elif RB == 8
+    run<256, 1, false, 6, 2, 13>("both d6 unr13 1x256", X, y, th, n, partial, ref[1]);
+    run<384, 1, false, 6, 2, 13>("both d6 unr13 1x384", X, y, th, n, partial, ref[1]);
+    run<512, 1, false, 4, 2, 13>("both d4 unr13 1x512", X, y, th, n, partial, ref[1]);
+    run<256, 2, false, 3, 2, 13>("both d3 unr13 2x256", X, y, th, n, partial, ref[1]);
+#else
+    run<256, 2, false, 6, 2, 13>("both d6 unr13 2x256", X, y, th, n, partial, ref[1]);
+    run<256, 3, false, 6, 2, 13>("both d6 unr13 3x256", X, y, th, n, partial, ref[1]);
+    run<256, 3, false, 8, 2, 13>("both d8 unr13 3x256", X, y, th, n, partial, ref[1]);
+    run<256, 4, false, 6, 2, 13>("both d6 unr13 4x256", X, y, th, n, partial, ref[1]);
+    run<128, 6, false, 6, 2, 13>("both d6 unr13 6x128", X, y, th, n, partial, ref[1]);
+    run<128, 8, false, 6, 2, 13>("both d6 unr13 8x128", X, y, th, n, partial, ref[1]);
+#endif
     return 0;
 }
