@@ -15,7 +15,7 @@ value     = tempered MH updates / s over all GPUs, device time (CUDA events on t
 e2e       = the same through the public API with HOST buffers: data + inits uploaded, run, mvSamples delivered to host
             memory of rank 0 (N = 1: copied back piece by piece while the run samples; N > 1: every rank's rows travel over
             NCCL to rank 0 piece by piece while the run samples, apt_run_args.gather), all inside the timed region; median
-            of 5 passes of K steps each (every pass listed in e2e.passes_s)
+            of 7 passes of K steps each after 3 untimed ones (every pass listed in e2e.passes_s)
 roofline  = dominant kernel of the timed region; for c2 the kernel is FP64-pipe bound, so the
             roofline is flop-based against the FP64 FMA peak measured live; roofline_c3 is the HBM one.
 --impl reference times the CPU oracle (restated reference, NOT nimble itself: R/nimble are absent).
@@ -315,7 +315,7 @@ def pinned_buffer(n):
     return torch.empty(max(int(n), 1), dtype=torch.float64, pin_memory=True).numpy()
 
 
-def measure(rk, workload, L, steps, warmup, thin, engine, reps=5, clock_index=None):
+def measure(rk, workload, L, steps, warmup, thin, engine, reps=7, clock_index=None):
     """Device-timed K steps, then end-to-end passes of K steps each through the public API with host buffers."""
     import nimbleapt_b200 as nb
     from nimbleapt_b200.workloads import build_engine, initial_values
@@ -353,7 +353,8 @@ def measure(rk, workload, L, steps, warmup, thin, engine, reps=5, clock_index=No
         t.append(time.perf_counter())
         return t
 
-    e2e_once()  # untimed pass of the same call sequence (first NCCL operations set up their channels, buffers reach their size)
+    for _ in range(3):  # untimed passes of the same call sequence (the first NCCL operations between every pair of ranks set up
+        e2e_once()      # their channels over several calls, buffers reach their size)
     passes, breakdown = [], []
     for _ in range(reps):
         rk.barrier()
