@@ -1439,6 +1439,21 @@ struct Lowerer {
                         int tmp;
                         cv_mode = true;
                         std::string pe2 = gen_slice_elem(ps, "(b_ * " + std::to_string(KB) + " + kq_)", e3, tmp);
+                        // A last block of only 1 or 2 columns would spend a whole DMMA step (16 pipe cycles per instruction) on
+                        // mostly zeros: those columns go through 4 x TBT plain FMAs per column instead (half the pipe time for 2
+                        // columns, a quarter for 1), on the same accumulators.
+                        const int remc = lp_ % KB;
+                        const bool rem_fma = (remc == 1 || remc == 2) && !getenv("APTB200_MMA_PAD");
+                        if (rem_fma) {
+                            std::string per = gen_slice_elem(ps, "(" + std::to_string((NBR - 1) * KB) + " + e_)", e3, tmp);
+                            out << "          if (b_ == " << NBR - 1 << ") {\n";
+                            out << "            _Pragma(\"unroll\") for (int e_ = 0; e_ < " << remc << "; ++e_) {\n";
+                            out << "              double xr_[R];\n";
+                            out << "              _Pragma(\"unroll\") for (int r_ = 0; r_ < R; ++r_) xr_[r_] = xw_[ring_pos * " << BLK << " + e_ * " << XS << " + rq_ + 8 * r_];\n";
+                            out << "              _Pragma(\"unroll\") for (int c_ = 0; c_ < TB; c_ += 2) { const double2 b2_ = *reinterpret_cast<const double2*>(&" << per << ");\n";
+                            out << "                _Pragma(\"unroll\") for (int r_ = 0; r_ < R; ++r_) { " << nm << "[r_][c_] = fma(xr_[r_], b2_.x, " << nm << "[r_][c_]); " << nm << "[r_][c_ + 1] = fma(xr_[r_], b2_.y, " << nm << "[r_][c_ + 1]); } }\n";
+                            out << "            }\n          } else {\n";
+                        } else out << "          {\n";
                         out << "          const bool live_ = b_ * " << KB << " + kq_ < " << lp_ << ";\n";
                         out << "          double bf_[" << NT << "];\n";
                         if (NT == 2) out << "          { const double2 f2_ = *reinterpret_cast<const double2*>(thF_ + b_ * 64); bf_[0] = f2_.x; bf_[1] = f2_.y; }\n";
@@ -1460,6 +1475,7 @@ struct Lowerer {
                         out << "            double a_ = xs_[8 * r_];\n";
                         if (lp_ % KB != 0) out << "            if (b_ == " << NBR - 1 << ") a_ = live_ ? a_ : 0.0;  // never multiply stale shared memory\n";
                         out << "            _Pragma(\"unroll\") for (int t_ = 0; t_ < " << NT << "; ++t_) apt::dmma884(" << nm << "[r_][2 * t_], " << nm << "[r_][2 * t_ + 1], a_, bf_[t_]);\n          }\n";
+                        out << "          }\n";
                     }
                     out << "          ring_pos = (ring_pos + 1 == " << TRS << ") ? 0 : ring_pos + 1;\n        }\n";
                     prime << "      if constexpr (GI == " << bi << ") {\n        const int lane_ = tid_ & 31;\n        double* xw_ = xbuf + (tid_ >> 5) * " << TRS * BLK << ";\n"
