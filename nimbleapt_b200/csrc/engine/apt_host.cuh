@@ -157,6 +157,7 @@ struct Engine {
                      (size_t)cap * G::NMON, (size_t)(r1 - r0) * G::NMON, L, cudaMemcpyDeviceToHost, copy_stream);
     }
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t evp[4] = {nullptr, nullptr, nullptr, nullptr};  // start / end of the two pieces in flight
     std::vector<DevBuf<double>> arrays;
     std::vector<DevBuf<int>> iarrays;
     Data D{};
@@ -287,6 +288,7 @@ struct Engine {
 
     ~Engine() {
         if (ev0) cudaEventDestroy(ev0);
+        for (auto e : evp) if (e) cudaEventDestroy(e);
         if (ev1) cudaEventDestroy(ev1);
         if (stream) cudaStreamDestroy(stream);
         if (copy_stream) cudaStreamDestroy(copy_stream);
@@ -440,11 +442,25 @@ struct Engine {
             long long chunk = ra->iters_per_launch > 0 ? ra->iters_per_launch : 4096;
             if (so_chunk > 0 && ra->iters_per_launch <= 0) chunk = std::min(chunk, so_chunk);
             const int grid = (L + SH::TEAMS - 1) / SH::TEAMS;
+            // Two pieces in flight: piece i + 1 is queued before the host waits for piece i, so the device never idles between
+            // two pieces (the host's wait + launch was ~15 us per piece: 10 % of a 1-ms run), and an interrupt is still noticed
+            // within two pieces.  The copy of a piece's rows waits for the piece's event on the second stream.
+            if (!evp[0]) for (auto& e : evp) APT_CUDA(cudaEventCreate(&e));
+            long long prev_it1 = -1;
+            int npiece = 0;
+            auto finish_piece = [&](int pi, long long it1p) {
+                APT_CUDA(cudaEventSynchronize(evp[2 * pi + 1]));
+                float ms = 0;
+                APT_CUDA(cudaEventElapsedTime(&ms, evp[2 * pi], evp[2 * pi + 1]));
+                timing.kernel_ms += ms; timing.main_kernel_ms += ms; timing.launches++; timing.main_launches++;
+                rows_after(it1p);
+            };
             for (long long it0 = 0; it0 < ra->niter; it0 += chunk) {
                 if (ra->should_abort && ra->should_abort(ra->abort_arg)) { aborted = true; break; }
                 a.it0 = it0; a.it1 = std::min<long long>(ra->niter, it0 + chunk);
                 a.rng_iter0 = rngIter; a.total_iters0 = totalIters;
-                APT_CUDA(cudaEventRecord(ev0, stream));
+                const int pi = npiece & 1;
+                APT_CUDA(cudaEventRecord(evp[2 * pi], stream));
                 if constexpr (G::CLUSTER > 1) {
                     cudaLaunchConfig_t cfg{};
                     cfg.gridDim = dim3((unsigned)(L * G::CLUSTER)); cfg.blockDim = dim3(SH::CTA);
@@ -457,16 +473,16 @@ struct Engine {
                 } else
                 ladder_kernel<G><<<grid, SH::CTA, SH::SM_BYTES, stream>>>(a);
                 APT_CUDA(cudaGetLastError());
-                APT_CUDA(cudaEventRecord(ev1, stream));
-                APT_CUDA(cudaEventSynchronize(ev1));
-                float ms = 0;
-                APT_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
-                timing.kernel_ms += ms; timing.main_kernel_ms += ms; timing.launches++; timing.main_launches++;
+                APT_CUDA(cudaEventRecord(evp[2 * pi + 1], stream));
                 rngIter += (uint64_t)(a.it1 - a.it0);
                 totalIters += (a.it1 - a.it0);
-                rows_after(a.it1);
+                if (so_ptr) APT_CUDA(cudaStreamWaitEvent(copy_stream, evp[2 * pi + 1], 0));
                 copy_rows_async(a.it0, a.it1);
+                if (prev_it1 >= 0) finish_piece(pi ^ 1, prev_it1);
+                prev_it1 = a.it1;
+                npiece++;
             }
+            if (prev_it1 >= 0) finish_piece((npiece - 1) & 1, prev_it1);
         }
         // APT:548: the model is left parameterised with the T=1 state
         model_from_rung1_kernel<G><<<std::min(L, 65535), 64, 0, stream>>>(L, theta.p, slot.p, model_theta.p);
