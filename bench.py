@@ -15,7 +15,7 @@ value     = tempered MH updates / s over all GPUs, device time (CUDA events on t
 e2e       = the same through the public API with HOST buffers: data + inits uploaded, run, mvSamples delivered to host
             memory of rank 0 (N = 1: copied back piece by piece while the run samples; N > 1: every rank's rows travel over
             NCCL to rank 0 piece by piece while the run samples, apt_run_args.gather), all inside the timed region; median
-            of 7 passes of K steps each after 3 untimed ones (every pass listed in e2e.passes_s)
+            of 7 passes of K steps each after 3 untimed ones (6 with N > 1; every pass listed in e2e.passes_s)
 roofline  = dominant kernel of the timed region; for c2 the kernel is FP64-pipe bound, so the
             roofline is flop-based against the FP64 FMA peak measured live; roofline_c3 is the HBM one.
 --impl reference times the CPU oracle (restated reference, NOT nimble itself: R/nimble are absent).
@@ -353,7 +353,7 @@ def measure(rk, workload, L, steps, warmup, thin, engine, reps=7, clock_index=No
         t.append(time.perf_counter())
         return t
 
-    for _ in range(3):  # untimed passes of the same call sequence (the first NCCL operations between every pair of ranks set up
+    for _ in range(3 if rk.dist is None else 6):  # untimed passes of the same call sequence (the first NCCL operations between every pair of ranks set up
         e2e_once()      # their channels over several calls, buffers reach their size)
     passes, breakdown = [], []
     for _ in range(reps):
