@@ -148,3 +148,25 @@ def test_demo_model_lowers_with_slice_sampler():
     assert os.path.exists(apt.modulePath)
     with pytest.raises(nb.AptError, match="grid engine: sampler_slice_tempered is not supported"):
         build_engine(models.demo_wrong(), compileOnly=True, engine=2)
+
+
+def test_concurrent_cold_builds_share_one_cache_entry(tmp_path):
+    """Several processes (8 ranks calling buildAPT at once) compile the same model into an empty cache whose path contains a
+    space: every one of them succeeds (sources, logs and modules are written under process-unique names and renamed into
+    place, shell arguments are quoted) and one module remains."""
+    import subprocess
+    import sys
+    cache = tmp_path / "jit cache"
+    cache.mkdir()
+    code = ("import sys; sys.path[:0] = [%r, %r]\n"
+            "import models\nfrom helpers import build_engine\n"
+            "apt = build_engine(models.c2_mixture(n=6, K=4, tmax=20.0), compileOnly=True)\nprint(apt.modulePath)\n") % (
+                os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, APTB200_CACHE=str(cache))
+    procs = [subprocess.Popen([sys.executable, "-c", code], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True) for _ in range(3)]
+    outs = [p.communicate(timeout=600) for p in procs]
+    assert all(p.returncode == 0 for p in procs), [o[1][-400:] for o in outs]
+    paths = {o[0].strip().splitlines()[-1] for o in outs}
+    assert len(paths) == 1 and os.path.exists(paths.pop())
+    left = sorted(os.listdir(cache))
+    assert [f for f in left if f.endswith(".so")] and not [f for f in left if ".tmp." in f], left
